@@ -1,0 +1,43 @@
+"""Shared case definitions for the controller-level parity tests (oracle vs reference build vs
+golden vectors vs CUDA engine)."""
+import numpy as np
+
+from assistedmanipulation_b200 import abi
+
+
+def assisted_params(energy=True, links=abi.LINKS_BODY_COM):
+    am = abi.default_assisted_manipulation()
+    am.enable_energy_limit = int(energy)
+    am.link_position_mode = links
+    return am
+
+
+def constant_wrench(T, force=(10.0, 0.0, 0.0)):
+    w = np.zeros((T, 6))
+    w[:, :3] = force
+    return w
+
+
+# name -> dict(system, objective, params(), K, horison, keep, threads, x0, updates, cadence, wrench, smoothing)
+REF_CASES = {
+    "toy_k100_nosmooth": dict(system=abi.SYSTEM_TOY, objective=abi.OBJECTIVE_TOY, params=abi.default_toy_objective, K=100,
+                              horison=1.0, keep=0, threads=1, x0=np.zeros(4), updates=6, cadence=0.05, wrench=None, smoothing=None),
+    "toy_k253_keep20": dict(system=abi.SYSTEM_TOY, objective=abi.OBJECTIVE_TOY, params=abi.default_toy_objective, K=253,
+                            horison=1.0, keep=20, threads=4, x0=np.array([0.1, -0.2, 0.3, 0.0]), updates=6, cadence=0.05,
+                            wrench=None, smoothing=(10, 1)),
+    "toy_k50_oddcadence": dict(system=abi.SYSTEM_TOY, objective=abi.OBJECTIVE_TOY, params=abi.default_toy_objective, K=50,
+                               horison=0.3, keep=20, threads=3, x0=np.zeros(4), updates=8, cadence=0.013, wrench=None,
+                               smoothing=(10, 1)),
+    "franka_trackpoint_k50": dict(system=abi.SYSTEM_FRANKA_RIDGEBACK, objective=abi.OBJECTIVE_TRACK_POINT,
+                                  params=abi.default_track_point, K=50, horison=0.3, keep=20, threads=4,
+                                  x0=abi.huddled_state(), updates=5, cadence=0.05, wrench=None, smoothing=(10, 1)),
+    "franka_assisted_k60": dict(system=abi.SYSTEM_FRANKA_RIDGEBACK, objective=abi.OBJECTIVE_ASSISTED_MANIPULATION,
+                                params=assisted_params, K=60, horison=0.3, keep=20, threads=4, x0=abi.huddled_state(10.0),
+                                updates=5, cadence=0.05, wrench=constant_wrench(30), smoothing=(10, 1)),
+}
+
+
+def config_for(case, **over):
+    kw = dict(keep_best=case["keep"], threads=case["threads"], smoothing=case["smoothing"])
+    kw.update(over)
+    return abi.make_config(case["system"], case["objective"], case["K"], case["horison"], **kw)
