@@ -1,0 +1,595 @@
+// Host side of the C ABI (include/mppi_b200.h): owns the device memory, the streams and the
+// per-update orchestration of mppi::Trajectory::update (reference src/controller/mppi.cpp:154-187).
+// Nothing here computes the path on the CPU: every stage is a kernel launch (kernels.cuh); the host
+// only evaluates the scalar bookkeeping the reference evaluates in double on its caller thread
+// (shift_by, mppi.cpp:194; the lerp readout, mppi.cpp:481-512).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mppi_b200.h"
+#include "kernels.cuh"
+#include "model_init.h"
+#include "params_convert.h"
+
+using namespace mppi_b200;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- NCCL, resolved at run time so the library loads on machines without it ---------------------
+struct Nccl {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string *why) {
+        if (handle) return true;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) { *why = std::string("cannot load libnccl: ") + dlerror(); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { *why = "libnccl lacks required symbols"; return false; }
+        return true;
+    }
+};
+Nccl g_nccl;
+std::mutex g_mutex;
+bool g_model_uploaded[64] = {false};
+
+// gram polynomial Savitzky–Golay weights (Gorry 1990): the taps of gram_sg::SavitzkyGolayFilter(m, t=0, n, s=0)
+double gram_poly(int i, int m, int k, int s) {
+    if (k > 0)
+        return (4. * k - 2.) / (k * (2. * m - k + 1.)) * (i * gram_poly(i, m, k - 1, s) + s * gram_poly(i, m, k - 1, s - 1)) -
+               ((k - 1.) * (2. * m + k)) / (k * (2. * m - k + 1.)) * gram_poly(i, m, k - 2, s);
+    return (k == 0 && s == 0) ? 1. : 0.;
+}
+double gen_fact(int a, int b) { double g = 1.; for (int j = a - b + 1; j <= a; j++) g *= j; return g; }
+std::vector<double> sg_weights(int m, int n) {
+    std::vector<double> w(2 * m + 1);
+    for (int i = -m; i <= m; i++) {
+        double s = 0;
+        for (int k = 0; k <= n; k++) s = s + (2 * k + 1) * (gen_fact(2 * m, k) / gen_fact(2 * m + k + 1, k + 1)) * gram_poly(i, m, k, 0) * gram_poly(0, m, k, 0);
+        w[i + m] = s;
+    }
+    return w;
+}
+
+// V * sqrt(Lambda) of the symmetric covariance, eigenvalues ascending (gaussian.hpp:48-55)
+std::vector<double> noise_transform(int n, const double *cov) {
+    std::vector<double> a(cov, cov + (size_t)n * n), V((size_t)n * n, 0.0), ev(n);
+    auto A = [&](int r, int c) -> double & { return a[(size_t)c * n + r]; };
+    auto E = [&](int r, int c) -> double & { return V[(size_t)c * n + r]; };
+    for (int i = 0; i < n; i++) E(i, i) = 1.0;
+    for (int sweep = 0; sweep < 64; sweep++) {
+        double off = 0.0;
+        for (int p = 0; p < n; p++) for (int q = p + 1; q < n; q++) off += A(p, q) * A(p, q);
+        if (off == 0.0) break;
+        for (int p = 0; p < n; p++)
+            for (int q = p + 1; q < n; q++) {
+                if (A(p, q) == 0.0) continue;
+                const double theta = (A(q, q) - A(p, p)) / (2.0 * A(p, q));
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; k++) { double x = A(k, p), y = A(k, q); A(k, p) = c * x - s * y; A(k, q) = s * x + c * y; }
+                for (int k = 0; k < n; k++) { double x = A(p, k), y = A(q, k); A(p, k) = c * x - s * y; A(q, k) = s * x + c * y; }
+                for (int k = 0; k < n; k++) { double x = E(k, p), y = E(k, q); E(k, p) = c * x - s * y; E(k, q) = s * x + c * y; }
+            }
+    }
+    for (int i = 0; i < n; i++) ev[i] = A(i, i);
+    for (int i = 0; i < n - 1; i++) {
+        int k = 0;
+        for (int j = 1; j < n - i; j++) if (ev[i + j] < ev[i + k]) k = j;
+        if (k > 0) { std::swap(ev[i], ev[i + k]); for (int r = 0; r < n; r++) std::swap(E(r, i), E(r, i + k)); }
+    }
+    std::vector<double> L((size_t)n * n);
+    for (int c = 0; c < n; c++) for (int r = 0; r < n; r++) L[(size_t)c * n + r] = E(r, c) * std::sqrt(ev[c] > 0 ? ev[c] : 0.0);
+    return L;
+}
+
+}  // namespace
+
+struct mppi_b200_engine {
+    mppi_b200_config cfg{};
+    DeviceState d{};
+    int variant = VAR_TOY;
+    bool faithful = false;
+    std::vector<unsigned char> params;  // objective block in kernel arithmetic
+    cudaStream_t stream = nullptr, side = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_main_done = nullptr, ev_side_done = nullptr;
+    bool side_pending = false;
+    // host mirrors (pinned)
+    unsigned char *h_frame = nullptr;  // Frame + wrench
+    double *h_U = nullptr;             // nu*T
+    double *h_stats = nullptr;         // minmax[3], argmin (as double bits), optimal cost, breakdown[8]
+    size_t frame_bytes = 0;
+    // device allocations
+    std::vector<void *> allocs;
+    unsigned char *d_frame = nullptr;
+    unsigned char *d_frame_snap = nullptr;
+    double *d_U_snap = nullptr;
+    void *d_zero_row = nullptr;
+    void *d_injected = nullptr;
+    size_t noise_elems = 0;
+    // reference bookkeeping
+    double last_shift_time = 0.0, last_rollout_time = 0.0, sg_last_trim = -1.0;
+    long long shift_by = 0, update_count = 0, launches = 0;
+    bool in_update = false;
+    std::vector<double> control_default;
+    bool has_default = false;
+    long long argmin = 0;
+    ncclComm_t comm = nullptr;
+    std::string error;
+    float last_ms = 0.f;
+};
+
+namespace {
+
+int fail_create(int code, const std::string &why) { g_create_error = why; return code; }
+int fail(mppi_b200_engine *e, int code, const std::string &why) { e->error = why; return code; }
+#define CUDA_TRY(e, call) do { cudaError_t _c = (call); if (_c != cudaSuccess) return fail((e), MPPI_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_c)); } while (0)
+
+template <class T> T *dev_alloc(mppi_b200_engine *e, size_t count, bool zero = true) {
+    void *p = nullptr;
+    if (cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    if (zero) cudaMemset(p, 0, std::max<size_t>(count, 1) * sizeof(T));
+    e->allocs.push_back(p);
+    return static_cast<T *>(p);
+}
+
+template <class R, class CP> void store_params(mppi_b200_engine *e, const CP &cp) {
+    auto P = convert<R>(cp);
+    e->params.resize(sizeof P);
+    std::memcpy(e->params.data(), &P, sizeof P);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mppi_b200_last_error(const mppi_b200_engine *engine) { return engine ? engine->error.c_str() : g_create_error.c_str(); }
+
+void mppi_b200_destroy(mppi_b200_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->side) cudaStreamSynchronize(e->side);
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    for (void *p : e->allocs) cudaFree(p);
+    if (e->h_frame) cudaFreeHost(e->h_frame);
+    if (e->h_U) cudaFreeHost(e->h_U);
+    if (e->h_stats) cudaFreeHost(e->h_stats);
+    for (cudaEvent_t ev : {e->ev_start, e->ev_end, e->ev_main_done, e->ev_side_done}) if (ev) cudaEventDestroy(ev);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->side) cudaStreamDestroy(e->side);
+    delete e;
+}
+
+int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, size_t objective_params_size, mppi_b200_engine **out) {
+    if (out) *out = nullptr;
+    if (!c || !out) return fail_create(MPPI_B200_ERR_INVALID, "null argument");
+    if (c->abi_version != MPPI_B200_ABI_VERSION) return fail_create(MPPI_B200_ERR_INVALID, "abi version mismatch");
+    // the (dynamics, cost) pair must be one a device binding exists for (no CPU fallback)
+    int nx = 0, nu = 0;
+    if (c->system == MPPI_B200_SYSTEM_TOY && c->objective == MPPI_B200_OBJECTIVE_TOY) { nx = 4; nu = 2; }
+    else if (c->system == MPPI_B200_SYSTEM_FRANKA_RIDGEBACK &&
+             (c->objective == MPPI_B200_OBJECTIVE_TRACK_POINT || c->objective == MPPI_B200_OBJECTIVE_ASSISTED_MANIPULATION)) { nx = 31; nu = 12; }
+    else return fail_create(MPPI_B200_ERR_UNSUPPORTED, "no device implementation for this (dynamics, cost) pair");
+    // mppi.cpp:18-69, same order, same messages
+    if (c->control_dof != nu) return fail_create(MPPI_B200_ERR_INVALID, "controller dynamics control dof " + std::to_string(c->control_dof) + " != cost control dof " + std::to_string(nu));
+    if (c->state_dof != nx) return fail_create(MPPI_B200_ERR_INVALID, "controller dynamics state dof " + std::to_string(c->state_dof) + " != cost state dof " + std::to_string(nx));
+    if (c->control_limits_size != nu || !c->control_min || !c->control_max) return fail_create(MPPI_B200_ERR_INVALID, "controller maximum and minimum must have length " + std::to_string(nu));
+    if (c->covariance_rows != c->covariance_cols || !c->covariance) return fail_create(MPPI_B200_ERR_INVALID, "controller covariance matrix not square");
+    if (c->covariance_rows != nu) return fail_create(MPPI_B200_ERR_INVALID, "controller sample variance dof " + std::to_string(c->covariance_rows) + " != dynamics and cost control dof " + std::to_string(nu));
+    if (c->rollouts < 1) return fail_create(MPPI_B200_ERR_INVALID, "trajectory rollouts must be greater than zero");
+    if (c->keep_best_rollouts < 0) return fail_create(MPPI_B200_ERR_INVALID, "trajectory cached rollouts cannot be less than zero");
+    if (c->threads <= 0) return fail_create(MPPI_B200_ERR_INVALID, "trajectory threads must be positive nonzero");
+    if (c->precision != MPPI_B200_FP64 && c->precision != MPPI_B200_FP32) return fail_create(MPPI_B200_ERR_INVALID, "precision");
+    if (c->world_size < 1 || c->rank < 0 || c->rank >= c->world_size) return fail_create(MPPI_B200_ERR_INVALID, "rank / world_size");
+    if (c->world_size > 1 && c->keep_best_rollouts > 0) return fail_create(MPPI_B200_ERR_UNSUPPORTED, "keep_best_rollouts > 0 is not available for a sharded rollout set yet");
+    if (!(c->time_step > 0) || !(c->horison > 0)) return fail_create(MPPI_B200_ERR_INVALID, "time_step and horison must be positive");
+    if (c->smoothing && c->smoothing_window > (unsigned)MAX_WINDOW) return fail_create(MPPI_B200_ERR_UNSUPPORTED, "smoothing window too large");
+    const int T = (int)std::ceil(c->horison / c->time_step);  // mppi.cpp:85
+    const int vec = c->precision == MPPI_B200_FP64 ? 2 : 4;
+    if ((nu * T) % vec != 0) return fail_create(MPPI_B200_ERR_UNSUPPORTED, "control_dof * steps must be a multiple of " + std::to_string(vec));
+    if (c->system == MPPI_B200_SYSTEM_FRANKA_RIDGEBACK) { std::string why; if (!topology_matches(&why)) return fail_create(MPPI_B200_ERR_INVALID, "robot model: " + why); }
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail_create(MPPI_B200_ERR_CUDA, "no CUDA device (this engine has no CPU fallback)");
+    if (c->device < 0 || c->device >= ndev) return fail_create(MPPI_B200_ERR_INVALID, "device ordinal");
+
+    auto *e = new mppi_b200_engine();
+    e->cfg = *c;
+    e->cfg.covariance = nullptr; e->cfg.control_min = nullptr; e->cfg.control_max = nullptr; e->cfg.control_default = nullptr;
+    e->faithful = c->dynamics_mode == MPPI_B200_DYNAMICS_FAITHFUL;
+    if (c->control_default) { e->has_default = true; e->control_default.assign(c->control_default, c->control_default + nu); }
+    auto bail = [&](int code, const std::string &why) { mppi_b200_destroy(e); return fail_create(code, why); };
+#define CREATE_TRY(call) do { cudaError_t _c = (call); if (_c != cudaSuccess) return bail(MPPI_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_c)); } while (0)
+    CREATE_TRY(cudaSetDevice(c->device));
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        if (!g_model_uploaded[c->device]) { CREATE_TRY(upload_robot_model()); g_model_uploaded[c->device] = true; }
+    }
+    // objective parameters in kernel arithmetic
+    const bool f64 = c->precision == MPPI_B200_FP64;
+    if (c->objective == MPPI_B200_OBJECTIVE_TOY) {
+        if (objective_params_size != sizeof(mppi_b200_toy_objective) || !objective_params) return bail(MPPI_B200_ERR_INVALID, "objective parameter block size");
+        const auto &p = *static_cast<const mppi_b200_toy_objective *>(objective_params);
+        e->variant = VAR_TOY;
+        if (f64) store_params<double>(e, p); else store_params<float>(e, p);
+    } else if (c->objective == MPPI_B200_OBJECTIVE_TRACK_POINT) {
+        if (objective_params_size != sizeof(mppi_b200_track_point) || !objective_params) return bail(MPPI_B200_ERR_INVALID, "objective parameter block size");
+        const auto &p = *static_cast<const mppi_b200_track_point *>(objective_params);
+        e->variant = variant_for(p);
+        if (f64) store_params<double>(e, p); else store_params<float>(e, p);
+    } else {
+        if (objective_params_size != sizeof(mppi_b200_assisted_manipulation) || !objective_params) return bail(MPPI_B200_ERR_INVALID, "objective parameter block size");
+        const auto &p = *static_cast<const mppi_b200_assisted_manipulation *>(objective_params);
+        e->variant = variant_for(p);
+        if (f64) store_params<double>(e, p); else store_params<float>(e, p);
+    }
+
+    DeviceState &d = e->d;
+    d.nu = nu; d.nx = nx; d.T = T;
+    d.K_total = c->rollouts + 2;
+    // contiguous shards in global index order
+    d.k_begin = d.K_total * c->rank / c->world_size;
+    d.k_count = d.K_total * (c->rank + 1) / c->world_size - d.k_begin;
+    d.keep_best = std::min<long long>(c->keep_best_rollouts, c->rollouts);
+    d.dt = c->time_step; d.gradient_step = c->gradient_step; d.cost_scale = c->cost_scale; d.discount = c->cost_discount_factor;
+    d.bound = c->control_bound;
+    for (int i = 0; i < nu; i++) { d.cmin[i] = c->control_min[i]; d.cmax[i] = c->control_max[i]; }
+    const size_t n = (size_t)nu * T, esz = f64 ? 8 : 4;
+    e->noise_elems = (size_t)d.k_count * n;
+    e->frame_bytes = sizeof(Frame) + sizeof(double) * 6 * T;
+
+    CREATE_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+    for (cudaEvent_t *ev : {&e->ev_start, &e->ev_end}) CREATE_TRY(cudaEventCreate(ev));
+    for (cudaEvent_t *ev : {&e->ev_main_done, &e->ev_side_done}) CREATE_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    CREATE_TRY(cudaMallocHost(&e->h_frame, e->frame_bytes));
+    CREATE_TRY(cudaMallocHost(&e->h_U, n * sizeof(double)));
+    CREATE_TRY(cudaMallocHost(&e->h_stats, 16 * sizeof(double)));
+    std::memset(e->h_frame, 0, e->frame_bytes);
+    std::memset(e->h_U, 0, n * sizeof(double));
+    std::memset(e->h_stats, 0, 16 * sizeof(double));
+
+    bool ok = true;
+    auto A = [&](auto *&ptr, size_t count) { using P = std::remove_reference_t<decltype(*ptr)>; ptr = dev_alloc<P>(e, count); ok = ok && ptr; };
+    e->d_frame = dev_alloc<unsigned char>(e, e->frame_bytes); ok = ok && e->d_frame;
+    e->d_frame_snap = dev_alloc<unsigned char>(e, e->frame_bytes); ok = ok && e->d_frame_snap;
+    e->d_U_snap = dev_alloc<double>(e, n); ok = ok && e->d_U_snap;
+    e->d_zero_row = dev_alloc<unsigned char>(e, n * esz); ok = ok && e->d_zero_row;
+    d.frame = reinterpret_cast<const Frame *>(e->d_frame);
+    d.wrench = reinterpret_cast<const double *>(e->d_frame + sizeof(Frame));
+    A(d.U, n); A(d.U_shift, n); A(d.costs, (size_t)d.k_count); A(d.weights, (size_t)d.k_count);
+    A(d.kept, (size_t)d.k_count); A(d.kept_list, (size_t)std::max<long long>(d.keep_best, 1));
+    A(d.minmax_enc, 2); A(d.valid_count, 1); A(d.argmin, 1); A(d.minmax, 4); A(d.sums, 1 + n);
+    d.weight_blocks = (int)((d.k_count + 255) / 256);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    d.grad_blocks = (int)std::min<long long>(d.k_count, 2LL * sms);
+    A(d.wsum_partial, (size_t)d.weight_blocks); A(d.grad_partial, (size_t)d.grad_blocks * n);
+    A(d.gradient, n); A(d.skip, 1); A(d.L, (size_t)nu * nu); A(d.optimal_cost, 1); A(d.breakdown, 8);
+    d.noise = dev_alloc<unsigned char>(e, e->noise_elems * esz); ok = ok && d.noise;
+    d.injected = nullptr; d.injected_is_double = 0;
+    d.sg_enabled = c->smoothing ? 1 : 0;
+    d.sg_window = (int)c->smoothing_window;
+    d.sg_len = T + 2 * d.sg_window + 1;
+    A(d.sg_uu, (size_t)nu * d.sg_len); A(d.sg_tt, (size_t)nu * d.sg_len); A(d.sg_weights, (size_t)2 * d.sg_window + 1); A(d.sg_started, 1);
+    if (!ok) return bail(MPPI_B200_ERR_CUDA, "device allocation failed");
+
+    const std::vector<double> L = noise_transform(nu, c->covariance);
+    CREATE_TRY(cudaMemcpy(d.L, L.data(), L.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (c->smoothing) {
+        const std::vector<double> w = sg_weights(d.sg_window, (int)c->smoothing_order);
+        CREATE_TRY(cudaMemcpy(d.sg_weights, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
+        std::vector<double> tt((size_t)nu * d.sg_len, -1.0);  // filter.cpp:30-32: times start at -1
+        CREATE_TRY(cudaMemcpy(d.sg_tt, tt.data(), tt.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    CREATE_TRY(cudaDeviceSynchronize());
+#undef CREATE_TRY
+    *out = e;
+    g_create_error.clear();
+    return MPPI_B200_OK;
+}
+
+int mppi_b200_update_begin(mppi_b200_engine *e, const double *state, double time, const double *wrench, const void *noise, int32_t noise_source, uint64_t seed) {
+    if (!e || !state) return MPPI_B200_ERR_INVALID;
+    DeviceState &d = e->d;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    if (noise_source != MPPI_B200_NOISE_PHILOX && !noise) return fail(e, MPPI_B200_ERR_INVALID, "noise buffer missing");
+    // mppi.cpp:194-201, evaluated in double on the host exactly as written
+    const long long shift_by = (long long)((time - e->last_shift_time) / d.dt);
+    if (shift_by > d.T) return fail(e, MPPI_B200_ERR_INVALID, "time advanced by more than the horizon (the reference indexes out of range here)");
+    if (d.sg_enabled && time < e->sg_last_trim) return fail(e, MPPI_B200_ERR_TIME, "Resetting the window back in the past. Can reset only to larger times than last reset!!!");
+    if (shift_by > 0) e->last_shift_time = time;
+    e->shift_by = shift_by;
+
+    // the previous update's pinned frame must have been consumed: the stream was synchronised in finish
+    Frame *f = reinterpret_cast<Frame *>(e->h_frame);
+    std::memset(f->x0, 0, sizeof f->x0);
+    std::memcpy(f->x0, state, sizeof(double) * d.nx);
+    f->time = time; f->sg_prev_trim = 0.0; f->shift_by = shift_by; f->seed = seed;
+    f->update_index = (unsigned long long)e->update_count;
+    f->has_wrench = wrench != nullptr; f->noise_source = noise_source;
+    if (wrench) std::memcpy(e->h_frame + sizeof(Frame), wrench, sizeof(double) * 6 * d.T);
+
+    CUDA_TRY(e, cudaEventRecord(e->ev_start, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_frame, e->h_frame, e->frame_bytes, cudaMemcpyHostToDevice, e->stream));
+    const int prec = e->cfg.precision;
+    if (noise_source == MPPI_B200_NOISE_HOST) {
+        if (!e->d_injected) { e->d_injected = dev_alloc<double>(e, e->noise_elems, false); if (!e->d_injected) return fail(e, MPPI_B200_ERR_CUDA, "device allocation failed"); }
+        // host layout [(K+2)][T][nu] doubles; this engine takes its own shard
+        const double *src = static_cast<const double *>(noise) + (size_t)d.k_begin * d.nu * d.T;
+        CUDA_TRY(e, cudaMemcpyAsync(e->d_injected, src, e->noise_elems * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        d.injected = e->d_injected; d.injected_is_double = 1;
+    } else if (noise_source == MPPI_B200_NOISE_DEVICE) {
+        d.injected = noise; d.injected_is_double = 0;  // engine precision, local shard
+    } else {
+        d.injected = nullptr; d.injected_is_double = 0;
+    }
+    int launches = 0;
+    if (d.keep_best > 0) { CUDA_TRY(e, launch_select_kept(d, e->stream)); launches++; }
+    CUDA_TRY(e, launch_prepare(d, prec, e->stream)); launches++;
+    CUDA_TRY(e, launch_sample(d, prec, e->stream, &launches));
+    CUDA_TRY(e, launch_rollout(d, prec, e->variant, e->faithful, e->params.data(), false, e->stream)); launches++;
+    CUDA_TRY(e, launch_minmax_publish(d, e->stream)); launches++;
+    e->launches += launches;
+    e->in_update = true;
+    return MPPI_B200_OK;
+}
+
+int mppi_b200_update_weights(mppi_b200_engine *e) {
+    if (!e || !e->in_update) return MPPI_B200_ERR_INVALID;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    int launches = 1;
+    CUDA_TRY(e, launch_weights(e->d, e->stream));
+    CUDA_TRY(e, launch_gradient(e->d, e->cfg.precision, e->stream, &launches));
+    e->launches += launches;
+    return MPPI_B200_OK;
+}
+
+int mppi_b200_update_finish(mppi_b200_engine *e) {
+    if (!e || !e->in_update) return MPPI_B200_ERR_INVALID;
+    DeviceState &d = e->d;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    const size_t n = (size_t)d.nu * d.T;
+    CUDA_TRY(e, launch_finish(d, e->stream));
+    e->launches += 1;
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_U, d.U, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_stats, d.minmax, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 4, d.argmin, sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaEventRecord(e->ev_end, e->stream));
+    // Optimal re-rollout (Trajectory::filter, mppi.cpp:450-479) off the critical path: with no
+    // mppi::Filter attached (actor.cpp:100) it only produces the optimal cost and its per-term
+    // breakdown, so it runs on a side stream over a snapshot of this update's inputs.
+    if (e->side_pending) CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_side_done, 0));
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_frame_snap, e->d_frame, e->frame_bytes, cudaMemcpyDeviceToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_U_snap, d.U_shift, n * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+    CUDA_TRY(e, cudaEventRecord(e->ev_main_done, e->stream));
+    CUDA_TRY(e, cudaStreamWaitEvent(e->side, e->ev_main_done, 0));
+    {
+        DeviceState o = d;
+        o.frame = reinterpret_cast<const Frame *>(e->d_frame_snap);
+        o.wrench = reinterpret_cast<const double *>(e->d_frame_snap + sizeof(Frame));
+        o.U_shift = e->d_U_snap;
+        o.noise = e->d_zero_row;
+        CUDA_TRY(e, launch_rollout(o, e->cfg.precision, e->variant, e->faithful, e->params.data(), true, e->side));
+        e->launches += 1;
+        CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 5, d.optimal_cost, sizeof(double), cudaMemcpyDeviceToHost, e->side));
+        CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 6, d.breakdown, 8 * sizeof(double), cudaMemcpyDeviceToHost, e->side));
+        CUDA_TRY(e, cudaEventRecord(e->ev_side_done, e->side));
+        e->side_pending = true;
+    }
+    CUDA_TRY(e, cudaEventSynchronize(e->ev_end));
+    cudaEventElapsedTime(&e->last_ms, e->ev_start, e->ev_end);
+    e->in_update = false;
+    // mppi.cpp:368-370: no (or a single) valid rollout is an error; nothing is published
+    if (!(e->h_stats[2] >= 2.0)) {
+        return fail(e, MPPI_B200_ERR_ALL_NAN, "all nan rollouts");
+    }
+    std::memcpy(&e->argmin, e->h_stats + 4, sizeof(long long));
+    if (d.sg_enabled && !(e->h_stats[1] + e->h_stats[0] < 1e-6)) e->sg_last_trim = reinterpret_cast<Frame *>(e->h_frame)->time;
+    e->last_rollout_time = reinterpret_cast<Frame *>(e->h_frame)->time;
+    e->update_count++;
+    return MPPI_B200_OK;
+}
+
+int mppi_b200_update(mppi_b200_engine *e, const double *state, double time, const double *wrench, const void *noise, int32_t noise_source, uint64_t seed) {
+    int rc = mppi_b200_update_begin(e, state, time, wrench, noise, noise_source, seed);
+    if (rc) return rc;
+    if (e->comm) {
+        ncclResult_t r = g_nccl.AllReduce(e->d.minmax, e->d.minmax, 3, ncclDouble, ncclMax, e->comm, e->stream);
+        if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-reduce failed");
+    }
+    rc = mppi_b200_update_weights(e);
+    if (rc) return rc;
+    if (e->comm) {
+        ncclResult_t r = g_nccl.AllReduce(e->d.sums, e->d.sums, 1 + (size_t)e->d.nu * e->d.T, ncclDouble, ncclSum, e->comm, e->stream);
+        if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-reduce failed");
+    }
+    return mppi_b200_update_finish(e);
+}
+
+int mppi_b200_reduce_buffers(mppi_b200_engine *e, void **minmax, size_t *minmax_count, void **sums, size_t *sums_count) {
+    if (!e) return MPPI_B200_ERR_INVALID;
+    if (minmax) *minmax = e->d.minmax;
+    if (minmax_count) *minmax_count = 3;
+    if (sums) *sums = e->d.sums;
+    if (sums_count) *sums_count = 1 + (size_t)e->d.nu * e->d.T;
+    return MPPI_B200_OK;
+}
+
+int mppi_b200_stream(mppi_b200_engine *e, void **cuda_stream) {
+    if (!e || !cuda_stream) return MPPI_B200_ERR_INVALID;
+    *cuda_stream = e->stream;
+    return MPPI_B200_OK;
+}
+
+int mppi_b200_synchronize(mppi_b200_engine *e) {
+    if (!e) return MPPI_B200_ERR_INVALID;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->side));
+    return MPPI_B200_OK;
+}
+
+int mppi_b200_comm_unique_id(void *id128) {
+    std::string why;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_nccl.load(&why)) { g_create_error = why; return MPPI_B200_ERR_NCCL; }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return MPPI_B200_ERR_NCCL; }
+    std::memcpy(id128, &id, 128);
+    return MPPI_B200_OK;
+}
+
+int mppi_b200_comm_init(mppi_b200_engine *e, const void *id128) {
+    if (!e || !id128) return MPPI_B200_ERR_INVALID;
+    std::string why;
+    { std::lock_guard<std::mutex> lock(g_mutex); if (!g_nccl.load(&why)) return fail(e, MPPI_B200_ERR_NCCL, why); }
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&e->comm, e->cfg.world_size, id, e->cfg.rank);
+    if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclCommInitRank failed");
+    return MPPI_B200_OK;
+}
+
+// mppi.cpp:481-512
+int mppi_b200_get(mppi_b200_engine *e, double *control, double time) {
+    if (!e || !control) return MPPI_B200_ERR_INVALID;
+    const int nu = e->d.nu, T = e->d.T;
+    if (time < e->last_rollout_time) return fail(e, MPPI_B200_ERR_INVALID, "time >= m_last_rollout_time (assert, mppi.cpp:483)");
+    double t = (time - e->last_rollout_time) / e->d.dt;
+    const int lower = (int)t, upper = lower + 1;
+    if (upper >= T) {
+        for (int i = 0; i < nu; i++) control[i] = e->has_default ? e->control_default[i] : e->h_U[(size_t)(T - 1) * nu + i];
+        return MPPI_B200_OK;
+    }
+    t -= lower;
+    for (int i = 0; i < nu; i++) control[i] = (1.0 - t) * e->h_U[(size_t)lower * nu + i] + t * e->h_U[(size_t)upper * nu + i];
+    return MPPI_B200_OK;
+}
+
+int mppi_b200_read(mppi_b200_engine *e, int32_t what, void *dst, size_t bytes) {
+    if (!e || !dst) return MPPI_B200_ERR_INVALID;
+    DeviceState &d = e->d;
+    int rc = mppi_b200_synchronize(e);
+    if (rc) return rc;
+    const size_t n = (size_t)d.nu * d.T, K = (size_t)d.k_count;
+    auto need = [&](size_t b) { return bytes == b; };
+    switch (what) {
+        case MPPI_B200_READ_OPTIMAL: if (!need(n * 8)) break; std::memcpy(dst, e->h_U, bytes); return MPPI_B200_OK;
+        case MPPI_B200_READ_COSTS: if (!need(K * 8)) break; CUDA_TRY(e, cudaMemcpy(dst, d.costs, bytes, cudaMemcpyDeviceToHost)); return MPPI_B200_OK;
+        case MPPI_B200_READ_WEIGHTS: if (!need(K * 8)) break; CUDA_TRY(e, cudaMemcpy(dst, d.weights, bytes, cudaMemcpyDeviceToHost)); return MPPI_B200_OK;
+        case MPPI_B200_READ_GRADIENT: if (!need(n * 8)) break; CUDA_TRY(e, cudaMemcpy(dst, d.gradient, bytes, cudaMemcpyDeviceToHost)); return MPPI_B200_OK;
+        case MPPI_B200_READ_NOISE: {
+            if (!need(K * n * 8)) break;
+            if (e->cfg.precision == MPPI_B200_FP64) { CUDA_TRY(e, cudaMemcpy(dst, d.noise, bytes, cudaMemcpyDeviceToHost)); return MPPI_B200_OK; }
+            std::vector<float> tmp(K * n);
+            CUDA_TRY(e, cudaMemcpy(tmp.data(), d.noise, tmp.size() * 4, cudaMemcpyDeviceToHost));
+            double *o = static_cast<double *>(dst);
+            for (size_t i = 0; i < tmp.size(); i++) o[i] = (double)tmp[i];
+            return MPPI_B200_OK;
+        }
+        case MPPI_B200_READ_MINMAX: if (!need(16)) break; static_cast<double *>(dst)[0] = -e->h_stats[0]; static_cast<double *>(dst)[1] = e->h_stats[1]; return MPPI_B200_OK;
+        case MPPI_B200_READ_OPTIMAL_COST: if (!need(8)) break; static_cast<double *>(dst)[0] = e->h_stats[5]; return MPPI_B200_OK;
+        case MPPI_B200_READ_BREAKDOWN: if (!need(64)) break; std::memcpy(dst, e->h_stats + 6, 64); return MPPI_B200_OK;
+        case MPPI_B200_READ_KEPT: {
+            const size_t k = bytes / 8;
+            if (bytes % 8 || k > (size_t)d.keep_best) break;
+            CUDA_TRY(e, cudaMemcpy(dst, d.kept_list, bytes, cudaMemcpyDeviceToHost));
+            return MPPI_B200_OK;
+        }
+    }
+    return fail(e, MPPI_B200_ERR_INVALID, "read: unknown item or wrong size");
+}
+
+int mppi_b200_query(mppi_b200_engine *e, int32_t what, int64_t *value) {
+    if (!e || !value) return MPPI_B200_ERR_INVALID;
+    switch (what) {
+        case MPPI_B200_QUERY_STEP_COUNT: *value = e->d.T; return 0;
+        case MPPI_B200_QUERY_ROLLOUT_COUNT: *value = e->d.K_total; return 0;
+        case MPPI_B200_QUERY_LOCAL_BEGIN: *value = e->d.k_begin; return 0;
+        case MPPI_B200_QUERY_LOCAL_COUNT: *value = e->d.k_count; return 0;
+        case MPPI_B200_QUERY_UPDATE_COUNT: *value = e->update_count; return 0;
+        case MPPI_B200_QUERY_KERNEL_LAUNCHES: *value = e->launches; return 0;
+        case MPPI_B200_QUERY_ARGMIN: *value = e->argmin; return 0;
+        case MPPI_B200_QUERY_SHIFT_BY: *value = e->shift_by; return 0;
+        case MPPI_B200_QUERY_STATE_DOF: *value = e->d.nx; return 0;
+        case MPPI_B200_QUERY_CONTROL_DOF: *value = e->d.nu; return 0;
+    }
+    return MPPI_B200_ERR_INVALID;
+}
+
+int mppi_b200_last_update_device_seconds(mppi_b200_engine *e, double *seconds) {
+    if (!e || !seconds) return MPPI_B200_ERR_INVALID;
+    *seconds = (double)e->last_ms * 1e-3;
+    return MPPI_B200_OK;
+}
+
+static mppi_b200_barrier B(double b, double s) { mppi_b200_barrier r; r.bound = b; r.scale = s; r.maximum_cost = 1e10; return r; }
+static mppi_b200_quadratic Q(double c0, double c1, double c2) { mppi_b200_quadratic r; r.constant_cost = c0; r.linear_cost = c1; r.quadratic_cost = c2; return r; }
+static const double ARM_LOWER[12] = {-2.0, -2.0, -6.28, -2.8, -1.745, -2.8, -3.0718, -2.7925, 0.349, -2.967, 0.0, 0.0};
+static const double ARM_UPPER[12] = {2.0, 2.0, 6.28, 2.8, 1.745, 2.8, 0.0, 2.7925, 4.53785, 2.967, 0.5, 0.5};
+
+void mppi_b200_default_toy_objective(mppi_b200_toy_objective *o) {
+    o->target[0] = 1.0; o->target[1] = 1.0; o->position_cost = 100.0; o->velocity_cost = 1.0; o->control_cost = 0.01;
+}
+
+// track_point.hpp:77-114
+void mppi_b200_default_track_point(mppi_b200_track_point *o) {
+    std::memset(o, 0, sizeof *o);
+    o->point[0] = o->point[1] = o->point[2] = 1.0;
+    o->enable_joint_limits = 1;
+    static const double lo_s[12] = {1.0, 0.0, 0.0, 10.0, 50.0, 10.0, 10.0, 10.0, 10.0, 10.0, 10.0, 10.0};
+    static const double hi_s[12] = {0.0, 0.0, 0.0, 10.0, 50.0, 10.0, 10.0, 10.0, 10.0, 10.0, 10.0, 10.0};
+    for (int i = 0; i < 12; i++) { o->lower_joint_limit[i] = B(ARM_LOWER[i], lo_s[i]); o->upper_joint_limit[i] = B(ARM_UPPER[i], hi_s[i]); }
+    o->self_collision_limit = B(0.0, 1.0);
+    o->self_collision_radii[0] = 0.75;
+    for (int i = 1; i < 8; i++) o->self_collision_radii[i] = 0.1;
+    o->maximum_reach_limit = B(0.8, 1.0);
+    o->link_position_mode = MPPI_B200_LINKS_ZERO;
+}
+
+// assisted_manipulation.hpp:133-206
+void mppi_b200_default_assisted_manipulation(mppi_b200_assisted_manipulation *o) {
+    std::memset(o, 0, sizeof *o);
+    o->enable_joint_limit = o->enable_self_collision_limit = o->enable_workspace_limit = 1;
+    o->enable_energy_limit = 0;
+    o->enable_velocity_cost = o->enable_trajectory_cost = o->enable_manipulability_cost = 1;
+    o->link_position_mode = MPPI_B200_LINKS_ZERO;
+    static const double s[12] = {0.0, 0.0, 0.0, 10.0, 10.0, 10.0, 10.0, 10.0, 10.0, 10.0, 0.0, 0.0};
+    static const double vq[12] = {1000.0, 1000.0, 100.0, 0.5, 1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 0.0, 0.0};
+    for (int i = 0; i < 12; i++) { o->lower_joint_limit[i] = B(ARM_LOWER[i], s[i]); o->upper_joint_limit[i] = B(ARM_UPPER[i], s[i]); o->velocity_cost[i] = Q(0, 0, vq[i]); }
+    o->self_collision_limit = B(0.0, 1.0);
+    o->self_collision_radii[0] = 0.75;
+    for (int i = 1; i < 8; i++) o->self_collision_radii[i] = 0.1;
+    o->workspace_limit_above = B(0.0, 1.0); o->workspace_limit_infront = B(0.0, 1.0); o->workspace_limit_reach = B(1.0, 1.0);
+    o->workspace_cost_yaw = Q(0, 0, 400.0);
+    o->energy_limit_below = B(0.0, 10.0); o->energy_limit_above = B(20.0, 10.0);
+    o->trajectory_target_scale = 1e-2; o->trajectory_target_maximum = 1.0;
+    o->trajectory_position_cost = Q(100.0, 0, 500.0); o->trajectory_position_threshold = 0.0;
+    o->trajectory_velocity_cost = Q(0, 0, 500.0);
+    o->trajectory_velocity_minimum = 0.1; o->trajectory_velocity_maximum = 5.0; o->trajectory_velocity_dropoff = 2.0;
+    o->manipulability_cost = Q(0, 0, 10.0);
+}
+
+}  // extern "C"

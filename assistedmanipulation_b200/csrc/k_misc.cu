@@ -1,0 +1,469 @@
+// K1 sample, K3 reduce/weights, K4 weighted sum, K5 finish — everything of
+// mppi::Trajectory::sample / optimise (reference src/controller/mppi.cpp:189-270, 344-448) and the
+// Savitzky–Golay window (src/controller/filter.cpp:19-173) that is not the rollout itself.
+#include <math_constants.h>
+
+#include <algorithm>
+
+#include "kernels.cuh"
+
+namespace mppi_b200 {
+
+cudaError_t upload_robot_model_f64();
+cudaError_t upload_robot_model_f32();
+cudaError_t upload_robot_model() {
+    cudaError_t e = upload_robot_model_f64();
+    if (e != cudaSuccess) return e;
+    return upload_robot_model_f32();
+}
+
+__device__ __forceinline__ unsigned long long encode_ordered(double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double decode_ordered(unsigned long long e) {
+    unsigned long long b = (e & 0x8000000000000000ull) ? (e & 0x7fffffffffffffffull) : ~e;
+    return __longlong_as_double((long long)b);
+}
+cudaError_t launch_rollout_f64(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s);
+cudaError_t launch_rollout_f32(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s);
+
+// ---- Philox4x32-10 (Salmon et al. 2011), key = seed, counter = (column lo, column hi, block, update) --
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+// two uniforms -> two standard normals (Box–Muller, single precision arithmetic; noise only needs
+// to be N(0,1) and reproducible, and the exact values are read back for any parity check)
+__device__ __forceinline__ void box_muller(unsigned a, unsigned b, float *z0, float *z1) {
+    const float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;  // (0,1]
+    const float u2 = ((float)b + 0.5f) * 2.3283064365386963e-10f;
+    const float r = sqrtf(-2.0f * __logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    *z0 = r * c; *z1 = r * s;
+}
+
+// ---- prepare: time shift of the optimal control, rollout 1 = -U_prev, reset of the reductions -------
+// mppi.cpp:194-206 (shift), :269 (rollout[1].noise = -m_optimal_control, the UNSHIFTED optimum).
+template <class R> __global__ void k_prepare(const __grid_constant__ DeviceState d) {
+    const int n = d.nu * d.T;
+    const long long shift = d.frame->shift_by;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        if (shift > 0) {
+            const int t = e / d.nu, dd = e - t * d.nu;
+            const long long shifted = d.T - shift;  // columns that survive
+            const int src_t = (t < shifted) ? (int)(t + shift) : d.T - 1;
+            d.U_shift[e] = d.U[src_t * d.nu + dd];
+        }
+        // global rollout 1 lives on the engine whose range contains it
+        if (d.k_begin <= 1 && 1 < d.k_begin + d.k_count) static_cast<R *>(d.noise)[(size_t)(1 - d.k_begin) * n + e] = (R)(-d.U[e]);
+        if (d.k_begin == 0) static_cast<R *>(d.noise)[e] = R(0);  // rollout 0: zero noise, always
+    }
+    if (threadIdx.x == 0) {
+        d.minmax_enc[0] = 0xffffffffffffffffull;
+        d.minmax_enc[1] = 0ull;
+        *d.valid_count = 0;
+        *d.argmin = 0x7fffffffffffffffll;
+        *d.skip = 0;
+    }
+}
+
+// ---- warm start: the keep_best lowest-cost rollouts of the PREVIOUS update (stable order) -----------
+// mppi.cpp:222-253. One block; each round finds the smallest (cost, index) pair that is strictly
+// greater than the previous pick, which enumerates the stable sort order without sorting.
+__global__ void k_select_kept(const __grid_constant__ DeviceState d) {
+    __shared__ unsigned long long s_key[32];
+    __shared__ long long s_idx[32];
+    __shared__ unsigned long long last_key;
+    __shared__ long long last_idx;
+    const long long first = 2;  // s_static_rollouts
+    for (long long k = threadIdx.x; k < d.k_count; k += blockDim.x) d.kept[k] = 0;
+    if (threadIdx.x == 0) { last_key = 0; last_idx = -1; }
+    __syncthreads();
+    const long long keep = d.keep_best < d.K_total - 2 ? d.keep_best : d.K_total - 2;
+    for (long long round = 0; round < keep; round++) {
+        unsigned long long best = 0xffffffffffffffffull; long long bi = 0x7fffffffffffffffll;
+        const unsigned long long lk = last_key; const long long li = last_idx;
+        for (long long k = first + threadIdx.x; k < d.k_count; k += blockDim.x) {
+            double c = d.costs[k];
+            if (c != c) c = CUDART_INF;  // NaN sorts last (SURVEY A-2)
+            const unsigned long long key = encode_ordered(c);
+            const bool after = (key > lk) || (key == lk && k > li);
+            if (after && (key < best || (key == best && k < bi))) { best = key; bi = k; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, best, o);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ok < best || (ok == best && oi < bi)) { best = ok; bi = oi; }
+        }
+        if ((threadIdx.x & 31) == 0) { s_key[threadIdx.x >> 5] = best; s_idx[threadIdx.x >> 5] = bi; }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int nw = blockDim.x >> 5;
+            best = threadIdx.x < nw ? s_key[threadIdx.x] : 0xffffffffffffffffull;
+            bi = threadIdx.x < nw ? s_idx[threadIdx.x] : 0x7fffffffffffffffll;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long ok = __shfl_xor_sync(0xffffffffu, best, o);
+                const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ok < best || (ok == best && oi < bi)) { best = ok; bi = oi; }
+            }
+            if (threadIdx.x == 0) {
+                last_key = best; last_idx = bi;
+                if (bi != 0x7fffffffffffffffll) { d.kept[bi] = 1; d.kept_list[round] = bi + d.k_begin; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- K1 sample -----------------------------------------------------------------------------------
+// One thread per (rollout, step) column. Fresh columns are eps = L z (z ~ N(0, I) from Philox, or the
+// injected buffer); kept rollouts first move their surviving columns left by shift_by.
+// In-place shift is safe because a kept row is processed by ONE block that stages it in shared memory.
+template <class R, class RI> __device__ __forceinline__ void fresh_column(const DeviceState &d, long long kg, int t, R *dst) {
+    const int nu = d.nu;
+    if (d.frame->noise_source != 0) {
+        const RI *src = static_cast<const RI *>(d.injected) + ((size_t)(kg - d.k_begin) * d.T + t) * nu;
+        for (int i = 0; i < nu; i++) dst[i] = (R)src[i];
+        return;
+    }
+    float z[MAX_NU];
+    const unsigned long long col = (unsigned long long)kg * (unsigned long long)d.T + (unsigned long long)t;
+    const uint2 key = make_uint2((unsigned)d.frame->seed, (unsigned)(d.frame->seed >> 32));
+    const unsigned upd = (unsigned)d.frame->update_index;
+#pragma unroll
+    for (int b = 0; b < (MAX_NU + 3) / 4; b++) {
+        if (4 * b < nu) {
+            const uint4 r = philox4x32_10(make_uint4((unsigned)col, (unsigned)(col >> 32), (unsigned)b, upd), key);
+            box_muller(r.x, r.y, &z[4 * b], &z[4 * b + 1]);
+            box_muller(r.z, r.w, &z[4 * b + 2], &z[4 * b + 3]);
+        }
+    }
+    for (int i = 0; i < nu; i++) {
+        double s = 0.0;
+        for (int j = 0; j < nu; j++) s += d.L[j * nu + i] * (double)z[j];
+        dst[i] = (R)s;
+    }
+}
+
+template <class R, class RI> __global__ void __launch_bounds__(256) k_sample(const __grid_constant__ DeviceState d) {
+    // A block produces 256 consecutive columns = one contiguous span of 256*nu values: every thread
+    // builds its column in shared memory, then the block streams the span out with 16-byte stores.
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *tile = reinterpret_cast<R *>(smem_raw);
+    const long long col0 = (long long)blockIdx.x * blockDim.x;
+    const long long col = col0 + threadIdx.x;   // local column index
+    const long long ncols = d.k_count * d.T;
+    const int nu = d.nu;
+    R *noise = static_cast<R *>(d.noise);
+    if (col < ncols) {
+        const long long kl = col / d.T;
+        const int t = (int)(col - kl * d.T);
+        const long long kg = kl + d.k_begin;
+        R v[MAX_NU];
+        if (kg < 2 || d.kept[kl]) {   // static rollouts (k_prepare) and kept rollouts (k_shift_kept) keep their values
+            for (int i = 0; i < nu; i++) v[i] = noise[(size_t)col * nu + i];
+        } else {
+            fresh_column<R, RI>(d, kg, t, v);
+        }
+        for (int i = 0; i < nu; i++) tile[threadIdx.x * nu + i] = v[i];
+    }
+    __syncthreads();
+    const long long cols_here = (ncols - col0 < (long long)blockDim.x) ? (ncols - col0) : (long long)blockDim.x;
+    const size_t span = (size_t)cols_here * nu;           // values in this block's span
+    constexpr int VN = 16 / sizeof(R);
+    R *dst = noise + (size_t)col0 * nu;
+    if (((size_t)col0 * nu) % VN == 0) {
+        const size_t nvec = span / VN;
+        for (size_t i = threadIdx.x; i < nvec; i += blockDim.x) reinterpret_cast<int4 *>(dst)[i] = reinterpret_cast<const int4 *>(tile)[i];
+        for (size_t i = nvec * VN + threadIdx.x; i < span; i += blockDim.x) dst[i] = tile[i];
+    } else {
+        for (size_t i = threadIdx.x; i < span; i += blockDim.x) dst[i] = tile[i];
+    }
+}
+
+// kept rollouts: one block per kept rollout (mppi.cpp:243-252); nothing happens when shift_by <= 0
+template <class R, class RI> __global__ void k_shift_kept(const __grid_constant__ DeviceState d) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *row = reinterpret_cast<R *>(smem_raw);
+    const long long shift = d.frame->shift_by;
+    if (shift <= 0) return;
+    const long long kg = d.kept_list[blockIdx.x];
+    const long long kl = kg - d.k_begin;
+    if (kl < 0 || kl >= d.k_count) return;
+    const int n = d.nu * d.T;
+    R *noise = static_cast<R *>(d.noise) + (size_t)kl * n;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) row[e] = noise[e];
+    __syncthreads();
+    const long long shifted = d.T - shift;
+    for (int t = threadIdx.x; t < d.T; t += blockDim.x) {
+        if (t < shifted) {
+            for (int i = 0; i < d.nu; i++) noise[t * d.nu + i] = row[(t + shift) * d.nu + i];
+        } else {
+            R v[MAX_NU];
+            fresh_column<R, RI>(d, kg, t, v);
+            for (int i = 0; i < d.nu; i++) noise[t * d.nu + i] = v[i];
+        }
+    }
+}
+
+// ---- K3 ---------------------------------------------------------------------------------------------
+// publish {-min, max, valid} into the exchange buffer (all-reduced with MAX when sharded)
+__global__ void k_minmax_publish(const __grid_constant__ DeviceState d) {
+    if (threadIdx.x == 0) {
+        const int n = *d.valid_count;
+        d.minmax[0] = n > 0 ? -decode_ordered(d.minmax_enc[0]) : -CUDART_INF;
+        d.minmax[1] = n > 0 ? decode_ordered(d.minmax_enc[1]) : -CUDART_INF;
+        d.minmax[2] = n >= 2 ? 2.0 : (double)n;
+    }
+}
+
+// w_k = exp(-cost_scale (c_k - min) / (max - min)), NaN -> 0 (mppi.cpp:381-397); block partial sums
+__global__ void __launch_bounds__(256) k_weights(const __grid_constant__ DeviceState d) {
+    __shared__ double s_part[8];
+    const double minimum = -d.minmax[0], maximum = d.minmax[1];
+    const double difference = maximum - minimum;
+    const bool bad = !(d.minmax[2] >= 2.0) || !(difference >= 1e-6);  // all-NaN / early return (mppi.cpp:368-375)
+    if (bad) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *d.skip = 1;
+    }
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double w = 0.0;
+    if (k < d.k_count) {
+        const double c = d.costs[k];
+        if (c == minimum) atomicMin(d.argmin, k + d.k_begin);
+        if (!bad) {
+            w = (c != c) ? 0.0 : exp(-d.cost_scale * (c - minimum) / difference);
+            d.weights[k] = w;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) s += s_part[i];
+        d.wsum_partial[blockIdx.x] = s;
+    }
+}
+
+// ---- K4 weighted sum G = sum_k w_k eps_k (mppi.cpp:415-418) -----------------------------------------
+// Memory bound: every noise element is read exactly once, 16 bytes per thread per load, rows are
+// contiguous so a warp reads 512 contiguous bytes. Block b owns rollouts b, b+B, b+2B, ...; the
+// partial sums are combined in a fixed order by k_gradient_reduce so results are reproducible.
+template <class R> struct Vec16;
+template <> struct Vec16<double> { typedef double2 type; static constexpr int n = 2; };
+template <> struct Vec16<float> { typedef float4 type; static constexpr int n = 4; };
+__device__ __forceinline__ void fma_vec(double *acc, double w, const double2 &v) { acc[0] = fma(w, v.x, acc[0]); acc[1] = fma(w, v.y, acc[1]); }
+__device__ __forceinline__ void fma_vec(double *acc, double w, const float4 &v) {
+    acc[0] = fma(w, (double)v.x, acc[0]); acc[1] = fma(w, (double)v.y, acc[1]); acc[2] = fma(w, (double)v.z, acc[2]); acc[3] = fma(w, (double)v.w, acc[3]);
+}
+
+template <class R> __global__ void __launch_bounds__(512) k_gradient(const __grid_constant__ DeviceState d) {
+    typedef typename Vec16<R>::type V;
+    constexpr int VN = Vec16<R>::n;
+    if (*d.skip) return;
+    const int n = d.nu * d.T;
+    const int nvec = n / VN;  // host guarantees divisibility
+    const V *noise = static_cast<const V *>(d.noise);
+    for (int e = threadIdx.x; e < nvec; e += blockDim.x) {
+        double acc[VN];
+#pragma unroll
+        for (int i = 0; i < VN; i++) acc[i] = 0.0;
+        long long k = blockIdx.x;
+        // 4 rows in flight per thread
+        for (; k + 3 * (long long)gridDim.x < d.k_count; k += 4 * (long long)gridDim.x) {
+            const V v0 = __ldg(noise + (size_t)k * nvec + e);
+            const V v1 = __ldg(noise + (size_t)(k + gridDim.x) * nvec + e);
+            const V v2 = __ldg(noise + (size_t)(k + 2 * (long long)gridDim.x) * nvec + e);
+            const V v3 = __ldg(noise + (size_t)(k + 3 * (long long)gridDim.x) * nvec + e);
+            const double w0 = d.weights[k], w1 = d.weights[k + gridDim.x], w2 = d.weights[k + 2 * (long long)gridDim.x], w3 = d.weights[k + 3 * (long long)gridDim.x];
+            fma_vec(acc, w0, v0); fma_vec(acc, w1, v1); fma_vec(acc, w2, v2); fma_vec(acc, w3, v3);
+        }
+        for (; k < d.k_count; k += gridDim.x) fma_vec(acc, d.weights[k], __ldg(noise + (size_t)k * nvec + e));
+#pragma unroll
+        for (int i = 0; i < VN; i++) d.grad_partial[(size_t)blockIdx.x * n + e * VN + i] = acc[i];
+    }
+}
+
+// fixed-order combination of the partials into the exchange buffer sums = {sum w, sum w*eps}
+__global__ void __launch_bounds__(256) k_gradient_reduce(const __grid_constant__ DeviceState d) {
+    if (*d.skip) return;
+    const int n = d.nu * d.T;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) {
+        double s = 0.0;
+        for (int b = 0; b < d.grad_blocks; b++) s += d.grad_partial[(size_t)b * n + e];
+        d.sums[1 + e] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double s = 0.0;
+        for (int b = 0; b < d.weight_blocks; b++) s += d.wsum_partial[b];
+        d.sums[0] = s;
+    }
+}
+
+// ---- K5 finish: gradient step, Savitzky–Golay smoothing, clamp, publish ------------------------------
+// mppi.cpp:415-447 + filter.cpp:19-173. One block; channel d of the window is run by thread d with the
+// window staged in shared memory (the recurrence is sequential in time, channels are independent).
+__device__ __forceinline__ int sg_lower_bound(const double *tt, int len, double t) {  // std::lower_bound
+    int first = 0;
+    while (len > 0) {
+        const int half = len >> 1, mid = first + half;
+        if (tt[mid] < t) { first = mid + 1; len = len - half - 1; } else len = half;
+    }
+    return first;
+}
+
+__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ DeviceState d) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *uu = reinterpret_cast<double *>(smem_raw);  // nu x Lw
+    double *tt = uu + d.nu * d.sg_len;                   // nu x Lw
+    const int n = d.nu * d.T;
+    const int skip = *d.skip;
+    if (!(d.minmax[2] >= 2.0)) return;  // "all nan rollouts" (mppi.cpp:368-370): the reference throws before publishing
+    if (!skip) {
+        const double total = d.sums[0];
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+            const double g = d.sums[1 + e] / total;
+            d.gradient[e] = g;
+            d.U_shift[e] += g * d.gradient_step;
+        }
+        // normalise the weights (std::transform, mppi.cpp:403-408)
+        for (long long k = threadIdx.x; k < d.k_count; k += blockDim.x) d.weights[k] = d.weights[k] / total;
+    }
+    __syncthreads();
+    if (!skip && d.sg_enabled) {
+        const int Lw = d.sg_len, w = d.sg_window;
+        for (int i = threadIdx.x; i < d.nu * Lw; i += blockDim.x) { uu[i] = d.sg_uu[i]; tt[i] = d.sg_tt[i]; }
+        __syncthreads();
+        if (threadIdx.x < d.nu) {
+            double *u = uu + threadIdx.x * Lw, *tm = tt + threadIdx.x * Lw;
+            const double t0 = d.frame->time;
+            // trim(t0): filter.cpp:34-67. start_idx is always w + T after a full update, or w initially.
+            const int start_idx = *d.sg_started ? w + d.T : w;
+            int trim_idx = start_idx;
+            for (int i = 0; i < start_idx; i++) if (tm[i] >= t0) { trim_idx = i; break; }
+            // rotate left by (trim_idx - w) as size_t arithmetic would: negative offsets wrap in the
+            // reference (UB there); we rotate modulo Lw which is what std::rotate does for in-range values
+            int offset = trim_idx - w;
+            if (offset > 0) {
+                // rotate left by offset, then refill the vacated tail with the last valid sample
+                for (int i = 0; i + offset < Lw; i++) { u[i] = u[i + offset]; tm[i] = tm[i + offset]; }
+                const double lu = u[Lw - offset - 1], lt = tm[Lw - offset - 1];
+                for (int i = Lw - offset; i < Lw; i++) { u[i] = lu; tm[i] = lt; }
+            }
+            tm[w] = t0;
+            // add_measurement x T (filter.cpp:69-90): final state = samples in [w, w+T), copies of the last beyond
+            // times are compared with == / >= later: no FMA contraction, exactly m_rollout_time + i * m_time_step (mppi.cpp:430)
+            for (int i = 0; i < d.T; i++) { u[w + i] = d.U_shift[i * d.nu + threadIdx.x]; tm[w + i] = __dadd_rn(t0, __dmul_rn((double)i, d.dt)); }
+            for (int i = w + d.T; i < Lw; i++) { u[i] = u[w + d.T - 1]; tm[i] = tm[w + d.T - 1]; }
+            // apply x T (filter.cpp:163-173): filtered value written ONE SLOT EARLIER than the sample
+            for (int i = 0; i < d.T; i++) {
+                const double t = __dadd_rn(t0, __dmul_rn((double)i, d.dt));
+                const int idx = sg_lower_bound(tm, Lw, t);
+                const double *v = u + idx - w;
+                double res = d.sg_weights[0] * v[0];
+                for (int j = 1; j < 2 * w + 1; j++) res += d.sg_weights[j] * v[j];
+                res = res / 1.0;
+                u[sg_lower_bound(tm, Lw, t) - 1] = res;
+                d.U_shift[i * d.nu + threadIdx.x] = res;
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < d.nu * Lw; i += blockDim.x) { d.sg_uu[i] = uu[i]; d.sg_tt[i] = tt[i]; }
+        if (threadIdx.x == 0) *d.sg_started = 1;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        double u = d.U_shift[e];
+        if (!skip && d.bound) {
+            const int dd = e % d.nu;
+            // cwiseMin(max).cwiseMax(min), mppi.cpp:443-447
+            u = std_min(u, d.cmax[dd]);   // std::min / std::max semantics: a NaN control stays NaN like in the reference
+            u = std_max(u, d.cmin[dd]);
+            d.U_shift[e] = u;
+        }
+        d.U[e] = u;  // publication: m_optimal_control = m_optimal_control_shifted (mppi.cpp:178-182)
+    }
+}
+
+// ---- launchers -----------------------------------------------------------------------------------------
+cudaError_t launch_prepare(const DeviceState &d, int precision, cudaStream_t s) {
+    if (precision == 0) k_prepare<double><<<1, 256, 0, s>>>(d); else k_prepare<float><<<1, 256, 0, s>>>(d);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_select_kept(const DeviceState &d, cudaStream_t s) {
+    k_select_kept<<<1, 1024, 0, s>>>(d);
+    return cudaGetLastError();
+}
+
+template <class R> static cudaError_t sample_t(const DeviceState &d, cudaStream_t s, int *launches) {
+    const size_t row = sizeof(R) * (size_t)d.nu * d.T;
+    if (d.keep_best > 0) {
+        if (row > 48 * 1024) {
+            cudaError_t e = d.injected_is_double ? cudaFuncSetAttribute(k_shift_kept<R, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row)
+                                                 : cudaFuncSetAttribute(k_shift_kept<R, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row);
+            if (e != cudaSuccess) return e;
+        }
+        if (d.injected_is_double) k_shift_kept<R, double><<<(unsigned)d.keep_best, 64, row, s>>>(d);
+        else k_shift_kept<R, R><<<(unsigned)d.keep_best, 64, row, s>>>(d);
+        ++*launches;
+    }
+    const long long ncols = d.k_count * d.T;
+    const unsigned grid = (unsigned)((ncols + 255) / 256);
+    const size_t tile = sizeof(R) * 256 * (size_t)d.nu;
+    if (d.injected_is_double) k_sample<R, double><<<grid, 256, tile, s>>>(d); else k_sample<R, R><<<grid, 256, tile, s>>>(d);
+    ++*launches;
+    return cudaGetLastError();
+}
+cudaError_t launch_sample(const DeviceState &d, int precision, cudaStream_t s, int *launches) {
+    return precision == 0 ? sample_t<double>(d, s, launches) : sample_t<float>(d, s, launches);
+}
+
+cudaError_t launch_rollout(const DeviceState &d, int precision, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s) {
+    return precision == 0 ? launch_rollout_f64(d, variant, faithful, params, optimal_only, s) : launch_rollout_f32(d, variant, faithful, params, optimal_only, s);
+}
+
+cudaError_t launch_minmax_publish(const DeviceState &d, cudaStream_t s) {
+    k_minmax_publish<<<1, 32, 0, s>>>(d);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_weights(const DeviceState &d, cudaStream_t s) {
+    k_weights<<<d.weight_blocks, 256, 0, s>>>(d);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gradient(const DeviceState &d, int precision, cudaStream_t s, int *launches) {
+    const int n = d.nu * d.T;
+    const int nvec = n / (precision == 0 ? 2 : 4);
+    const int threads = std::min(512, ((nvec + 127) / 128) * 128);
+    if (precision == 0) k_gradient<double><<<d.grad_blocks, threads, 0, s>>>(d); else k_gradient<float><<<d.grad_blocks, threads, 0, s>>>(d);
+    k_gradient_reduce<<<(n + 255) / 256, 256, 0, s>>>(d);
+    *launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finish(const DeviceState &d, cudaStream_t s) {
+    const size_t smem = d.sg_enabled ? sizeof(double) * 2 * (size_t)d.nu * d.sg_len : 0;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k_finish<<<1, 256, smem, s>>>(d);
+    return cudaGetLastError();
+}
+
+}  // namespace mppi_b200

@@ -1,0 +1,114 @@
+// K2 — the rollout kernel (replaces the thread-pool loop of reference src/controller/mppi.cpp:272-342
+// and everything it calls per sample). One thread owns one rollout for the whole horizon: joint
+// state, tank energy and stale kinematics live in registers, the shared control sequence / wrench
+// table / initial state are staged once per block in shared memory, and the only per-step global
+// traffic is the thread's own noise column (16-byte vector loads; the row is contiguous).
+// After the horizon the block folds its costs into the running min / max (warp shuffles, then one
+// order-preserving atomicMin / atomicMax per block) so no separate reduction pass is needed.
+#pragma once
+#include "kernels.cuh"
+
+namespace mppi_b200 {
+
+// The including translation unit defines MPPI_DEVICE_MODEL: its own __constant__ RobotModel<R>
+// (one per precision, so no relocatable device code is needed).
+
+// order preserving map double -> u64 (so that integer atomicMin/Max order like the doubles)
+__device__ __forceinline__ unsigned long long encode_ordered(double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double decode_ordered(unsigned long long e) {
+    unsigned long long b = (e & 0x8000000000000000ull) ? (e & 0x7fffffffffffffffull) : ~e;
+    return __longlong_as_double((long long)b);
+}
+
+template <class R, int VAR, bool FAITHFUL, class ParamsT>
+__global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ DeviceState d, const __grid_constant__ ParamsT P, int optimal_only) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R *sU = reinterpret_cast<R *>(smem_raw);        // nu*T
+    R *sW = sU + d.nu * d.T;                         // 6*T
+    R *sx = sW + 6 * d.T;                            // 32
+    const double *Usrc = d.U_shift;
+    for (int i = threadIdx.x; i < d.nu * d.T; i += blockDim.x) sU[i] = (R)Usrc[i];
+    const int has_w = d.frame->has_wrench;
+    for (int i = threadIdx.x; i < 6 * d.T; i += blockDim.x) sW[i] = has_w ? (R)d.wrench[i] : R(0);
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) sx[i] = (R)d.frame->x0[i];
+    __syncthreads();
+
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double cost = 0.0;
+    bool active = optimal_only ? (k == 0) : (k < d.k_count);
+    if (active) {
+        // the optimal re-rollout (Trajectory::filter, mppi.cpp:450-479) reads a row of zeros
+        const R *eps = static_cast<const R *>(d.noise) + (size_t)k * d.T * d.nu;
+        if constexpr (VAR == VAR_TOY) {
+            cost = rollout_toy<R>(P, sx, sU, eps, d.T, (R)d.dt, d.discount);
+        } else {
+            RolloutInputs<R> in;
+            in.x0 = sx; in.U = sU; in.W = has_w ? sW : nullptr; in.T = d.T; in.dt = (R)d.dt; in.discount = d.discount;
+            double bd[7] = {0, 0, 0, 0, 0, 0, 0};
+            cost = rollout_franka<R, VAR, FAITHFUL>(MPPI_DEVICE_MODEL, P, in, eps, optimal_only ? bd : nullptr);
+            if (optimal_only) {
+                for (int i = 0; i < 7; i++) d.breakdown[i] = bd[i];
+                d.breakdown[7] = cost;
+            }
+        }
+        if (optimal_only) d.optimal_cost[0] = cost; else d.costs[k] = cost;
+    }
+    if (optimal_only) return;
+
+    // block min / max over the non-NaN costs
+    const bool valid = active && !(cost != cost);
+    double mn = valid ? cost : __longlong_as_double(0x7ff0000000000000ll);   // +inf
+    double mx = valid ? cost : __longlong_as_double(0xfff0000000000000ll);   // -inf
+    int cnt = valid ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt > 0) {
+        atomicMin(&d.minmax_enc[0], encode_ordered(mn));
+        atomicMax(&d.minmax_enc[1], encode_ordered(mx));
+        atomicAdd(d.valid_count, cnt);
+    }
+}
+
+template <class R, int VAR, bool FAITHFUL, class ParamsT>
+cudaError_t launch_rollout_t(const DeviceState &d, const void *params, bool optimal_only, cudaStream_t s) {
+    const ParamsT &P = *static_cast<const ParamsT *>(params);
+    // few rollouts: one warp per block spreads them over the SMs; many: 128-thread blocks
+    int block = d.k_count <= 148 * 64 ? 32 : (d.k_count <= 148 * 256 ? 64 : 128);
+    long long grid = optimal_only ? 1 : (d.k_count + block - 1) / block;
+    if (optimal_only) block = 32;
+    size_t smem = sizeof(R) * ((size_t)d.nu * d.T + 6 * (size_t)d.T + 32);
+    auto kern = k_rollout<R, VAR, FAITHFUL, ParamsT>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<(unsigned)grid, block, smem, s>>>(d, P, optimal_only ? 1 : 0);
+    return cudaGetLastError();
+}
+
+template <class R> cudaError_t launch_rollout_r(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s) {
+    switch (variant) {
+        case VAR_TOY: return launch_rollout_t<R, VAR_TOY, false, ToyP<R>>(d, params, optimal_only, s);
+        case VAR_TP_LEAN: return faithful ? launch_rollout_t<R, VAR_TP_LEAN, true, TrackPointP<R>>(d, params, optimal_only, s)
+                                          : launch_rollout_t<R, VAR_TP_LEAN, false, TrackPointP<R>>(d, params, optimal_only, s);
+        case VAR_TP_FULL: return faithful ? launch_rollout_t<R, VAR_TP_FULL, true, TrackPointP<R>>(d, params, optimal_only, s)
+                                          : launch_rollout_t<R, VAR_TP_FULL, false, TrackPointP<R>>(d, params, optimal_only, s);
+        case VAR_AM: return faithful ? launch_rollout_t<R, VAR_AM, true, AssistedP<R>>(d, params, optimal_only, s)
+                                     : launch_rollout_t<R, VAR_AM, false, AssistedP<R>>(d, params, optimal_only, s);
+        case VAR_AM_ENERGY: return faithful ? launch_rollout_t<R, VAR_AM_ENERGY, true, AssistedP<R>>(d, params, optimal_only, s)
+                                            : launch_rollout_t<R, VAR_AM_ENERGY, false, AssistedP<R>>(d, params, optimal_only, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_rollout_f64(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s);
+cudaError_t launch_rollout_f32(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s);
+
+}  // namespace mppi_b200

@@ -1,0 +1,88 @@
+// Launch interface between the host engine (engine.cu) and the sm_100a kernels.
+// Kernel list: K1 sample, K2 rollout, K3 reduce/weights, K4 weighted sum,
+// K5 finish (gradient step + Savitzky–Golay smoothing + clamp), K6 optimal re-rollout (= K2 with
+// one thread on the zero-noise row).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rollout_core.cuh"
+
+namespace mppi_b200 {
+
+constexpr int MAX_NU = 12;
+constexpr int MAX_WINDOW = 64;  // Savitzky–Golay half window supported by the finish kernel
+
+// Per-update inputs, written by the host into pinned memory and copied to the device in ONE
+// transfer; kernels read it from global memory so a captured CUDA graph stays valid.
+struct Frame {
+    double x0[32];       // state (31 used for Franka+Ridgeback, 4 for the toy)
+    double time;         // m_rollout_time
+    double sg_prev_trim; // last smoothing reset time before this update
+    long long shift_by;  // (int64)((time - last_shift_time) / dt), evaluated on the host in double (mppi.cpp:194)
+    unsigned long long seed;
+    unsigned long long update_index;
+    int has_wrench;
+    int noise_source;    // MPPI_B200_NOISE_*
+    // followed by T x 6 doubles of forecast wrench
+};
+
+// Device-resident state of one engine (pointers only; owned by the engine).
+struct DeviceState {
+    // geometry
+    int nu, nx, T;
+    long long K_total;     // K + 2
+    long long k_begin;     // first global rollout index owned by this engine
+    long long k_count;     // rollouts owned
+    long long keep_best;
+    // buffers
+    const Frame *frame;
+    const double *wrench;  // inside the frame block
+    double *U;             // published optimal control, nu x T
+    double *U_shift;       // working copy (m_optimal_control_shifted)
+    void *noise;           // k_count x T x nu, engine precision
+    const void *injected;  // same layout (precision of `injected_is_double`), or nullptr
+    int injected_is_double;
+    double *costs;         // k_count
+    double *weights;       // k_count (unnormalised until finish)
+    unsigned char *kept;   // k_count flags for the warm start
+    long long *kept_list;  // keep_best global indices, sorted order
+    unsigned long long *minmax_enc;  // [2] order-preserving encodings for atomicMin / atomicMax
+    int *valid_count;      // number of non-NaN local rollouts
+    long long *argmin;     // global index of the best rollout
+    double *minmax;        // exchange buffer {-min, max, valid(<=2)}
+    double *sums;          // exchange buffer {sum w, sum w*eps [nu*T]}
+    double *wsum_partial;  // per block of the weights kernel
+    double *grad_partial;  // [grad_blocks][nu*T]
+    int grad_blocks;
+    int weight_blocks;
+    double *gradient;      // normalised gradient (get_gradient())
+    int *skip;             // 1 when max-min < 1e-6 (mppi.cpp:373-375): weights/gradient/U left untouched
+    double *L;             // nu x nu column-major noise transform V*sqrt(Lambda) (gaussian.hpp:48-55)
+    // smoothing window state, per channel: uu[Lw], tt[Lw], then start_idx/last_trim in sg_meta
+    double *sg_uu, *sg_tt;
+    double *sg_weights;    // 2*window+1
+    int sg_enabled, sg_window, sg_len;
+    int *sg_started;       // 0 until the first smoothing pass (window start_idx = w), then start_idx = w + T
+    // constants
+    double dt, gradient_step, cost_scale, discount;
+    int bound;
+    double cmin[MAX_NU], cmax[MAX_NU];
+    // optimal re-rollout outputs
+    double *optimal_cost;  // [1]
+    double *breakdown;     // [8]
+};
+
+cudaError_t upload_robot_model();  // once per device
+
+cudaError_t launch_prepare(const DeviceState &d, int precision, cudaStream_t s);
+cudaError_t launch_select_kept(const DeviceState &d, cudaStream_t s);
+cudaError_t launch_sample(const DeviceState &d, int precision, cudaStream_t s, int *launches);
+// objective params: pointer to the host-side block in kernel arithmetic (ToyP/TrackPointP/AssistedP<R>)
+cudaError_t launch_rollout(const DeviceState &d, int precision, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s);
+cudaError_t launch_minmax_publish(const DeviceState &d, cudaStream_t s);
+cudaError_t launch_weights(const DeviceState &d, cudaStream_t s);
+cudaError_t launch_gradient(const DeviceState &d, int precision, cudaStream_t s, int *launches);
+cudaError_t launch_finish(const DeviceState &d, cudaStream_t s);
+
+}  // namespace mppi_b200

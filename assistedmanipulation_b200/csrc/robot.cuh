@@ -1,0 +1,374 @@
+// Rigid-body step of the Franka Research 3 + Ridgeback model for ONE rollout, held by ONE thread.
+// Replaces, per sample, the pinocchio calls of FrankaRidgeback::PinocchioDynamics::calculate
+// (reference src/frankaridgeback/pinocchio_dynamics.cpp:153-224): nonLinearEffects (RNEA),
+// aba, forwardKinematics, updateFramePlacements, computeFrameJacobian(WORLD),
+// getFrameVelocity(WORLD).
+//
+// Written for the GPU, not translated: the 12-joint topology is fixed at compile time (every
+// joint loop is a template recursion, so joint type and parent are constants in the SASS), all
+// joints are axis aligned (x, y or z — panda_finger_joint2's -y axis is folded into a sign), the
+// articulated inertia is carried as three 3x3 blocks with symmetric storage, and two evaluation
+// modes exist (include/mppi_b200.h MPPI_B200_DYNAMICS_*):
+//   FAITHFUL  tau = u + nle(q,v); a = ABA(q,v,tau)      — operation for operation what the reference asks of pinocchio
+//   FUSED     a = ABA(q, 0, u) without gravity           — identical in exact arithmetic (nle cancels), ~40 % fewer flops;
+//             nle is evaluated only when the energy tank needs tau^T v.
+// Host/device so tests can compare against the oracle on the CPU.
+#pragma once
+#include "spatial.cuh"
+
+namespace mppi_b200 {
+
+constexpr int NJ = 12;
+enum JointType { JT_PX = 0, JT_PY = 1, JT_RZ = 2 };
+
+// Topology (checked against robot_model.h at engine creation).
+template <int I> struct Joint {
+    static constexpr int parent = (I == 11) ? 9 : I - 1;
+    static constexpr int type = (I == 0) ? JT_PX : ((I == 1 || I >= 10) ? JT_PY : JT_RZ);
+};
+
+// Model constants in the arithmetic of the kernel. One instance per precision in __constant__ memory.
+template <class R> struct RobotModel {
+    R place_R[NJ][9];  // fixed placement of joint i in its parent joint frame
+    R place_p[NJ][3];
+    R sign[NJ];        // +1, or -1 for a joint whose axis points along the negative coordinate axis
+    R mass[NJ];
+    R mc[NJ][3];       // mass * com
+    R Io[NJ][6];       // rotational inertia about the joint origin: xx xy xz yy yz zz
+    R com[NJ][3];
+    R ee_p[3];         // end effector frame origin in joint 9
+    R mount_p[3];      // arm_mount_joint frame origin in joint 2
+    R gravity;         // 9.81
+};
+
+// What the objective needs from the kinematics of one calculate() call. These are the values the
+// reference's costs read "stale" at the next step.
+template <class R> struct Kinematics {
+    Vec3<R> ee_pos;      // data.oMf[ee].translation()
+    Vec3<R> mount_pos;   // data.oMf[arm_mount_joint].translation()
+    Vec3<R> ee_lin_vel;  // getFrameVelocity(ee, WORLD).linear()
+    R manip_det;         // det(J_a J_a^T), J_a = rows 0-2 / columns 3-9 of the WORLD jacobian
+    Vec3<R> link_com[8]; // world COM of Link::PIVOT, PANDA_LINK1..7
+};
+
+enum KinFlags { KIN_MOUNT = 1, KIN_VEL = 2, KIN_MANIP = 4, KIN_LINKS = 8 };
+
+template <class R> MPPI_HD Art<R> body_inertia(const RobotModel<R> &M, int i) {
+    Art<R> a;
+    const R m = M.mass[i], cx = M.mc[i][0], cy = M.mc[i][1], cz = M.mc[i][2];
+    a.A.xx = m; a.A.yy = m; a.A.zz = m; a.A.xy = R(0); a.A.xz = R(0); a.A.yz = R(0);
+    // B = -m [c]x
+    a.B.m[0] = R(0); a.B.m[1] = cz;   a.B.m[2] = -cy;
+    a.B.m[3] = -cz;  a.B.m[4] = R(0); a.B.m[5] = cx;
+    a.B.m[6] = cy;   a.B.m[7] = -cx;  a.B.m[8] = R(0);
+    a.D.xx = M.Io[i][0]; a.D.xy = M.Io[i][1]; a.D.xz = M.Io[i][2]; a.D.yy = M.Io[i][3]; a.D.yz = M.Io[i][4]; a.D.zz = M.Io[i][5];
+    return a;
+}
+
+// Y * motion for the rigid body of joint i: f = m v - mc x w ; n = mc x v + Io w
+template <class R> MPPI_HD Frc<R> body_mul(const RobotModel<R> &M, int i, const Mot<R> &a) {
+    const Vec3<R> mc = v3<R>(M.mc[i][0], M.mc[i][1], M.mc[i][2]);
+    Sym3<R> Io; Io.xx = M.Io[i][0]; Io.xy = M.Io[i][1]; Io.xz = M.Io[i][2]; Io.yy = M.Io[i][3]; Io.yz = M.Io[i][4]; Io.zz = M.Io[i][5];
+    Frc<R> f;
+    f.f = a.v * M.mass[i] - cross(mc, a.w);
+    f.n = cross(mc, a.v) + mul(Io, a.w);
+    return f;
+}
+
+template <class R, int TYPE> MPPI_HD Mot<R> joint_motion(R qd) {  // S * qd
+    Mot<R> m; m.v = v3<R>(R(0), R(0), R(0)); m.w = m.v;
+    if (TYPE == JT_PX) m.v.x = qd; else if (TYPE == JT_PY) m.v.y = qd; else m.w.z = qd;
+    return m;
+}
+// v x (S qd) specialised by joint type (skips the structurally zero products)
+template <class R, int TYPE> MPPI_HD Mot<R> cross_joint(const Mot<R> &a, R qd) {
+    Mot<R> o;
+    if (TYPE == JT_RZ) {       // b = (0 ; 0,0,qd)
+        o.v = v3<R>(a.v.y * qd, -(a.v.x * qd), R(0));
+        o.w = v3<R>(a.w.y * qd, -(a.w.x * qd), R(0));
+    } else if (TYPE == JT_PX) {  // b = (qd,0,0 ; 0): o.v = a.w x b.v
+        o.v = v3<R>(R(0), a.w.z * qd, -(a.w.y * qd));
+        o.w = v3<R>(R(0), R(0), R(0));
+    } else {
+        o.v = v3<R>(-(a.w.z * qd), R(0), a.w.x * qd);
+        o.w = v3<R>(R(0), R(0), R(0));
+    }
+    return o;
+}
+template <class R, int TYPE> MPPI_HD R joint_dot(const Frc<R> &f) {  // S^T f
+    return TYPE == JT_PX ? f.f.x : (TYPE == JT_PY ? f.f.y : f.n.z);
+}
+template <class R, int TYPE> MPPI_HD R joint_dot(const Mot<R> &m) {
+    return TYPE == JT_PX ? m.v.x : (TYPE == JT_PY ? m.v.y : m.w.z);
+}
+
+// Per-step scratch. Arrays are indexed with compile-time constants only (template recursion), so
+// ptxas keeps what fits in registers and parks the rest in thread-local memory.
+template <class R> struct Scratch {
+    Xf<R> li[NJ];      // parent <- joint transforms
+    Mot<R> v[NJ];      // body velocities (joint frame)
+    Mot<R> c[NJ];      // velocity-product accelerations
+    Frc<R> f[NJ];      // RNEA forces
+    Frc<R> pA[NJ];     // ABA bias forces
+    Frc<R> U[NJ];      // Yaba * S
+    R Dinv[NJ], u[NJ];
+    Art<R> Ia;         // articulated inertia being propagated down the chain
+    Art<R> Ia9;        // joint 9 collects two children
+};
+
+template <class R, int I> MPPI_HD void joint_transform(const RobotModel<R> &M, R q, Xf<R> &X) {
+    constexpr int T = Joint<I>::type;
+    const R *P = M.place_R[I];
+    if (T == JT_RZ) {
+        R s, c;
+        sincos_(q, &s, &c);
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            X.R_.m[3 * r + 0] = P[3 * r + 0] * c + P[3 * r + 1] * s;
+            X.R_.m[3 * r + 1] = P[3 * r + 1] * c - P[3 * r + 0] * s;
+            X.R_.m[3 * r + 2] = P[3 * r + 2];
+        }
+        X.p = v3<R>(M.place_p[I][0], M.place_p[I][1], M.place_p[I][2]);
+    } else {
+        constexpr int ax = (T == JT_PX) ? 0 : 1;
+#pragma unroll
+        for (int k = 0; k < 9; k++) X.R_.m[k] = P[k];
+        X.p = v3<R>(M.place_p[I][0] + P[0 + ax] * q, M.place_p[I][1] + P[3 + ax] * q, M.place_p[I][2] + P[6 + ax] * q);
+    }
+}
+
+// ---- pass 1: transforms, velocities, RNEA forces ----------------------------------------------
+template <class R, int I, bool VEL, bool NLE, bool BIAS>
+MPPI_HD void pass1(const RobotModel<R> &M, const R *q, const R *qd, Scratch<R> &S, Mot<R> *agf) {
+    constexpr int P = Joint<I>::parent, T = Joint<I>::type;
+    const R sg = M.sign[I];
+    joint_transform<R, I>(M, q[I] * sg, S.li[I]);
+    if (VEL) {
+        const R w = qd[I] * sg;
+        Mot<R> vj = joint_motion<R, T>(w);
+        if (P >= 0) { Mot<R> vp = act_inv(S.li[I], S.v[P < 0 ? 0 : P]); S.v[I].v = vp.v + vj.v; S.v[I].w = vp.w + vj.w; }
+        else S.v[I] = vj;
+        if (NLE || BIAS) {
+            S.c[I] = cross_joint<R, T>(S.v[I], w);
+            Frc<R> h = body_mul(M, I, S.v[I]);
+            Frc<R> vxh = fcross(S.v[I], h);
+            if (NLE) {
+                Mot<R> ap;
+                if (P >= 0) ap = act_inv(S.li[I], agf[P < 0 ? 0 : P]);
+                else { ap.v = tmul(S.li[I].R_, v3<R>(R(0), R(0), M.gravity)); ap.w = v3<R>(R(0), R(0), R(0)); }
+                agf[I].v = ap.v + S.c[I].v; agf[I].w = ap.w + S.c[I].w;
+                Frc<R> ya = body_mul(M, I, agf[I]);
+                S.f[I].f = ya.f + vxh.f; S.f[I].n = ya.n + vxh.n;
+            }
+            if (BIAS) S.pA[I] = vxh;
+        }
+    }
+    if (I + 1 < NJ) pass1<R, (I + 1 < NJ ? I + 1 : I), VEL, NLE, BIAS>(M, q, qd, S, agf);
+}
+
+// ---- RNEA backward: nle_i = S^T f_i ; f_parent += X f_i ----------------------------------------
+template <class R, int I> MPPI_HD void rnea_back(const RobotModel<R> &M, Scratch<R> &S, R *nle) {
+    constexpr int P = Joint<I>::parent, T = Joint<I>::type;
+    nle[I] = joint_dot<R, T>(S.f[I]) * M.sign[I];
+    if (P >= 0) {
+        Frc<R> fp = act(S.li[I], S.f[I]);
+        S.f[P < 0 ? 0 : P].f = S.f[P < 0 ? 0 : P].f + fp.f;
+        S.f[P < 0 ? 0 : P].n = S.f[P < 0 ? 0 : P].n + fp.n;
+    }
+    if (I > 0) rnea_back<R, (I > 0 ? I - 1 : 0)>(M, S, nle);
+}
+
+// A P^ and P^ A helpers, P^ = [p]x
+template <class R> MPPI_HD Mat3<R> mul_skew(const Mat3<R> &m, const Vec3<R> &p) {  // m * [p]x
+    Mat3<R> o;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        o(i, 0) = m(i, 1) * p.z - m(i, 2) * p.y;
+        o(i, 1) = m(i, 2) * p.x - m(i, 0) * p.z;
+        o(i, 2) = m(i, 0) * p.y - m(i, 1) * p.x;
+    }
+    return o;
+}
+template <class R> MPPI_HD Mat3<R> sym_mul_skew(const Sym3<R> &s, const Vec3<R> &p) {
+    Mat3<R> m;
+    m.m[0] = s.xx; m.m[1] = s.xy; m.m[2] = s.xz; m.m[3] = s.xy; m.m[4] = s.yy; m.m[5] = s.yz; m.m[6] = s.xz; m.m[7] = s.yz; m.m[8] = s.zz;
+    return mul_skew(m, p);
+}
+
+// Ia (joint frame of child) -> parent frame through X, accumulated into `dst`.
+template <class R> MPPI_HD void art_transform_add(const Art<R> &Ia, const Xf<R> &X, Art<R> &dst) {
+    const Sym3<R> A = conj(X.R_, Ia.A);
+    const Mat3<R> Bb = conj(X.R_, Ia.B);
+    const Sym3<R> Db = conj(X.R_, Ia.D);
+    const Mat3<R> AP = sym_mul_skew(A, X.p);
+    Mat3<R> Bn;
+#pragma unroll
+    for (int k = 0; k < 9; k++) Bn.m[k] = Bb.m[k] - AP.m[k];
+    // D' = Db - Bb^T P^ + P^ B'   (only the upper triangle)
+    const Vec3<R> p = X.p;
+    // (Bb^T P^)(i,j): row i of Bb^T = column i of Bb
+    auto btp = [&](int i, int j) -> R {
+        const R b0 = Bb(0, i), b1 = Bb(1, i), b2 = Bb(2, i);
+        return j == 0 ? (b1 * p.z - b2 * p.y) : (j == 1 ? (b2 * p.x - b0 * p.z) : (b0 * p.y - b1 * p.x));
+    };
+    auto pb = [&](int i, int j) -> R {  // (P^ B')(i,j)
+        return i == 0 ? (p.y * Bn(2, j) - p.z * Bn(1, j)) : (i == 1 ? (p.z * Bn(0, j) - p.x * Bn(2, j)) : (p.x * Bn(1, j) - p.y * Bn(0, j)));
+    };
+    dst.A.xx += A.xx; dst.A.xy += A.xy; dst.A.xz += A.xz; dst.A.yy += A.yy; dst.A.yz += A.yz; dst.A.zz += A.zz;
+#pragma unroll
+    for (int k = 0; k < 9; k++) dst.B.m[k] += Bn.m[k];
+    dst.D.xx += Db.xx - btp(0, 0) + pb(0, 0);
+    dst.D.xy += Db.xy - btp(0, 1) + pb(0, 1);
+    dst.D.xz += Db.xz - btp(0, 2) + pb(0, 2);
+    dst.D.yy += Db.yy - btp(1, 1) + pb(1, 1);
+    dst.D.yz += Db.yz - btp(1, 2) + pb(1, 2);
+    dst.D.zz += Db.zz - btp(2, 2) + pb(2, 2);
+}
+
+template <class R> MPPI_HD Frc<R> art_mul(const Art<R> &I, const Mot<R> &a) {
+    Frc<R> f;
+    f.f = mul(I.A, a.v) + mul(I.B, a.w);
+    f.n = tmul(I.B, a.v) + mul(I.D, a.w);
+    return f;
+}
+
+// ---- ABA backward pass -------------------------------------------------------------------------
+// `cur` holds the articulated inertia of joint I (its own body + whatever its children added).
+template <class R, int I, bool BIAS>
+MPPI_HD void aba_back(const RobotModel<R> &M, const R *tau, Scratch<R> &S, Art<R> &cur) {
+    constexpr int P = Joint<I>::parent, T = Joint<I>::type;
+    // U = Yaba * S : a column of the 6x6
+    Frc<R> U;
+    R D;
+    if (T == JT_PX) { U.f = v3<R>(cur.A.xx, cur.A.xy, cur.A.xz); U.n = v3<R>(cur.B(0, 0), cur.B(0, 1), cur.B(0, 2)); D = cur.A.xx; }
+    else if (T == JT_PY) { U.f = v3<R>(cur.A.xy, cur.A.yy, cur.A.yz); U.n = v3<R>(cur.B(1, 0), cur.B(1, 1), cur.B(1, 2)); D = cur.A.yy; }
+    else { U.f = v3<R>(cur.B(0, 2), cur.B(1, 2), cur.B(2, 2)); U.n = v3<R>(cur.D.xz, cur.D.yz, cur.D.zz); D = cur.D.zz; }
+    const R Dinv = R(1) / D;
+    // Without bias terms pA is only what the children pushed down: nothing for the two leaves.
+    constexpr bool HAS_PA = BIAS || I < 10;
+    R u = tau[I] * M.sign[I];
+    if (HAS_PA) u -= joint_dot<R, T>(S.pA[I]);
+    S.U[I] = U; S.Dinv[I] = Dinv; S.u[I] = u;
+    if (P >= 0) {
+        Frc<R> UD; UD.f = U.f * Dinv; UD.n = U.n * Dinv;
+        Art<R> Ia = cur;
+        Ia.A.xx -= UD.f.x * U.f.x; Ia.A.xy -= UD.f.x * U.f.y; Ia.A.xz -= UD.f.x * U.f.z;
+        Ia.A.yy -= UD.f.y * U.f.y; Ia.A.yz -= UD.f.y * U.f.z; Ia.A.zz -= UD.f.z * U.f.z;
+        const R uf[3] = {UD.f.x, UD.f.y, UD.f.z}, un[3] = {U.n.x, U.n.y, U.n.z};
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int cc = 0; cc < 3; cc++) Ia.B(r, cc) -= uf[r] * un[cc];
+        Ia.D.xx -= UD.n.x * U.n.x; Ia.D.xy -= UD.n.x * U.n.y; Ia.D.xz -= UD.n.x * U.n.z;
+        Ia.D.yy -= UD.n.y * U.n.y; Ia.D.yz -= UD.n.y * U.n.z; Ia.D.zz -= UD.n.z * U.n.z;
+        // pa = pA + Ia c + UDinv u
+        Frc<R> pa;
+        pa.f = UD.f * u; pa.n = UD.n * u;
+        if (HAS_PA) { pa.f = pa.f + S.pA[I].f; pa.n = pa.n + S.pA[I].n; }
+        if (BIAS) {
+            Frc<R> ic = art_mul(Ia, S.c[I]);
+            pa.f = pa.f + ic.f; pa.n = pa.n + ic.n;
+        }
+        Frc<R> pp = act(S.li[I], pa);
+        constexpr int PP = P < 0 ? 0 : P;
+        // with bias terms every pA starts as v x* (Y v); without, the first child to arrive assigns
+        if (BIAS || I == 10) { S.pA[PP].f = S.pA[PP].f + pp.f; S.pA[PP].n = S.pA[PP].n + pp.n; }
+        else S.pA[PP] = pp;
+        // articulated inertia of the parent: its own body first (chain), or the collector (joint 9)
+        if (I == 11) { S.Ia9 = body_inertia(M, 9); art_transform_add(Ia, S.li[I], S.Ia9); }
+        else if (I == 10) { art_transform_add(Ia, S.li[I], S.Ia9); }
+        else { Art<R> next = body_inertia(M, PP); art_transform_add(Ia, S.li[I], next); cur = next; }
+    }
+}
+
+template <class R, int I, bool BIAS>
+MPPI_HD void aba_back_all(const RobotModel<R> &M, const R *tau, Scratch<R> &S, Art<R> &cur) {
+    if (I == 11 || I == 10) cur = body_inertia(M, I);
+    if (I == 9) cur = S.Ia9;
+    aba_back<R, I, BIAS>(M, tau, S, cur);
+    if (I > 0) aba_back_all<R, (I > 0 ? I - 1 : 0), BIAS>(M, tau, S, cur);
+}
+
+// ---- ABA forward pass ---------------------------------------------------------------------------
+template <class R, int I, bool BIAS>
+MPPI_HD void aba_fwd(const RobotModel<R> &M, Scratch<R> &S, Mot<R> *a, R *qdd) {
+    constexpr int P = Joint<I>::parent, T = Joint<I>::type;
+    Mot<R> ap;
+    if (P >= 0) ap = act_inv(S.li[I], a[P < 0 ? 0 : P]);
+    else if (BIAS) { ap.v = tmul(S.li[I].R_, v3<R>(R(0), R(0), M.gravity)); ap.w = v3<R>(R(0), R(0), R(0)); }
+    else { ap.v = v3<R>(R(0), R(0), R(0)); ap.w = ap.v; }
+    if (BIAS) { ap.v = ap.v + S.c[I].v; ap.w = ap.w + S.c[I].w; }
+    const R dd = S.Dinv[I] * (S.u[I] - (dot(S.U[I].f, ap.v) + dot(S.U[I].n, ap.w)));
+    qdd[I] = dd * M.sign[I];
+    a[I] = ap;
+    if (T == JT_PX) a[I].v.x += dd; else if (T == JT_PY) a[I].v.y += dd; else a[I].w.z += dd;
+    if (I + 1 < NJ) aba_fwd<R, (I + 1 < NJ ? I + 1 : I), BIAS>(M, S, a, qdd);
+}
+
+// ---- world kinematics for the objective ----------------------------------------------------------
+template <class R, int I, int FLAGS>
+MPPI_HD void world_chain(const RobotModel<R> &M, const Scratch<R> &S, Xf<R> &oM, Kinematics<R> &K, R *Jl /* 3 x 7 */) {
+    // oM enters as oMi[I-1], leaves as oMi[I]
+    if (I == 0) oM = S.li[0];
+    else {
+        Xf<R> n;
+        n.R_ = matmul(oM.R_, S.li[I].R_);
+        n.p = mul(oM.R_, S.li[I].p) + oM.p;
+        oM = n;
+    }
+    if ((FLAGS & KIN_MOUNT) && I == 2) K.mount_pos = mul(oM.R_, v3<R>(M.mount_p[0], M.mount_p[1], M.mount_p[2])) + oM.p;
+    if ((FLAGS & KIN_LINKS) && I >= 2) K.link_com[I - 2] = mul(oM.R_, v3<R>(M.com[I][0], M.com[I][1], M.com[I][2])) + oM.p;
+    if ((FLAGS & KIN_MANIP) && I >= 3) {  // WORLD jacobian column of a revolute joint: linear = p x z
+        const Vec3<R> z = v3<R>(oM.R_.m[2], oM.R_.m[5], oM.R_.m[8]);
+        const Vec3<R> l = cross(oM.p, z);
+        Jl[0 * 7 + (I - 3)] = l.x; Jl[1 * 7 + (I - 3)] = l.y; Jl[2 * 7 + (I - 3)] = l.z;
+    }
+    if (I == 9) {
+        K.ee_pos = mul(oM.R_, v3<R>(M.ee_p[0], M.ee_p[1], M.ee_p[2])) + oM.p;
+        if (FLAGS & KIN_VEL) K.ee_lin_vel = mul(oM.R_, S.v[9].v) + cross(oM.p, mul(oM.R_, S.v[9].w));
+    }
+    if (I < 9) world_chain<R, (I < 9 ? I + 1 : I), FLAGS>(M, S, oM, K, Jl);
+}
+
+// One PinocchioDynamics::calculate(): accelerations + the kinematics the objective will read.
+//   u      : generalised forces commanded by the control, tau = [0,0,0,u3..u9,0,0] (pinocchio_dynamics.cpp:238-239)
+//   FUSED  : a = M^-1 u
+//   NLE    : also produce nle(q, qd) (needed for tau^T v of the energy tank, or in FAITHFUL mode)
+template <class R, bool FAITHFUL, bool NLE, int FLAGS>
+MPPI_HD void robot_calculate(const RobotModel<R> &M, const R *q, const R *qd, const R *u, R *qdd, R *nle, Kinematics<R> &K) {
+    Scratch<R> S;
+    Mot<R> agf[NJ];
+    constexpr bool NEED_NLE = NLE || FAITHFUL;
+    constexpr bool VEL = NEED_NLE || (FLAGS & KIN_VEL);
+    pass1<R, 0, VEL, NEED_NLE, FAITHFUL>(M, q, qd, S, agf);
+    {
+        Xf<R> oM;
+        R Jl[21];
+        world_chain<R, 0, FLAGS>(M, S, oM, K, Jl);
+        if (FLAGS & KIN_MANIP) {
+            R g[6];  // J J^T, symmetric: 00 01 02 11 12 22
+            int n = 0;
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = r; c < 3; c++) {
+                    R s = R(0);
+#pragma unroll
+                    for (int j = 0; j < 7; j++) s += Jl[r * 7 + j] * Jl[c * 7 + j];
+                    g[n++] = s;
+                }
+            // determinant laid out like Eigen's 3x3 cofactor expansion along the first row
+            K.manip_det = g[0] * (g[3] * g[5] - g[4] * g[4]) - g[1] * (g[1] * g[5] - g[4] * g[2]) + g[2] * (g[1] * g[4] - g[3] * g[2]);
+        }
+    }
+    R tau[NJ];
+    if (NEED_NLE) rnea_back<R, NJ - 1>(M, S, nle);
+#pragma unroll
+    for (int i = 0; i < NJ; i++) tau[i] = FAITHFUL ? (u[i] + nle[i]) : u[i];
+    Art<R> cur;
+    aba_back_all<R, NJ - 1, FAITHFUL>(M, tau, S, cur);
+    Mot<R> a[NJ];
+    aba_fwd<R, 0, FAITHFUL>(M, S, a, qdd);
+}
+
+}  // namespace mppi_b200

@@ -1,0 +1,281 @@
+// One MPPI rollout, start to finish, for one thread: the T-step recurrence of
+// mppi::Trajectory::rollout(Rollout*, Dynamics*, Cost*) (reference src/controller/mppi.cpp:309-342)
+// with the objective (objective/track_point.cpp:10-174, objective/assisted_manipulation.cpp:37-319,
+// cost.hpp functors, energy.hpp tank) and the dynamics step (pinocchio_dynamics.cpp:226-260) fused
+// into straight-line code. Joint state, tank energy and the one-step-stale kinematics the costs
+// read stay in registers for the whole horizon; the only memory traffic is
+// the rollout's own noise row and the shared control / wrench tables.
+// Host/device: tests compile this for the CPU to check it against the oracle.
+#pragma once
+#include "robot.cuh"
+
+namespace mppi_b200 {
+
+template <class R> struct BarrierP { R bound, scale, maxc; };
+template <class R> struct QuadP { R c0, c1, c2; };
+
+// cost.hpp:25-31
+template <class R> MPPI_HD R quadratic(const QuadP<R> &c, R v) { return c.c0 + c.c1 * fabs_(v) + c.c2 * v * v; }
+// cost.hpp:57-62
+template <class R> MPPI_HD R right_barrier(const BarrierP<R> &b, R v) {
+    if (v >= b.bound) { const R d = v - b.bound; return b.maxc + b.scale * (d * d); }
+    return std_min(b.scale / (b.bound - v), b.maxc);
+}
+// cost.hpp:88-93
+template <class R> MPPI_HD R left_barrier(const BarrierP<R> &b, R v) {
+    if (v <= b.bound) { const R d = b.bound - v; return b.maxc + b.scale * (d * d); }
+    return std_min(b.scale / (v - b.bound), b.maxc);
+}
+
+// ---- objective parameter blocks in kernel arithmetic -----------------------------------------
+template <class R> struct ToyP { R target[2]; R qp, qv, qu; };
+
+template <class R> struct TrackPointP {
+    R point[3];
+    int joint_limits, self_collision, reach, link_mode;
+    BarrierP<R> collision_limit;
+    R radii[20];  // sum of the two sphere radii per checked pair
+    BarrierP<R> reach_limit;
+};
+
+template <class R> struct AssistedP {
+    int joint_limit, self_collision, workspace, energy, velocity, trajectory, manipulability, link_mode;
+    BarrierP<R> lower[12], upper[12];
+    BarrierP<R> collision_limit;
+    R radii[20];
+    BarrierP<R> ws_above, ws_infront, ws_reach;
+    QuadP<R> ws_yaw;
+    BarrierP<R> energy_below, energy_above;
+    R vel_quad[12];
+    R traj_scale, traj_max, traj_threshold, traj_vmin, traj_vmax, traj_dropoff;
+    QuadP<R> traj_position, traj_velocity, manip;
+};
+
+// pairs of Link enum values minus 3 (PIVOT = 0 ... PANDA_LINK7 = 7): track_point.cpp:81-118
+#define MPPI_PAIR_A(i) ((i) < 5 ? 0 : (i) < 10 ? 1 : (i) < 14 ? 2 : (i) < 17 ? 3 : (i) < 19 ? 4 : 5)
+#define MPPI_PAIR_B(i) ((i) < 5 ? 3 + (i) : (i) < 10 ? 3 + (i) - 5 : (i) < 14 ? 4 + (i) - 10 : (i) < 17 ? 5 + (i) - 14 : (i) < 19 ? 6 + (i) - 17 : 7)
+
+template <class R, bool FLIP> MPPI_HD R self_collision_cost(const BarrierP<R> &lim, const R *radii, int link_mode, const Kinematics<R> &K) {
+    R cost = R(0);
+#pragma unroll
+    for (int i = 0; i < 20; i++) {
+        R distance = R(0);
+        if (link_mode != 0) {
+            const Vec3<R> d = K.link_com[MPPI_PAIR_A(i)] - K.link_com[MPPI_PAIR_B(i)];
+            distance = sqrt_(dot(d, d));
+        }
+        // track_point.cpp:140 uses radii - distance, assisted_manipulation.cpp:149 distance - radii
+        cost += left_barrier(lim, FLIP ? radii[i] - distance : distance - radii[i]);
+    }
+    return cost;
+}
+
+enum Variant { VAR_TOY = 0, VAR_TP_LEAN = 1, VAR_TP_FULL = 2, VAR_AM = 3, VAR_AM_ENERGY = 4 };
+
+template <int VAR> struct VariantTraits {
+    static constexpr int kin = VAR == VAR_TP_LEAN ? 0 : (VAR == VAR_TP_FULL ? (KIN_MOUNT | KIN_LINKS) : (KIN_MOUNT | KIN_VEL | KIN_MANIP | KIN_LINKS));
+    static constexpr bool power = VAR == VAR_AM_ENERGY;
+};
+
+// kinematics only (PinocchioDynamics::set_state -> calculate(), the values the first cost evaluation reads)
+template <class R, int FLAGS> MPPI_HD void robot_kinematics(const RobotModel<R> &M, const R *q, const R *qd, Kinematics<R> &K) {
+    Scratch<R> S;
+    Mot<R> agf[1];
+    pass1<R, 0, (FLAGS & KIN_VEL) != 0, false, false>(M, q, qd, S, agf);
+    Xf<R> oM;
+    R Jl[21];
+    world_chain<R, 0, FLAGS>(M, S, oM, K, Jl);
+    if (FLAGS & KIN_MANIP) {
+        R g[6];
+        int n = 0;
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = r; c < 3; c++) {
+                R s = R(0);
+#pragma unroll
+                for (int j = 0; j < 7; j++) s += Jl[r * 7 + j] * Jl[c * 7 + j];
+                g[n++] = s;
+            }
+        K.manip_det = g[0] * (g[3] * g[5] - g[4] * g[4]) - g[1] * (g[1] * g[5] - g[4] * g[2]) + g[2] * (g[1] * g[4] - g[3] * g[2]);
+    }
+}
+
+// objective/track_point.cpp:10-79,120-174
+template <class R> MPPI_HD R track_point_cost(const TrackPointP<R> &P, const R *q, const Kinematics<R> &K) {
+    const Vec3<R> e = K.ee_pos - v3<R>(P.point[0], P.point[1], P.point[2]);
+    const R distance = sqrt_(dot(e, e));
+    R cost = R(100) * (distance * distance);
+    if (P.joint_limits) {
+        const R lo[10] = {R(-2.0), R(-2.0), R(-6.28), R(-2.8973), R(-1.7628), R(-2.8973), R(-3.0718), R(-2.8973), R(-0.0175), R(-2.8973)};
+        const R hi[10] = {R(2.0), R(2.0), R(6.28), R(2.8973), R(1.7628), R(2.8973), R(0.0698), R(2.8973), R(3.7525), R(2.8973)};
+        R c = R(0);
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            if (q[i] < lo[i]) { const R d = lo[i] - q[i]; c += R(1000) + R(100000) * (d * d); }
+            if (q[i] > hi[i]) { const R d = q[i] - hi[i]; c += R(1000) + R(100000) * (d * d); }
+        }
+        cost += c;
+    }
+    if (P.self_collision) cost += self_collision_cost<R, true>(P.collision_limit, P.radii, P.link_mode, K);
+    if (P.reach) {
+        R sy, cy;
+        sincos_(q[2], &sy, &cy);
+        const Vec3<R> robot = K.mount_pos + v3<R>(cy * R(0.3), sy * R(0.3), R(0.15));
+        const Vec3<R> d = K.ee_pos - robot;
+        cost += right_barrier(P.reach_limit, sqrt_(dot(d, d)));
+    }
+    return cost;
+}
+
+// objective/assisted_manipulation.cpp:37-319; bd (7 doubles) accumulates the per-term totals the
+// reference's logger reads after Trajectory::filter() (logging/assisted_manipulation.cpp:58-103).
+template <class R> MPPI_HD R assisted_cost(const AssistedP<R> &P, const R *q, const R *qd, R energy, const Kinematics<R> &K, const R *wrench, double *bd) {
+    R cost = R(0);
+    if (P.joint_limit) {
+        R c = R(0);
+#pragma unroll
+        for (int i = 0; i < NJ; i++) c += left_barrier(P.lower[i], q[i]) + right_barrier(P.upper[i], q[i]);
+        if (bd) bd[0] += (double)c;
+        cost += c;
+    }
+    if (P.self_collision) {
+        const R c = self_collision_cost<R, false>(P.collision_limit, P.radii, P.link_mode, K);
+        if (bd) bd[1] += (double)c;
+        cost += c;
+    }
+    if (P.workspace) {
+        R c = R(0);
+        R sy, cy;
+        sincos_(q[2], &sy, &cy);
+        const Vec3<R> fwd = v3<R>(cy, sy, R(0));
+        const Vec3<R> robot = K.mount_pos + v3<R>(cy * R(0.1), sy * R(0.1), R(0.15));
+        const Vec3<R> d = K.ee_pos - robot;
+        c += left_barrier(P.ws_infront, dot(d, fwd) / dot(fwd, fwd));
+        c += right_barrier(P.ws_reach, sqrt_(dot(d, d)));
+        const R n1 = sqrt_(d.x * d.x + d.y * d.y), n2 = sqrt_(fwd.x * fwd.x + fwd.y * fwd.y);
+        const R yaw = acos_((d.x * fwd.x + d.y * fwd.y) / n1 / n2);
+        if (!(yaw != yaw)) c += quadratic(P.ws_yaw, fabs_(yaw));
+        c += left_barrier(P.ws_above, K.ee_pos.z - robot.z);
+        if (bd) bd[2] += (double)c;
+        cost += c;
+    }
+    if (P.energy) {
+        const R c = left_barrier(P.energy_below, energy) + right_barrier(P.energy_above, energy);
+        if (bd) bd[3] += (double)c;
+        cost += c;
+    }
+    if (P.velocity) {
+        R c = R(0);
+#pragma unroll
+        for (int i = 0; i < NJ; i++) { const R a = fabs_(qd[i]); c += P.vel_quad[i] * (a * a); }
+        if (bd) bd[4] += (double)c;
+        cost += c;
+    }
+    if (P.trajectory && wrench) {
+        R c = R(0);
+        const Vec3<R> t = v3<R>(std_max(std_min(P.traj_scale * wrench[0], P.traj_max), -P.traj_max),
+                                std_max(std_min(P.traj_scale * wrench[1], P.traj_max), -P.traj_max),
+                                std_max(std_min(P.traj_scale * wrench[2], P.traj_max), -P.traj_max));
+        const R distance = sqrt_(dot(t, t));
+        if (distance > P.traj_threshold) {
+            c += quadratic(P.traj_position, distance);
+            R proj = dot(K.ee_lin_vel, t) / dot(t, t);
+            const Vec3<R> tp = t * proj;
+            proj = copysign_(R(1), proj) * sqrt_(dot(tp, tp));
+            const R target = std_clamp(exp_(P.traj_dropoff * distance) - R(1), P.traj_vmin, P.traj_vmax);
+            c += quadratic(P.traj_velocity, fabs_(target - proj));
+        }
+        if (bd) bd[5] += (double)c;
+        cost += c;
+    }
+    if (P.manipulability) {
+        R vol = sqrt_(K.manip_det);
+        if (vol != vol) vol = R(1e-5);
+        else vol = std_clamp(vol, R(1e-5), R(1e5));
+        const R c = quadratic(P.manip, R(1) / vol);
+        if (bd) bd[6] += (double)c;
+        cost += c;
+    }
+    return cost;
+}
+
+MPPI_HD double discount_pow(double g, int step) { return g == 1.0 ? 1.0 : pow(g, (double)step); }
+
+// Everything one rollout of the Franka+Ridgeback system needs that does not depend on the sample.
+template <class R> struct RolloutInputs {
+    const R *x0;      // 31: q, qd, wrench, tank energy (state.hpp:113-260)
+    const R *U;       // nu x T column-major: m_optimal_control_shifted
+    const R *W;       // T x 6 forecast wrench table, or nullptr (no forecast handle)
+    int T;
+    R dt;
+    double discount;
+};
+
+// VAR selects objective + which kinematics are alive; FAITHFUL selects the dynamics evaluation.
+// eps: this rollout's noise, [t][d]. Returns the rollout cost (NaN = failed rollout, mppi.cpp:331-334).
+template <class R, int VAR, bool FAITHFUL, class ParamsT>
+MPPI_HD double rollout_franka(const RobotModel<R> &M, const ParamsT &P, const RolloutInputs<R> &in, const R *eps, double *bd) {
+    constexpr int KF = VariantTraits<VAR>::kin;
+    constexpr bool POWER = VariantTraits<VAR>::power;
+    R q[NJ], qd[NJ];
+#pragma unroll
+    for (int i = 0; i < NJ; i++) { q[i] = in.x0[i]; qd[i] = in.x0[NJ + i]; }
+    R energy = in.x0[30];
+    Kinematics<R> K;
+    robot_kinematics<R, KF>(M, q, qd, K);
+    double total = 0.0;
+    for (int step = 0; step < in.T; ++step) {
+        R u[NJ];
+#pragma unroll
+        for (int d = 0; d < NJ; d++) u[d] = in.U[step * NJ + d] + eps[step * NJ + d];
+        R c;
+        if constexpr (VAR == VAR_TP_LEAN || VAR == VAR_TP_FULL) c = track_point_cost<R>(P, q, K);
+        else c = assisted_cost<R>(P, q, qd, energy, K, in.W ? in.W + step * 6 : nullptr, bd);
+        const double sc = discount_pow(in.discount, step) * (double)c;
+        if (sc != sc) return sc;  // NaN
+        total += sc;
+        if (step + 1 == in.T) break;  // the state after the last step is never costed (mppi.cpp:316-341)
+        // PinocchioDynamics::step, pinocchio_dynamics.cpp:226-260
+        R sy, cy;
+        sincos_(q[2], &sy, &cy);
+        qd[0] = cy * u[0] - sy * u[1];
+        qd[1] = sy * u[0] + cy * u[1];
+        qd[2] = u[2];
+        R tau[NJ], qdd[NJ], nle[NJ];
+#pragma unroll
+        for (int i = 0; i < NJ; i++) { tau[i] = (i >= 3 && i < 10) ? u[i] : R(0); nle[i] = R(0); }
+        robot_calculate<R, FAITHFUL, POWER, KF>(M, q, qd, tau, qdd, nle, K);
+#pragma unroll
+        for (int i = 0; i < NJ; i++) qd[i] += qdd[i] * in.dt;
+#pragma unroll
+        for (int i = 0; i < NJ; i++) q[i] += qd[i] * in.dt;
+        if (POWER) {
+            R p = R(0);
+#pragma unroll
+            for (int i = 0; i < NJ; i++) p += (tau[i] + nle[i]) * qd[i];
+            energy = std_max(R(0), energy + p * in.dt);  // energy.hpp:19-22
+        }
+    }
+    return total;
+}
+
+// toy double integrator (BASELINE.json config 1)
+template <class R>
+MPPI_HD double rollout_toy(const ToyP<R> &P, const R *x0, const R *U, const R *eps, int T, R dt, double discount) {
+    R px = x0[0], py = x0[1], vx = x0[2], vy = x0[3];
+    double total = 0.0;
+    for (int step = 0; step < T; ++step) {
+        const R ux = U[step * 2] + eps[step * 2], uy = U[step * 2 + 1] + eps[step * 2 + 1];
+        const R ex = px - P.target[0], ey = py - P.target[1];
+        const R c = P.qp * (ex * ex + ey * ey) + P.qv * (vx * vx + vy * vy) + P.qu * (ux * ux + uy * uy);
+        const double sc = discount_pow(discount, step) * (double)c;
+        if (sc != sc) return sc;
+        total += sc;
+        vx += ux * dt; vy += uy * dt;
+        px += vx * dt; py += vy * dt;
+    }
+    return total;
+}
+
+}  // namespace mppi_b200

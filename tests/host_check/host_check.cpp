@@ -1,0 +1,84 @@
+// TEST INFRASTRUCTURE — compiles the engine's host/device templates (csrc/robot.cuh,
+// objectives.cuh, rollout_core.cuh) for the CPU so their arithmetic can be checked against the
+// oracle without a GPU. Built by tests/test_device_math_host.py into tests/host_check/; the
+// product library (libmppi_b200.so) contains none of this and has no CPU path.
+#include <cstring>
+#include <vector>
+#include "model_init.h"
+#ifdef HAVE_ROLLOUT_CORE
+#include "rollout_core.cuh"
+#endif
+
+using namespace mppi_b200;
+
+template <class R, bool FAITHFUL, bool NLE>
+static void calc(const double *q, const double *qd, const double *u, double *qdd, double *nle, double *kin) {
+    static const RobotModel<R> M = make_robot_model<R>();
+    R q_[12], qd_[12], u_[12], qdd_[12], nle_[12];
+    for (int i = 0; i < 12; i++) { q_[i] = (R)q[i]; qd_[i] = (R)qd[i]; u_[i] = (R)u[i]; nle_[i] = 0; }
+    Kinematics<R> K;
+    robot_calculate<R, FAITHFUL, NLE, KIN_MOUNT | KIN_VEL | KIN_MANIP | KIN_LINKS>(M, q_, qd_, u_, qdd_, nle_, K);
+    for (int i = 0; i < 12; i++) { qdd[i] = qdd_[i]; nle[i] = nle_[i]; }
+    double *k = kin;
+    *k++ = K.ee_pos.x; *k++ = K.ee_pos.y; *k++ = K.ee_pos.z;
+    *k++ = K.mount_pos.x; *k++ = K.mount_pos.y; *k++ = K.mount_pos.z;
+    *k++ = K.ee_lin_vel.x; *k++ = K.ee_lin_vel.y; *k++ = K.ee_lin_vel.z;
+    *k++ = K.manip_det;
+    for (int l = 0; l < 8; l++) { *k++ = K.link_com[l].x; *k++ = K.link_com[l].y; *k++ = K.link_com[l].z; }
+}
+
+extern "C" {
+// mode: bit0 = FAITHFUL, bit1 = NLE requested, bit2 = float
+void host_robot_calculate(int mode, const double *q, const double *qd, const double *u, double *qdd, double *nle, double *kin34) {
+    switch (mode) {
+        case 0: calc<double, false, false>(q, qd, u, qdd, nle, kin34); break;
+        case 1: calc<double, true, true>(q, qd, u, qdd, nle, kin34); break;
+        case 2: calc<double, false, true>(q, qd, u, qdd, nle, kin34); break;
+        case 4: calc<float, false, false>(q, qd, u, qdd, nle, kin34); break;
+        case 5: calc<float, true, true>(q, qd, u, qdd, nle, kin34); break;
+        case 6: calc<float, false, true>(q, qd, u, qdd, nle, kin34); break;
+    }
+}
+int host_topology_matches() { std::string w; return topology_matches(&w) ? 1 : 0; }
+}
+
+// ---- whole rollouts ------------------------------------------------------------------------------
+#include "params_convert.h"
+#include "rollout_core.cuh"
+
+template <class R, int VAR, bool FAITHFUL, class CP>
+static void run_rollouts(const CP &cp, const double *x0, const double *U, const double *W, const double *eps, int K, int T, double dt, double discount, double *costs, double *bd) {
+    static const RobotModel<R> M = make_robot_model<R>();
+    auto P = convert<R>(cp);
+    std::vector<R> x(31), u((size_t)12 * T), w, e((size_t)12 * T);
+    for (int i = 0; i < 31; i++) x[i] = (R)x0[i];
+    for (size_t i = 0; i < u.size(); i++) u[i] = (R)U[i];
+    if (W) { w.resize((size_t)6 * T); for (size_t i = 0; i < w.size(); i++) w[i] = (R)W[i]; }
+    RolloutInputs<R> in{x.data(), u.data(), W ? w.data() : nullptr, T, (R)dt, discount};
+    for (int k = 0; k < K; k++) {
+        for (size_t i = 0; i < e.size(); i++) e[i] = (R)eps[(size_t)k * 12 * T + i];
+        costs[k] = rollout_franka<R, VAR, FAITHFUL>(M, P, in, e.data(), bd);
+    }
+}
+
+extern "C" {
+// objective: 1 track point, 2 assisted manipulation; flags: bit0 FAITHFUL, bit2 float
+void host_rollouts(int objective, int flags, const void *params, const double *x0, const double *U, const double *W, const double *eps, int K, int T,
+                   double dt, double discount, double *costs, double *bd7) {
+    const bool faithful = flags & 1, f32 = flags & 4;
+#define RUN(R, VAR, CP) do { if (faithful) run_rollouts<R, VAR, true>(CP, x0, U, W, eps, K, T, dt, discount, costs, bd7); \
+                             else run_rollouts<R, VAR, false>(CP, x0, U, W, eps, K, T, dt, discount, costs, bd7); } while (0)
+    if (objective == 1) {
+        const auto &cp = *static_cast<const mppi_b200_track_point *>(params);
+        int var = variant_for(cp);
+        if (f32) { if (var == VAR_TP_LEAN) RUN(float, VAR_TP_LEAN, cp); else RUN(float, VAR_TP_FULL, cp); }
+        else { if (var == VAR_TP_LEAN) RUN(double, VAR_TP_LEAN, cp); else RUN(double, VAR_TP_FULL, cp); }
+    } else {
+        const auto &cp = *static_cast<const mppi_b200_assisted_manipulation *>(params);
+        int var = variant_for(cp);
+        if (f32) { if (var == VAR_AM) RUN(float, VAR_AM, cp); else RUN(float, VAR_AM_ENERGY, cp); }
+        else { if (var == VAR_AM) RUN(double, VAR_AM, cp); else RUN(double, VAR_AM_ENERGY, cp); }
+    }
+#undef RUN
+}
+}
