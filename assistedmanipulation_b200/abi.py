@@ -90,7 +90,9 @@ EXPORTS = [
     "mppi_b200_comm_unique_id", "mppi_b200_comm_init", "mppi_b200_get", "mppi_b200_read",
     "mppi_b200_query", "mppi_b200_last_update_device_seconds", "mppi_b200_default_track_point",
     "mppi_b200_default_assisted_manipulation", "mppi_b200_default_toy_objective",
+    "mppi_b200_set_profiling", "mppi_b200_stage_seconds", "mppi_b200_measure_fma_peak",
 ]
+STAGES = ("h2d", "warm_start_shift", "sample", "rollout", "weights", "weighted_sum", "finish", "d2h")
 
 _dp = C.POINTER(C.c_double)
 
@@ -137,6 +139,12 @@ def load_library(path=None):
     lib.mppi_b200_query.restype = C.c_int
     lib.mppi_b200_last_update_device_seconds.argtypes = [C.c_void_p, _dp]
     lib.mppi_b200_last_update_device_seconds.restype = C.c_int
+    lib.mppi_b200_set_profiling.argtypes = [C.c_void_p, C.c_int32]
+    lib.mppi_b200_set_profiling.restype = C.c_int
+    lib.mppi_b200_stage_seconds.argtypes = [C.c_void_p, _dp, C.c_size_t]
+    lib.mppi_b200_stage_seconds.restype = C.c_int
+    lib.mppi_b200_measure_fma_peak.argtypes = [C.c_int32, C.c_int32, _dp]
+    lib.mppi_b200_measure_fma_peak.restype = C.c_int
     lib.mppi_b200_default_track_point.argtypes = [C.POINTER(TrackPoint)]
     lib.mppi_b200_default_assisted_manipulation.argtypes = [C.POINTER(AssistedManipulation)]
     lib.mppi_b200_default_toy_objective.argtypes = [C.POINTER(ToyObjective)]

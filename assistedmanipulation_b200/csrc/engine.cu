@@ -114,8 +114,9 @@ struct mppi_b200_engine {
     bool side_pending = false;
     // host mirrors (pinned)
     unsigned char *h_frame = nullptr;  // Frame + wrench
-    double *h_U = nullptr;             // nu*T
-    double *h_stats = nullptr;         // minmax[3], argmin (as double bits), optimal cost, breakdown[8]
+    double *h_U = nullptr;             // nu*T (stable copy of the published sequence for get())
+    double *h_result = nullptr;        // host-mapped block k_finish writes: U, {-min,max,valid}, argmin, sum w
+    double *h_stats = nullptr;         // {-min,max,valid}, argmin bits, sum w, -, optimal cost, breakdown[8]
     size_t frame_bytes = 0;
     // device allocations
     std::vector<void *> allocs;
@@ -135,12 +136,18 @@ struct mppi_b200_engine {
     ncclComm_t comm = nullptr;
     std::string error;
     float last_ms = 0.f;
+    bool profiling = false;
+    double weights_total = 1.0;
+    bool weights_valid = false;
+    cudaEvent_t ev_stage[MPPI_B200_STAGES + 1] = {};
+    double stage_s[MPPI_B200_STAGES] = {};
 };
 
 namespace {
 
 int fail_create(int code, const std::string &why) { g_create_error = why; return code; }
 int fail(mppi_b200_engine *e, int code, const std::string &why) { e->error = why; return code; }
+#define STAGE(e, i) do { if ((e)->profiling) cudaEventRecord((e)->ev_stage[i], (e)->stream); } while (0)
 #define CUDA_TRY(e, call) do { cudaError_t _c = (call); if (_c != cudaSuccess) return fail((e), MPPI_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_c)); } while (0)
 
 template <class T> T *dev_alloc(mppi_b200_engine *e, size_t count, bool zero = true) {
@@ -172,8 +179,10 @@ void mppi_b200_destroy(mppi_b200_engine *e) {
     for (void *p : e->allocs) cudaFree(p);
     if (e->h_frame) cudaFreeHost(e->h_frame);
     if (e->h_U) cudaFreeHost(e->h_U);
+    if (e->h_result) cudaFreeHost(e->h_result);
     if (e->h_stats) cudaFreeHost(e->h_stats);
     for (cudaEvent_t ev : {e->ev_start, e->ev_end, e->ev_main_done, e->ev_side_done}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->ev_stage) if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->side) cudaStreamDestroy(e->side);
     delete e;
@@ -206,7 +215,7 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     const int T = (int)std::ceil(c->horison / c->time_step);  // mppi.cpp:85
     const int vec = c->precision == MPPI_B200_FP64 ? 2 : 4;
     if ((nu * T) % vec != 0) return fail_create(MPPI_B200_ERR_UNSUPPORTED, "control_dof * steps must be a multiple of " + std::to_string(vec));
-    if (c->system == MPPI_B200_SYSTEM_FRANKA_RIDGEBACK) { std::string why; if (!topology_matches(&why)) return fail_create(MPPI_B200_ERR_INVALID, "robot model: " + why); }
+    if (c->system == MPPI_B200_SYSTEM_FRANKA_RIDGEBACK) { std::string why; if (!topology_matches(&why) || !fast_structure_matches(&why)) return fail_create(MPPI_B200_ERR_INVALID, "robot model: " + why); }
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail_create(MPPI_B200_ERR_CUDA, "no CUDA device (this engine has no CPU fallback)");
@@ -264,6 +273,9 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     CREATE_TRY(cudaMallocHost(&e->h_frame, e->frame_bytes));
     CREATE_TRY(cudaMallocHost(&e->h_U, n * sizeof(double)));
     CREATE_TRY(cudaMallocHost(&e->h_stats, 16 * sizeof(double)));
+    CREATE_TRY(cudaHostAlloc(&e->h_result, (n + 8) * sizeof(double), cudaHostAllocMapped));
+    std::memset(e->h_result, 0, (n + 8) * sizeof(double));
+    CREATE_TRY(cudaHostGetDevicePointer((void **)&d.result, e->h_result, 0));
     std::memset(e->h_frame, 0, e->frame_bytes);
     std::memset(e->h_U, 0, n * sizeof(double));
     std::memset(e->h_stats, 0, 16 * sizeof(double));
@@ -294,6 +306,8 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     if (!ok) return bail(MPPI_B200_ERR_CUDA, "device allocation failed");
 
     const std::vector<double> L = noise_transform(nu, c->covariance);
+    d.L_is_diagonal = 1;
+    for (int cc = 0; cc < nu; cc++) for (int r = 0; r < nu; r++) { if (r != cc && L[(size_t)cc * nu + r] != 0.0) d.L_is_diagonal = 0; if (r == cc) d.Ldiag[r] = L[(size_t)cc * nu + r]; }
     CREATE_TRY(cudaMemcpy(d.L, L.data(), L.size() * sizeof(double), cudaMemcpyHostToDevice));
     if (c->smoothing) {
         const std::vector<double> w = sg_weights(d.sg_window, (int)c->smoothing_order);
@@ -330,6 +344,7 @@ int mppi_b200_update_begin(mppi_b200_engine *e, const double *state, double time
     if (wrench) std::memcpy(e->h_frame + sizeof(Frame), wrench, sizeof(double) * 6 * d.T);
 
     CUDA_TRY(e, cudaEventRecord(e->ev_start, e->stream));
+    STAGE(e, 0);
     CUDA_TRY(e, cudaMemcpyAsync(e->d_frame, e->h_frame, e->frame_bytes, cudaMemcpyHostToDevice, e->stream));
     const int prec = e->cfg.precision;
     if (noise_source == MPPI_B200_NOISE_HOST) {
@@ -344,10 +359,14 @@ int mppi_b200_update_begin(mppi_b200_engine *e, const double *state, double time
         d.injected = nullptr; d.injected_is_double = 0;
     }
     int launches = 0;
+    STAGE(e, 1);
     if (d.keep_best > 0) { CUDA_TRY(e, launch_select_kept(d, e->stream)); launches++; }
     CUDA_TRY(e, launch_prepare(d, prec, e->stream)); launches++;
+    STAGE(e, 2);
     CUDA_TRY(e, launch_sample(d, prec, e->stream, &launches));
+    STAGE(e, 3);
     CUDA_TRY(e, launch_rollout(d, prec, e->variant, e->faithful, e->params.data(), false, e->stream)); launches++;
+    STAGE(e, 4);
     CUDA_TRY(e, launch_minmax_publish(d, e->stream)); launches++;
     e->launches += launches;
     e->in_update = true;
@@ -359,6 +378,7 @@ int mppi_b200_update_weights(mppi_b200_engine *e) {
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     int launches = 1;
     CUDA_TRY(e, launch_weights(e->d, e->stream));
+    STAGE(e, 5);
     CUDA_TRY(e, launch_gradient(e->d, e->cfg.precision, e->stream, &launches));
     e->launches += launches;
     return MPPI_B200_OK;
@@ -369,12 +389,13 @@ int mppi_b200_update_finish(mppi_b200_engine *e) {
     DeviceState &d = e->d;
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     const size_t n = (size_t)d.nu * d.T;
+    STAGE(e, 6);
     CUDA_TRY(e, launch_finish(d, e->stream));
     e->launches += 1;
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_U, d.U, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_stats, d.minmax, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 4, d.argmin, sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
+    STAGE(e, 7);
+    // k_finish wrote the control sequence and the update's scalars straight into host-mapped memory
     CUDA_TRY(e, cudaEventRecord(e->ev_end, e->stream));
+    STAGE(e, 8);
     // Optimal re-rollout (Trajectory::filter, mppi.cpp:450-479) off the critical path: with no
     // mppi::Filter attached (actor.cpp:100) it only produces the optimal cost and its per-term
     // breakdown, so it runs on a side stream over a snapshot of this update's inputs.
@@ -391,19 +412,25 @@ int mppi_b200_update_finish(mppi_b200_engine *e) {
         o.noise = e->d_zero_row;
         CUDA_TRY(e, launch_rollout(o, e->cfg.precision, e->variant, e->faithful, e->params.data(), true, e->side));
         e->launches += 1;
-        CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 5, d.optimal_cost, sizeof(double), cudaMemcpyDeviceToHost, e->side));
-        CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 6, d.breakdown, 8 * sizeof(double), cudaMemcpyDeviceToHost, e->side));
+        CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 6, d.optimal_cost, sizeof(double), cudaMemcpyDeviceToHost, e->side));
+        CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 7, d.breakdown, 8 * sizeof(double), cudaMemcpyDeviceToHost, e->side));
         CUDA_TRY(e, cudaEventRecord(e->ev_side_done, e->side));
         e->side_pending = true;
     }
     CUDA_TRY(e, cudaEventSynchronize(e->ev_end));
     cudaEventElapsedTime(&e->last_ms, e->ev_start, e->ev_end);
+    if (e->profiling) {
+        for (int i = 0; i < MPPI_B200_STAGES; i++) { float ms = 0.f; cudaEventElapsedTime(&ms, e->ev_stage[i], e->ev_stage[i + 1]); e->stage_s[i] = ms * 1e-3; }
+    }
     e->in_update = false;
     // mppi.cpp:368-370: no (or a single) valid rollout is an error; nothing is published
+    std::memcpy(e->h_stats, e->h_result + n, 5 * sizeof(double));   // {-min, max, valid}, argmin, sum w
     if (!(e->h_stats[2] >= 2.0)) {
         return fail(e, MPPI_B200_ERR_ALL_NAN, "all nan rollouts");
     }
-    std::memcpy(&e->argmin, e->h_stats + 4, sizeof(long long));
+    std::memcpy(e->h_U, e->h_result, n * sizeof(double));
+    std::memcpy(&e->argmin, e->h_stats + 3, sizeof(long long));
+    if (!(e->h_stats[1] + e->h_stats[0] < 1e-6)) { e->weights_total = e->h_stats[4]; e->weights_valid = true; }  // early return leaves the weights untouched
     if (d.sg_enabled && !(e->h_stats[1] + e->h_stats[0] < 1e-6)) e->sg_last_trim = reinterpret_cast<Frame *>(e->h_frame)->time;
     e->last_rollout_time = reinterpret_cast<Frame *>(e->h_frame)->time;
     e->update_count++;
@@ -498,7 +525,16 @@ int mppi_b200_read(mppi_b200_engine *e, int32_t what, void *dst, size_t bytes) {
     switch (what) {
         case MPPI_B200_READ_OPTIMAL: if (!need(n * 8)) break; std::memcpy(dst, e->h_U, bytes); return MPPI_B200_OK;
         case MPPI_B200_READ_COSTS: if (!need(K * 8)) break; CUDA_TRY(e, cudaMemcpy(dst, d.costs, bytes, cudaMemcpyDeviceToHost)); return MPPI_B200_OK;
-        case MPPI_B200_READ_WEIGHTS: if (!need(K * 8)) break; CUDA_TRY(e, cudaMemcpy(dst, d.weights, bytes, cudaMemcpyDeviceToHost)); return MPPI_B200_OK;
+        case MPPI_B200_READ_WEIGHTS: {
+            // the device keeps exp(-cost_scale (c - min)/(max - min)); the division by the total of
+            // mppi.cpp:403-408 is applied here (the weighted sum divides once, in k_finish)
+            if (!need(K * 8)) break;
+            CUDA_TRY(e, cudaMemcpy(dst, d.weights, bytes, cudaMemcpyDeviceToHost));
+            double *w = static_cast<double *>(dst);
+            const double total = e->weights_total;
+            if (e->weights_valid) for (size_t i = 0; i < K; i++) w[i] = w[i] / total;
+            return MPPI_B200_OK;
+        }
         case MPPI_B200_READ_GRADIENT: if (!need(n * 8)) break; CUDA_TRY(e, cudaMemcpy(dst, d.gradient, bytes, cudaMemcpyDeviceToHost)); return MPPI_B200_OK;
         case MPPI_B200_READ_NOISE: {
             if (!need(K * n * 8)) break;
@@ -510,8 +546,8 @@ int mppi_b200_read(mppi_b200_engine *e, int32_t what, void *dst, size_t bytes) {
             return MPPI_B200_OK;
         }
         case MPPI_B200_READ_MINMAX: if (!need(16)) break; static_cast<double *>(dst)[0] = -e->h_stats[0]; static_cast<double *>(dst)[1] = e->h_stats[1]; return MPPI_B200_OK;
-        case MPPI_B200_READ_OPTIMAL_COST: if (!need(8)) break; static_cast<double *>(dst)[0] = e->h_stats[5]; return MPPI_B200_OK;
-        case MPPI_B200_READ_BREAKDOWN: if (!need(64)) break; std::memcpy(dst, e->h_stats + 6, 64); return MPPI_B200_OK;
+        case MPPI_B200_READ_OPTIMAL_COST: if (!need(8)) break; static_cast<double *>(dst)[0] = e->h_stats[6]; return MPPI_B200_OK;
+        case MPPI_B200_READ_BREAKDOWN: if (!need(64)) break; std::memcpy(dst, e->h_stats + 7, 64); return MPPI_B200_OK;
         case MPPI_B200_READ_KEPT: {
             const size_t k = bytes / 8;
             if (bytes % 8 || k > (size_t)d.keep_best) break;
@@ -537,6 +573,29 @@ int mppi_b200_query(mppi_b200_engine *e, int32_t what, int64_t *value) {
         case MPPI_B200_QUERY_CONTROL_DOF: *value = e->d.nu; return 0;
     }
     return MPPI_B200_ERR_INVALID;
+}
+
+int mppi_b200_set_profiling(mppi_b200_engine *e, int32_t enabled) {
+    if (!e) return MPPI_B200_ERR_INVALID;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    if (enabled) for (cudaEvent_t &ev : e->ev_stage) if (!ev) CUDA_TRY(e, cudaEventCreate(&ev));
+    e->profiling = enabled != 0;
+    return MPPI_B200_OK;
+}
+
+int mppi_b200_stage_seconds(mppi_b200_engine *e, double *seconds, size_t count) {
+    if (!e || !seconds || count != MPPI_B200_STAGES) return MPPI_B200_ERR_INVALID;
+    std::memcpy(seconds, e->stage_s, sizeof e->stage_s);
+    return MPPI_B200_OK;
+}
+
+int mppi_b200_measure_fma_peak(int32_t device, int32_t precision, double *tflops) {
+    if (!tflops) return MPPI_B200_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return MPPI_B200_ERR_CUDA;
+    double v = 0.0;
+    if (measure_fma_peak(precision, &v) != cudaSuccess) return MPPI_B200_ERR_CUDA;
+    *tflops = v;
+    return MPPI_B200_OK;
 }
 
 int mppi_b200_last_update_device_seconds(mppi_b200_engine *e, double *seconds) {

@@ -129,7 +129,7 @@ __global__ void k_select_kept(const __grid_constant__ DeviceState d) {
 // One thread per (rollout, step) column. Fresh columns are eps = L z (z ~ N(0, I) from Philox, or the
 // injected buffer); kept rollouts first move their surviving columns left by shift_by.
 // In-place shift is safe because a kept row is processed by ONE block that stages it in shared memory.
-template <class R, class RI> __device__ __forceinline__ void fresh_column(const DeviceState &d, long long kg, int t, R *dst) {
+template <class R, class RI> __device__ __forceinline__ void fresh_column(const DeviceState &d, const double *sL, long long kg, int t, R *dst) {
     const int nu = d.nu;
     if (d.frame->noise_source != 0) {
         const RI *src = static_cast<const RI *>(d.injected) + ((size_t)(kg - d.k_begin) * d.T + t) * nu;
@@ -148,9 +148,14 @@ template <class R, class RI> __device__ __forceinline__ void fresh_column(const 
             box_muller(r.z, r.w, &z[4 * b + 2], &z[4 * b + 3]);
         }
     }
+    if (d.L_is_diagonal) {
+#pragma unroll
+        for (int i = 0; i < MAX_NU; i++) if (i < nu) dst[i] = (R)(d.Ldiag[i] * (double)z[i]);
+        return;
+    }
     for (int i = 0; i < nu; i++) {
         double s = 0.0;
-        for (int j = 0; j < nu; j++) s += d.L[j * nu + i] * (double)z[j];
+        for (int j = 0; j < nu; j++) s += sL[j * nu + i] * (double)z[j];
         dst[i] = (R)s;
     }
 }
@@ -160,6 +165,8 @@ template <class R, class RI> __global__ void __launch_bounds__(256) k_sample(con
     // builds its column in shared memory, then the block streams the span out with 16-byte stores.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *tile = reinterpret_cast<R *>(smem_raw);
+    __shared__ double sL[MAX_NU * MAX_NU];
+    if (!d.L_is_diagonal) { for (int i = threadIdx.x; i < d.nu * d.nu; i += blockDim.x) sL[i] = d.L[i]; __syncthreads(); }
     const long long col0 = (long long)blockIdx.x * blockDim.x;
     const long long col = col0 + threadIdx.x;   // local column index
     const long long ncols = d.k_count * d.T;
@@ -173,7 +180,7 @@ template <class R, class RI> __global__ void __launch_bounds__(256) k_sample(con
         if (kg < 2 || d.kept[kl]) {   // static rollouts (k_prepare) and kept rollouts (k_shift_kept) keep their values
             for (int i = 0; i < nu; i++) v[i] = noise[(size_t)col * nu + i];
         } else {
-            fresh_column<R, RI>(d, kg, t, v);
+            fresh_column<R, RI>(d, sL, kg, t, v);
         }
         for (int i = 0; i < nu; i++) tile[threadIdx.x * nu + i] = v[i];
     }
@@ -195,8 +202,10 @@ template <class R, class RI> __global__ void __launch_bounds__(256) k_sample(con
 template <class R, class RI> __global__ void k_shift_kept(const __grid_constant__ DeviceState d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *row = reinterpret_cast<R *>(smem_raw);
+    __shared__ double sL[MAX_NU * MAX_NU];
     const long long shift = d.frame->shift_by;
     if (shift <= 0) return;
+    for (int i = threadIdx.x; i < d.nu * d.nu; i += blockDim.x) sL[i] = d.L[i];
     const long long kg = d.kept_list[blockIdx.x];
     const long long kl = kg - d.k_begin;
     if (kl < 0 || kl >= d.k_count) return;
@@ -210,7 +219,7 @@ template <class R, class RI> __global__ void k_shift_kept(const __grid_constant_
             for (int i = 0; i < d.nu; i++) noise[t * d.nu + i] = row[(t + shift) * d.nu + i];
         } else {
             R v[MAX_NU];
-            fresh_column<R, RI>(d, kg, t, v);
+            fresh_column<R, RI>(d, sL, kg, t, v);
             for (int i = 0; i < d.nu; i++) noise[t * d.nu + i] = v[i];
         }
     }
@@ -296,20 +305,40 @@ template <class R> __global__ void __launch_bounds__(512) k_gradient(const __gri
     }
 }
 
-// fixed-order combination of the partials into the exchange buffer sums = {sum w, sum w*eps}
+// fixed-order combination of the partials into the exchange buffer sums = {sum w, sum w*eps}.
+// Block = 32 elements x 8 slices of the partial rows; slice sums are combined in slice order.
 __global__ void __launch_bounds__(256) k_gradient_reduce(const __grid_constant__ DeviceState d) {
+    __shared__ double part[8][33];
     if (*d.skip) return;
     const int n = d.nu * d.T;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + lane;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (e < n) {
-        double s = 0.0;
-        for (int b = 0; b < d.grad_blocks; b++) s += d.grad_partial[(size_t)b * n + e];
+        int b = slice;
+        for (; b + 24 < d.grad_blocks; b += 32) {
+            s0 += d.grad_partial[(size_t)b * n + e];
+            s1 += d.grad_partial[(size_t)(b + 8) * n + e];
+            s2 += d.grad_partial[(size_t)(b + 16) * n + e];
+            s3 += d.grad_partial[(size_t)(b + 24) * n + e];
+        }
+        for (; b < d.grad_blocks; b += 8) s0 += d.grad_partial[(size_t)b * n + e];
+    }
+    part[slice][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (slice == 0 && e < n) {
+        double s = part[0][lane];
+#pragma unroll
+        for (int i = 1; i < 8; i++) s += part[i][lane];
         d.sums[1 + e] = s;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        // sum of the weights: warp-strided partial sums, then a fixed-order shuffle tree
         double s = 0.0;
-        for (int b = 0; b < d.weight_blocks; b++) s += d.wsum_partial[b];
-        d.sums[0] = s;
+        for (int b = threadIdx.x; b < d.weight_blocks; b += 32) s += d.wsum_partial[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) d.sums[0] = s;
     }
 }
 
@@ -327,36 +356,42 @@ __device__ __forceinline__ int sg_lower_bound(const double *tt, int len, double 
 
 __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ DeviceState d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *uu = reinterpret_cast<double *>(smem_raw);  // nu x Lw
-    double *tt = uu + d.nu * d.sg_len;                   // nu x Lw
+    double *sU = reinterpret_cast<double *>(smem_raw);   // nu*T working copy of m_optimal_control_shifted
+    double *uu = sU + d.nu * d.T;                          // nu x Lw
+    double *tt = uu + d.nu * d.sg_len;                     // nu x Lw
+    double *sw = tt + d.nu * d.sg_len;                     // 2w+1 taps
     const int n = d.nu * d.T;
     const int skip = *d.skip;
-    if (!(d.minmax[2] >= 2.0)) return;  // "all nan rollouts" (mppi.cpp:368-370): the reference throws before publishing
-    if (!skip) {
-        const double total = d.sums[0];
-        for (int e = threadIdx.x; e < n; e += blockDim.x) {
-            const double g = d.sums[1 + e] / total;
-            d.gradient[e] = g;
-            d.U_shift[e] += g * d.gradient_step;
-        }
-        // normalise the weights (std::transform, mppi.cpp:403-408)
-        for (long long k = threadIdx.x; k < d.k_count; k += blockDim.x) d.weights[k] = d.weights[k] / total;
+    const bool dead = !(d.minmax[2] >= 2.0);  // "all nan rollouts" (mppi.cpp:368-370): the reference throws before publishing
+    if (threadIdx.x == 0) {
+        d.result[n + 0] = d.minmax[0]; d.result[n + 1] = d.minmax[1]; d.result[n + 2] = d.minmax[2];
+        d.result[n + 3] = __longlong_as_double(*d.argmin);
+        d.result[n + 4] = d.sums[0];
     }
-    __syncthreads();
+    if (dead) return;
+    const double total = d.sums[0];
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        double u = d.U_shift[e];
+        if (!skip) {
+            const double g = d.sums[1 + e] / total;   // weights are normalised by the total (mppi.cpp:403-408)
+            d.gradient[e] = g;
+            u += g * d.gradient_step;
+        }
+        sU[e] = u;
+    }
     if (!skip && d.sg_enabled) {
         const int Lw = d.sg_len, w = d.sg_window;
         for (int i = threadIdx.x; i < d.nu * Lw; i += blockDim.x) { uu[i] = d.sg_uu[i]; tt[i] = d.sg_tt[i]; }
+        for (int i = threadIdx.x; i < 2 * w + 1; i += blockDim.x) sw[i] = d.sg_weights[i];
         __syncthreads();
         if (threadIdx.x < d.nu) {
             double *u = uu + threadIdx.x * Lw, *tm = tt + threadIdx.x * Lw;
             const double t0 = d.frame->time;
-            // trim(t0): filter.cpp:34-67. start_idx is always w + T after a full update, or w initially.
+            // trim(t0): filter.cpp:34-67. start_idx is w before the first pass and w + T after any pass.
             const int start_idx = *d.sg_started ? w + d.T : w;
             int trim_idx = start_idx;
             for (int i = 0; i < start_idx; i++) if (tm[i] >= t0) { trim_idx = i; break; }
-            // rotate left by (trim_idx - w) as size_t arithmetic would: negative offsets wrap in the
-            // reference (UB there); we rotate modulo Lw which is what std::rotate does for in-range values
-            int offset = trim_idx - w;
+            const int offset = trim_idx - w;
             if (offset > 0) {
                 // rotate left by offset, then refill the vacated tail with the last valid sample
                 for (int i = 0; i + offset < Lw; i++) { u[i] = u[i + offset]; tm[i] = tm[i + offset]; }
@@ -364,20 +399,22 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ DeviceSt
                 for (int i = Lw - offset; i < Lw; i++) { u[i] = lu; tm[i] = lt; }
             }
             tm[w] = t0;
-            // add_measurement x T (filter.cpp:69-90): final state = samples in [w, w+T), copies of the last beyond
-            // times are compared with == / >= later: no FMA contraction, exactly m_rollout_time + i * m_time_step (mppi.cpp:430)
-            for (int i = 0; i < d.T; i++) { u[w + i] = d.U_shift[i * d.nu + threadIdx.x]; tm[w + i] = __dadd_rn(t0, __dmul_rn((double)i, d.dt)); }
+            // add_measurement x T (filter.cpp:69-90): final state = samples in [w, w+T), copies of the last beyond.
+            // Times are compared with == / >= later: no FMA contraction, exactly m_rollout_time + i * m_time_step (mppi.cpp:430).
+            for (int i = 0; i < d.T; i++) { u[w + i] = sU[i * d.nu + threadIdx.x]; tm[w + i] = __dadd_rn(t0, __dmul_rn((double)i, d.dt)); }
             for (int i = w + d.T; i < Lw; i++) { u[i] = u[w + d.T - 1]; tm[i] = tm[w + d.T - 1]; }
-            // apply x T (filter.cpp:163-173): filtered value written ONE SLOT EARLIER than the sample
+            // apply x T (filter.cpp:163-173): the filtered value is written ONE SLOT EARLIER than the sample
             for (int i = 0; i < d.T; i++) {
                 const double t = __dadd_rn(t0, __dmul_rn((double)i, d.dt));
-                const int idx = sg_lower_bound(tm, Lw, t);
+                // std::lower_bound over the (sorted) times; the common answer w + i is verified, else searched
+                int idx = w + i;
+                if (!(tm[idx] >= t && tm[idx - 1] < t)) idx = sg_lower_bound(tm, Lw, t);
                 const double *v = u + idx - w;
-                double res = d.sg_weights[0] * v[0];
-                for (int j = 1; j < 2 * w + 1; j++) res += d.sg_weights[j] * v[j];
-                res = res / 1.0;
-                u[sg_lower_bound(tm, Lw, t) - 1] = res;
-                d.U_shift[i * d.nu + threadIdx.x] = res;
+                double res = sw[0] * v[0];
+#pragma unroll 4
+                for (int j = 1; j < 2 * w + 1; j++) res += sw[j] * v[j];
+                u[idx - 1] = res;
+                sU[i * d.nu + threadIdx.x] = res;
             }
         }
         __syncthreads();
@@ -386,16 +423,62 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ DeviceSt
     }
     __syncthreads();
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
-        double u = d.U_shift[e];
+        double u = sU[e];
         if (!skip && d.bound) {
             const int dd = e % d.nu;
-            // cwiseMin(max).cwiseMax(min), mppi.cpp:443-447
-            u = std_min(u, d.cmax[dd]);   // std::min / std::max semantics: a NaN control stays NaN like in the reference
+            u = std_min(u, d.cmax[dd]);   // cwiseMin(max).cwiseMax(min), mppi.cpp:443-447; std::min / std::max NaN semantics
             u = std_max(u, d.cmin[dd]);
-            d.U_shift[e] = u;
         }
-        d.U[e] = u;  // publication: m_optimal_control = m_optimal_control_shifted (mppi.cpp:178-182)
+        d.U_shift[e] = u;
+        d.U[e] = u;        // publication: m_optimal_control = m_optimal_control_shifted (mppi.cpp:178-182)
+        d.result[e] = u;   // host-mapped copy, visible to the caller when the stream completes
     }
+}
+
+// ---- FMA-chain microbenchmark: the roofline denominator of the rollout kernel -------------------------
+template <class R> __global__ void __launch_bounds__(256) k_fma_peak(R *out, int iters) {
+    R a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = R(threadIdx.x + i) * R(1e-3);
+    const R m = R(0.999), c = R(1e-6);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = a[i] * m + c;
+    }
+    R s = R(0);
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+cudaError_t measure_fma_peak(int precision, double *tflops) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    void *buf = nullptr;
+    cudaError_t e = cudaMalloc(&buf, (size_t)blocks * threads * 8);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(a);
+        if (precision == 0) k_fma_peak<double><<<blocks, threads>>>((double *)buf, iters); else k_fma_peak<float><<<blocks, threads>>>((float *)buf, iters);
+        cudaEventRecord(b);
+        e = cudaEventSynchronize(b);
+        if (e != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(buf);
+    if (e != cudaSuccess) return e;
+    const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return cudaGetLastError();
 }
 
 // ---- launchers -----------------------------------------------------------------------------------------
@@ -451,13 +534,13 @@ cudaError_t launch_gradient(const DeviceState &d, int precision, cudaStream_t s,
     const int nvec = n / (precision == 0 ? 2 : 4);
     const int threads = std::min(512, ((nvec + 127) / 128) * 128);
     if (precision == 0) k_gradient<double><<<d.grad_blocks, threads, 0, s>>>(d); else k_gradient<float><<<d.grad_blocks, threads, 0, s>>>(d);
-    k_gradient_reduce<<<(n + 255) / 256, 256, 0, s>>>(d);
+    k_gradient_reduce<<<(n + 31) / 32, 256, 0, s>>>(d);
     *launches += 2;
     return cudaGetLastError();
 }
 
 cudaError_t launch_finish(const DeviceState &d, cudaStream_t s) {
-    const size_t smem = d.sg_enabled ? sizeof(double) * 2 * (size_t)d.nu * d.sg_len : 0;
+    const size_t smem = sizeof(double) * ((size_t)d.nu * d.T + 2 * (size_t)d.nu * d.sg_len + 2 * (size_t)d.sg_window + 1);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -10,8 +10,8 @@
 
 namespace mppi_b200 {
 
-// The including translation unit defines MPPI_DEVICE_MODEL: its own __constant__ RobotModel<R>
-// (one per precision, so no relocatable device code is needed).
+// The including translation unit defines MPPI_DEVICE_MODEL / MPPI_DEVICE_FAST_MODEL: its own
+// __constant__ RobotModel<R> / FastModel<R> (one per precision, so no relocatable device code is needed).
 
 // order preserving map double -> u64 (so that integer atomicMin/Max order like the doubles)
 __device__ __forceinline__ unsigned long long encode_ordered(double v) {
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ DeviceS
             RolloutInputs<R> in;
             in.x0 = sx; in.U = sU; in.W = has_w ? sW : nullptr; in.T = d.T; in.dt = (R)d.dt; in.discount = d.discount;
             double bd[7] = {0, 0, 0, 0, 0, 0, 0};
-            cost = rollout_franka<R, VAR, FAITHFUL>(MPPI_DEVICE_MODEL, P, in, eps, optimal_only ? bd : nullptr);
+            cost = rollout_franka<R, VAR, FAITHFUL>(MPPI_DEVICE_MODEL, MPPI_DEVICE_FAST_MODEL, P, in, eps, optimal_only ? bd : nullptr);
             if (optimal_only) {
                 for (int i = 0; i < 7; i++) d.breakdown[i] = bd[i];
                 d.breakdown[7] = cost;

@@ -59,6 +59,8 @@ struct DeviceState {
     double *gradient;      // normalised gradient (get_gradient())
     int *skip;             // 1 when max-min < 1e-6 (mppi.cpp:373-375): weights/gradient/U left untouched
     double *L;             // nu x nu column-major noise transform V*sqrt(Lambda) (gaussian.hpp:48-55)
+    int L_is_diagonal;     // every reference configuration (base.hpp:79-83): eps_i = Ldiag[i] * z_i
+    double Ldiag[MAX_NU];
     // smoothing window state, per channel: uu[Lw], tt[Lw], then start_idx/last_trim in sg_meta
     double *sg_uu, *sg_tt;
     double *sg_weights;    // 2*window+1
@@ -69,6 +71,7 @@ struct DeviceState {
     int bound;
     double cmin[MAX_NU], cmax[MAX_NU];
     // optimal re-rollout outputs
+    double *result;        // host-mapped: U [nu*T], {-min, max, valid} [3], argmin [1], sum w [1] — written by k_finish
     double *optimal_cost;  // [1]
     double *breakdown;     // [8]
 };
@@ -84,5 +87,6 @@ cudaError_t launch_minmax_publish(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_weights(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_gradient(const DeviceState &d, int precision, cudaStream_t s, int *launches);
 cudaError_t launch_finish(const DeviceState &d, cudaStream_t s);
+cudaError_t measure_fma_peak(int precision, double *tflops);
 
 }  // namespace mppi_b200

@@ -334,7 +334,7 @@ MPPI_HD void world_chain(const RobotModel<R> &M, const Scratch<R> &S, Xf<R> &oM,
 //   u      : generalised forces commanded by the control, tau = [0,0,0,u3..u9,0,0] (pinocchio_dynamics.cpp:238-239)
 //   FUSED  : a = M^-1 u
 //   NLE    : also produce nle(q, qd) (needed for tau^T v of the energy tank, or in FAITHFUL mode)
-template <class R, bool FAITHFUL, bool NLE, int FLAGS>
+template <class R, bool FAITHFUL, bool NLE, int FLAGS, bool DO_ABA = true>
 MPPI_HD void robot_calculate(const RobotModel<R> &M, const R *q, const R *qd, const R *u, R *qdd, R *nle, Kinematics<R> &K) {
     Scratch<R> S;
     Mot<R> agf[NJ];
@@ -363,6 +363,7 @@ MPPI_HD void robot_calculate(const RobotModel<R> &M, const R *q, const R *qd, co
     }
     R tau[NJ];
     if (NEED_NLE) rnea_back<R, NJ - 1>(M, S, nle);
+    if (!DO_ABA) return;  // the caller runs the structure-exploiting solver of robot_fast.cuh instead
 #pragma unroll
     for (int i = 0; i < NJ; i++) tau[i] = FAITHFUL ? (u[i] + nle[i]) : u[i];
     Art<R> cur;

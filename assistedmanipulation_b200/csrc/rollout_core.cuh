@@ -8,6 +8,7 @@
 // Host/device: tests compile this for the CPU to check it against the oracle.
 #pragma once
 #include "robot.cuh"
+#include "robot_fast.cuh"
 
 namespace mppi_b200 {
 
@@ -215,15 +216,23 @@ template <class R> struct RolloutInputs {
 // VAR selects objective + which kinematics are alive; FAITHFUL selects the dynamics evaluation.
 // eps: this rollout's noise, [t][d]. Returns the rollout cost (NaN = failed rollout, mppi.cpp:331-334).
 template <class R, int VAR, bool FAITHFUL, class ParamsT>
-MPPI_HD double rollout_franka(const RobotModel<R> &M, const ParamsT &P, const RolloutInputs<R> &in, const R *eps, double *bd) {
+MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, const ParamsT &P, const RolloutInputs<R> &in, const R *eps, double *bd) {
     constexpr int KF = VariantTraits<VAR>::kin;
     constexpr bool POWER = VariantTraits<VAR>::power;
+    constexpr bool LEAN = !FAITHFUL && KF == 0 && !POWER;  // only the end effector position is read by the objective
     R q[NJ], qd[NJ];
 #pragma unroll
     for (int i = 0; i < NJ; i++) { q[i] = in.x0[i]; qd[i] = in.x0[NJ + i]; }
     R energy = in.x0[30];
     Kinematics<R> K;
-    robot_kinematics<R, KF>(M, q, qd, K);
+    R cs[NJ], sn[NJ];
+    if constexpr (LEAN) {
+#pragma unroll
+        for (int i = 2; i < 10; i++) sincos_(q[i], &sn[i], &cs[i]);
+        K.ee_pos = ee_position_fast<R>(F, q, cs, sn);
+    } else {
+        robot_kinematics<R, KF>(M, q, qd, K);
+    }
     double total = 0.0;
     for (int step = 0; step < in.T; ++step) {
         R u[NJ];
@@ -237,15 +246,29 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const ParamsT &P, const Ro
         total += sc;
         if (step + 1 == in.T) break;  // the state after the last step is never costed (mppi.cpp:316-341)
         // PinocchioDynamics::step, pinocchio_dynamics.cpp:226-260
-        R sy, cy;
-        sincos_(q[2], &sy, &cy);
-        qd[0] = cy * u[0] - sy * u[1];
-        qd[1] = sy * u[0] + cy * u[1];
-        qd[2] = u[2];
         R tau[NJ], qdd[NJ], nle[NJ];
 #pragma unroll
         for (int i = 0; i < NJ; i++) { tau[i] = (i >= 3 && i < 10) ? u[i] : R(0); nle[i] = R(0); }
-        robot_calculate<R, FAITHFUL, POWER, KF>(M, q, qd, tau, qdd, nle, K);
+        if constexpr (FAITHFUL) {
+            R sy, cy;
+            sincos_(q[2], &sy, &cy);
+            qd[0] = cy * u[0] - sy * u[1];
+            qd[1] = sy * u[0] + cy * u[1];
+            qd[2] = u[2];
+            robot_calculate<R, true, POWER, KF>(M, q, qd, tau, qdd, nle, K);
+        } else {
+            // FUSED: qdd = M(q)^-1 tau through the structure-exploiting solver; joint sines / cosines are shared
+            if (!(LEAN && step == 0)) {
+#pragma unroll
+                for (int i = 2; i < 10; i++) sincos_(q[i], &sn[i], &cs[i]);
+            }
+            qd[0] = cs[2] * u[0] - sn[2] * u[1];
+            qd[1] = sn[2] * u[0] + cs[2] * u[1];
+            qd[2] = u[2];
+            if constexpr (LEAN) K.ee_pos = ee_position_fast<R>(F, q, cs, sn);
+            else robot_calculate<R, false, POWER, KF, false>(M, q, qd, tau, qdd, nle, K);
+            aba_fused_fast<R>(F, q, cs, sn, tau, qdd);
+        }
 #pragma unroll
         for (int i = 0; i < NJ; i++) qd[i] += qdd[i] * in.dt;
 #pragma unroll

@@ -1,0 +1,274 @@
+#!/usr/bin/env python3
+"""bench.py — the MPPI rollout path on N B200s (driver contract, tier ④).
+
+A "step" is one mppi::Trajectory::update() (reference src/controller/mppi.cpp:154-187): sample ->
+K+2 rollouts of T steps -> exp-weighting -> weighted-sum update -> smoothing/clamp. Workload at N=1 is
+BASELINE.json configs[1]: Franka Research 3 + Ridgeback, TrackPoint objective, K=4096 x T=64, FP64.
+For N>1 the rollout set grows with N (K = 4096*N, "weak") and is sharded over the ranks; the two
+exchanges of the path (min/max of the costs, weighted sums) are NCCL all-reduces inside the library.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg3|toy]
+
+`--impl reference` times the reference's CPU algorithm (the oracle port with its thread pool on all
+host cores; the reference itself cannot run K > 253 nor be built offline) on the same
+workload, one bounded sample per step.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from assistedmanipulation_b200 import abi  # noqa: E402
+
+# Algorithmic work per rollout-step: Featherstone operation counts at n = 12 one-dof
+# joints — ABA 4641 + RNEA 1880 + second-order FK / frames / WORLD jacobian ~2300 + cost + Euler + tank.
+FLOPS_PER_STEP = {"cfg2": 9000.0, "cfg3": 9500.0, "toy": 25.0}
+
+
+def workload(name, n_gpus):
+    if name == "cfg2":
+        return dict(name="franka_ridgeback_trackpoint_K4096xT64_fp64", system=abi.SYSTEM_FRANKA_RIDGEBACK, objective=abi.OBJECTIVE_TRACK_POINT,
+                    params=abi.default_track_point(), K=4096 * n_gpus, horison=0.64, precision=abi.FP64, dtype="f64", x0=abi.huddled_state(), wrench=None)
+    if name == "cfg3":
+        import cases
+        return dict(name="franka_ridgeback_assisted_K16384xT128_fp32", system=abi.SYSTEM_FRANKA_RIDGEBACK, objective=abi.OBJECTIVE_ASSISTED_MANIPULATION,
+                    params=cases.assisted_params(True, abi.LINKS_BODY_COM), K=16384 * n_gpus, horison=1.28, precision=abi.FP32, dtype="f32",
+                    x0=abi.huddled_state(10.0), wrench=cases.constant_wrench(128))
+    if name == "toy":
+        return dict(name="toy_double_integrator_K1024xT100_fp64", system=abi.SYSTEM_TOY, objective=abi.OBJECTIVE_TOY, params=abi.default_toy_objective(),
+                    K=1024 * n_gpus, horison=1.0, precision=abi.FP64, dtype="f64", x0=np.zeros(4), wrench=None)
+    raise SystemExit("unknown workload " + name)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:6]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def run_oracle(wl, steps, warmup, threads, budget_s=None):
+    """The reference's CPU algorithm (oracle port) on the host cores; returns per-update seconds."""
+    import oracle_lib as ol
+    lib = ol.load()
+    holder = abi.make_config(wl["system"], wl["objective"], wl["K"], wl["horison"], keep_best=0, threads=threads)
+    o = ol.Oracle(lib, holder, wl["params"])
+    times = []
+    t_begin = time.perf_counter()
+    for u in range(warmup + steps):
+        t0 = time.perf_counter()
+        rc = o.update(wl["x0"], 0.05 * u, wl["wrench"], None)  # own mt19937 sampling, like the reference
+        t1 = time.perf_counter()
+        assert rc == 0
+        if u >= warmup:
+            times.append(t1 - t0)
+        if budget_s is not None and u >= warmup and time.perf_counter() - t_begin > budget_s:
+            break
+    T, R = o.query(abi.QUERY_STEP_COUNT), o.query(abi.QUERY_ROLLOUT_COUNT)
+    phases = np.zeros(4)
+    lib.oracle_phase_seconds(o.h, ol.ptr(phases))
+    o.close()
+    return np.array(times), T, R, phases
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-l2-flush", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, 1)
+    args.warmup = max(args.warmup, 3)
+    wl = workload(args.workload, n_gpus)
+    host_threads = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        # bounded sample per step: one full update of the same workload at N=1 size per GPU
+        times, T, R, phases = run_oracle(wl, args.steps, args.warmup, host_threads)
+        value = R * T / times.mean()
+        line = {"impl": "reference", "metric": "rollout-steps/s", "value": value, "unit": "rollout-steps/s", "n_gpus": n_gpus, "steps": len(times),
+                "warmup": args.warmup, "ms_per_step": times.mean() * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["name"], "rollouts": wl["K"], "steps_per_rollout": T, "noise": "mt19937 gaussian (controller/gaussian.hpp)"},
+                "latency_us": {"p50": float(np.median(times) * 1e6), "p99": float(np.percentile(times, 99) * 1e6)},
+                "cpu_baseline": {"value": value, "unit": "rollout-steps/s", "cores": host_threads, "kind": "port",
+                                 "sample": "%d full updates of the workload (K+2=%d rollouts x T=%d)" % (len(times), R, T),
+                                 "phase_split_s": dict(zip(["sample", "rollout", "optimise", "filter"], [float(x) for x in phases]))},
+                "e2e": {"value": value, "unit": "rollout-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import engine_lib as el
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    holder = abi.make_config(wl["system"], wl["objective"], wl["K"], wl["horison"], precision=wl["precision"], dynamics_mode=abi.DYNAMICS_FUSED,
+                             keep_best=0, device=local_rank, rank=rank, world_size=world)
+    e = el.Engine(holder, wl["params"])
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            assert e.lib.mppi_b200_comm_unique_id(buf) == 0
+            uid.copy_(torch.tensor(list(buf), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        raw = bytes(uid.cpu().tolist())
+        assert e.lib.mppi_b200_comm_init(e.h, C.c_char_p(raw)) == 0, e.error()
+    T, R = e.query(abi.QUERY_STEP_COUNT), e.query(abi.QUERY_ROLLOUT_COUNT)
+    nu = e.query(abi.QUERY_CONTROL_DOF)
+    flush = None if args.no_l2_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    x0, wrench = wl["x0"], wl["wrench"]
+    step = 0
+    for _ in range(args.warmup):
+        assert e.update(x0, 0.05 * step, wrench, seed=1) == 0, e.error()
+        step += 1
+    launches0 = e.query(abi.QUERY_KERNEL_LAUNCHES)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    dev_s, wall_s = [], []
+    t_region0 = time.perf_counter()
+    for _ in range(args.steps):
+        if flush is not None:
+            flush.fill_(step & 0xff)          # evict L2 between timed iterations
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rc = e.update(x0, 0.05 * step, wrench, seed=1)   # host state in, host control sequence out
+        t1 = time.perf_counter()
+        assert rc == 0, e.error()
+        wall_s.append(t1 - t0)
+        dev_s.append(e.device_seconds())
+        step += 1
+    barrier()
+    t_region1 = time.perf_counter()
+    sampler.stop_flag = True
+    sampler.join()
+    launches = e.query(abi.QUERY_KERNEL_LAUNCHES) - launches0
+    dev_s, wall_s = np.array(dev_s), np.array(wall_s)
+
+    # per-stage device times (separate short loop: the extra events are not in the timed region)
+    assert e.lib.mppi_b200_set_profiling(e.h, 1) == 0
+    stage = np.zeros((20, len(abi.STAGES)))
+    for i in range(20):
+        assert e.update(x0, 0.05 * step, wrench, seed=1) == 0
+        step += 1
+        e.lib.mppi_b200_stage_seconds(e.h, stage[i].ctypes.data_as(C.POINTER(C.c_double)), len(abi.STAGES))
+    stage = np.median(stage, axis=0)
+    e.lib.mppi_b200_set_profiling(e.h, 0)
+
+    t_dev, t_wall = float(dev_s.sum()), float(wall_s.sum())
+    if world > 1:
+        tt = torch.tensor([t_dev, t_wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_wall = float(tt[0]), float(tt[1])
+    if rank != 0:
+        e.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    units = R * T * args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    fma_peak = C.c_double()
+    assert e.lib.mppi_b200_measure_fma_peak(local_rank, wl["precision"], C.byref(fma_peak)) == 0
+    rollout_s = float(stage[abi.STAGES.index("rollout")])
+    k_local = e.query(abi.QUERY_LOCAL_COUNT)
+    achieved_tflops = FLOPS_PER_STEP.get(args.workload, 9000.0) * k_local * T / rollout_s / 1e12
+    esz = 8 if wl["precision"] == abi.FP64 else 4
+    noise_bytes = k_local * T * nu * esz
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    line = {
+        "metric": "rollout-steps/s", "value": units / t_dev, "unit": "rollout-steps/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+        "config": {"workload": wl["name"], "rollouts": wl["K"], "static_rollouts": 2, "steps_per_rollout": T, "time_step": 0.01, "update_cadence_s": 0.05,
+                   "noise": "in-kernel Philox4x32-10", "dynamics_mode": "fused", "keep_best_rollouts": 0,
+                   "parallelism": "rollouts sharded over %d GPU(s); NCCL all-reduce of [-min,max] and [sum w, sum w*eps]" % world,
+                   "l2": "not flushed" if flush is None else "flushed between timed iterations (256 MiB write)",
+                   "timing": "value: CUDA events on the engine stream around each update (inputs resident); e2e: host clock around the C-ABI call"},
+        "clocks": sampler.result(),
+        "e2e": {"value": units / t_wall, "unit": "rollout-steps/s", "h2d_bytes_per_step": int(8 * (40 + 6 * T)), "d2h_bytes_per_step": int(8 * (nu * T + 4)),
+                "update_latency_us": {"p50": float(np.median(wall_s) * 1e6), "p99": float(np.percentile(wall_s, 99) * 1e6), "max": float(wall_s.max() * 1e6)}},
+        "gpu_launches": int(launches),
+        "device_update_us": {"p50": float(np.median(dev_s) * 1e6), "p99": float(np.percentile(dev_s, 99) * 1e6)},
+        "stages_us": {n: float(s * 1e6) for n, s in zip(abi.STAGES, stage)},
+        "roofline": {"kernel": "k_rollout", "bound": "fp64_pipe" if wl["precision"] == abi.FP64 else "fp32_pipe", "achieved": achieved_tflops, "peak": fma_peak.value,
+                     "unit": "TFLOP/s", "frac": achieved_tflops / fma_peak.value, "traffic": None,
+                     "peak_source": "FMA-chain microbenchmark run in this process (mppi_b200_measure_fma_peak); MEASURED_PEAKS.json has no vector FP peak",
+                     "algorithmic_flops_per_rollout_step": FLOPS_PER_STEP.get(args.workload, 9000.0)},
+        "roofline_hbm": {
+            "sample": {"bound": "hbm", "achieved": noise_bytes / float(stage[abi.STAGES.index("sample")]) / 1e9, "peak": hbm_peak, "unit": "GB/s"},
+            "weighted_sum": {"bound": "hbm", "achieved": noise_bytes / float(stage[abi.STAGES.index("weighted_sum")]) / 1e9, "peak": hbm_peak, "unit": "GB/s"},
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+            "note": "the noise buffer (%.1f MB) is produced and consumed inside one update and fits the 126 MB L2" % (noise_bytes / 1e6)},
+        "wall_region_s": t_region1 - t_region0,
+    }
+    for k in ("sample", "weighted_sum"):
+        line["roofline_hbm"][k]["frac"] = line["roofline_hbm"][k]["achieved"] / hbm_peak
+    e.close()
+    if world > 1:
+        dist.destroy_process_group()
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        wl1 = workload(args.workload, 1)
+        times, T1, R1, phases = run_oracle(wl1, 8, 1, host_threads, budget_s=25.0)
+        line["cpu_baseline"] = {"value": R1 * T1 / times.mean(), "unit": "rollout-steps/s", "cores": host_threads, "kind": "port",
+                                "sample": "%d full updates of the same workload (K+2=%d x T=%d) on the oracle port, %d pool threads" % (len(times), R1, T1, host_threads),
+                                "update_ms": {"p50": float(np.median(times) * 1e3), "max": float(times.max() * 1e3)},
+                                "phase_split_s": dict(zip(["sample", "rollout", "optimise", "filter"], [float(x) for x in phases]))}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -228,6 +228,18 @@ int mppi_b200_query(mppi_b200_engine *engine, int32_t what, int64_t *value);
 /* time of the kernels of the last update on the device, seconds (CUDA events on the engine stream) */
 int mppi_b200_last_update_device_seconds(mppi_b200_engine *engine, double *seconds);
 
+/* Per-stage device time of the last update (CUDA events between the stages; off by default because
+ * the extra events cost a little latency). Stages: 0 host->device inputs, 1 warm start + shift,
+ * 2 sample (K1), 3 rollout (K2), 4 min/max + weights (K3), 5 weighted sum (K4), 6 finish (K5),
+ * 7 device->host result. */
+#define MPPI_B200_STAGES 8
+int mppi_b200_set_profiling(mppi_b200_engine *engine, int32_t enabled);
+int mppi_b200_stage_seconds(mppi_b200_engine *engine, double *seconds, size_t count);
+
+/* Roofline denominator for the rollout kernel: sustained FMA rate of the vector pipe of `device` in
+ * the given precision (MPPI_B200_FP64 / FP32), measured with a register-resident FMA-chain kernel. */
+int mppi_b200_measure_fma_peak(int32_t device, int32_t precision, double *tflops);
+
 /* Defaults of the reference, so that callers need not restate them:
  * TrackPoint::DEFAULT_CONFIGURATION (track_point.hpp:77-114),
  * AssistedManipulation::DEFAULT_CONFIGURATION (assisted_manipulation.hpp:133-206). */

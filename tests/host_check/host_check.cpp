@@ -39,6 +39,26 @@ void host_robot_calculate(int mode, const double *q, const double *qd, const dou
         case 6: calc<float, false, true>(q, qd, u, qdd, nle, kin34); break;
     }
 }
+// robot_fast.cuh: qdd = M^-1 u and the end effector position
+void host_fast_aba(int f32, const double *q, const double *u, double *qdd, double *ee) {
+    if (f32) {
+        static const FastModel<float> F = make_fast_model<float>();
+        float q_[12], u_[12], c[12], s[12], o[12];
+        for (int i = 0; i < 12; i++) { q_[i] = (float)q[i]; u_[i] = (float)u[i]; c[i] = cosf(q_[i]); s[i] = sinf(q_[i]); }
+        aba_fused_fast<float>(F, q_, c, s, u_, o);
+        Vec3<float> p = ee_position_fast<float>(F, q_, c, s);
+        for (int i = 0; i < 12; i++) qdd[i] = o[i];
+        ee[0] = p.x; ee[1] = p.y; ee[2] = p.z;
+    } else {
+        static const FastModel<double> F = make_fast_model<double>();
+        double c[12], s[12];
+        for (int i = 0; i < 12; i++) { c[i] = cos(q[i]); s[i] = sin(q[i]); }
+        aba_fused_fast<double>(F, q, c, s, u, qdd);
+        Vec3<double> p = ee_position_fast<double>(F, q, c, s);
+        ee[0] = p.x; ee[1] = p.y; ee[2] = p.z;
+    }
+}
+int host_fast_structure_matches() { std::string w; return fast_structure_matches(&w) ? 1 : 0; }
 int host_topology_matches() { std::string w; return topology_matches(&w) ? 1 : 0; }
 }
 
@@ -49,6 +69,7 @@ int host_topology_matches() { std::string w; return topology_matches(&w) ? 1 : 0
 template <class R, int VAR, bool FAITHFUL, class CP>
 static void run_rollouts(const CP &cp, const double *x0, const double *U, const double *W, const double *eps, int K, int T, double dt, double discount, double *costs, double *bd) {
     static const RobotModel<R> M = make_robot_model<R>();
+    static const FastModel<R> F = make_fast_model<R>();
     auto P = convert<R>(cp);
     std::vector<R> x(31), u((size_t)12 * T), w, e((size_t)12 * T);
     for (int i = 0; i < 31; i++) x[i] = (R)x0[i];
@@ -57,7 +78,7 @@ static void run_rollouts(const CP &cp, const double *x0, const double *U, const 
     RolloutInputs<R> in{x.data(), u.data(), W ? w.data() : nullptr, T, (R)dt, discount};
     for (int k = 0; k < K; k++) {
         for (size_t i = 0; i < e.size(); i++) e[i] = (R)eps[(size_t)k * 12 * T + i];
-        costs[k] = rollout_franka<R, VAR, FAITHFUL>(M, P, in, e.data(), bd);
+        costs[k] = rollout_franka<R, VAR, FAITHFUL>(M, F, P, in, e.data(), bd);
     }
 }
 

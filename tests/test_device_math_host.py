@@ -1,0 +1,121 @@
+"""The engine's host/device templates (csrc/robot.cuh, rollout_core.cuh) compiled for the CPU and
+checked against the oracle — an independent implementation (the device code is specialised by joint
+type, carries the articulated inertia in symmetric blocks and has a FUSED evaluation mode; the
+oracle follows pinocchio's generic recursion). This is test infrastructure: the product library has
+no CPU path (tests/host_check builds its own shared object)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+import oracle_lib as ol
+from assistedmanipulation_b200 import abi
+
+HC_DIR = os.path.join(ol.ROOT, "tests", "host_check")
+_dp = ol._dp
+
+
+@pytest.fixture(scope="module")
+def hc():
+    so = os.path.join(HC_DIR, "libhost_check.so")
+    src = os.path.join(HC_DIR, "host_check.cpp")
+    csrc = os.path.join(ol.ROOT, "assistedmanipulation_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("robot.cuh", "rollout_core.cuh", "spatial.cuh", "model_init.h", "params_convert.h", "robot_model.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-x", "c++", "-fPIC", "-shared", "-I" + csrc, "-o", so, src])
+    lib = C.CDLL(so)
+    lib.host_robot_calculate.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
+    lib.host_rollouts.argtypes = [C.c_int, C.c_int, C.c_void_p, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_double, C.c_double, _dp, _dp]
+    return lib
+
+
+def test_topology_matches_generated_model(hc):
+    assert hc.host_topology_matches() == 1
+
+
+@pytest.mark.parametrize("mode,tol", [(0, 1e-12), (1, 1e-12), (2, 1e-12), (4, 5e-5), (5, 5e-5)])
+def test_calculate_matches_oracle(oracle, hc, mode, tol):
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        q, v, u = rng.uniform(-1.5, 1.5, 12), rng.uniform(-1, 1, 12), np.zeros(12)
+        u[3:10] = rng.uniform(-10, 10, 7)
+        nle, a = np.zeros(12), np.zeros(12)
+        oracle.oracle_robot_nle(ol.ptr(q), ol.ptr(v), ol.ptr(nle))
+        tau = u + nle
+        oracle.oracle_robot_aba(ol.ptr(q), ol.ptr(v), ol.ptr(tau), ol.ptr(a))
+        pos, lin, ang, J = np.zeros(3), np.zeros(3), np.zeros(3), np.zeros(72)
+        oracle.oracle_robot_kinematics(ol.ptr(q), ol.ptr(v), ol.ptr(pos), ol.ptr(lin), ol.ptr(ang), ol.ptr(J))
+        Ja = J.reshape(6, 12)[:3, 3:10]
+        ee, mt, lc = np.zeros(3), np.zeros(3), np.zeros(39)
+        oracle.oracle_robot_fk(ol.ptr(q), ol.ptr(ee), ol.ptr(mt), ol.ptr(lc))
+        qdd, n2, kin = np.zeros(12), np.zeros(12), np.zeros(34)
+        hc.host_robot_calculate(mode, ol.ptr(q), ol.ptr(v), ol.ptr(u), ol.ptr(qdd), ol.ptr(n2), ol.ptr(kin))
+        assert np.abs(qdd - a).max() <= tol * np.abs(a).max()
+        if mode & 3:
+            assert np.abs(n2 - nle).max() <= tol * max(np.abs(nle).max(), 1.0)
+        assert np.abs(kin[:3] - pos).max() <= tol and np.abs(kin[3:6] - mt).max() <= tol
+        assert np.abs(kin[6:9] - lin).max() <= tol * 10
+        assert abs(kin[9] - np.linalg.det(Ja @ Ja.T)) <= max(tol, 1e-10) * 10 * abs(np.linalg.det(Ja @ Ja.T)) + tol * 1e-3
+        assert np.abs(kin[10:].reshape(8, 3) - lc.reshape(13, 3)[3:11]).max() <= tol
+
+
+def _oracle_costs(oracle, objective, params, K, T, x0, wrench, seed):
+    holder = abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, objective, K, T * 0.01, smoothing=None, threads=4)
+    o = ol.Oracle(oracle, holder, params)
+    eps = np.random.default_rng(seed).standard_normal((K + 2, T, 12)) * np.sqrt(abi.FRANKA_COVARIANCE_DIAG)
+    assert o.update(x0, 0.0, wrench, eps) == 0
+    costs, noise = o.read(abi.READ_COSTS, K + 2), o.read(abi.READ_NOISE, (K + 2) * T * 12)
+    bd = o.read(abi.READ_BREAKDOWN, 8)
+    U = o.read(abi.READ_OPTIMAL, 12 * T)
+    o.close()
+    return costs, noise, bd, U
+
+
+CASES = {
+    "track_point": (abi.OBJECTIVE_TRACK_POINT, abi.default_track_point, None),
+    "assisted_energy_com": (abi.OBJECTIVE_ASSISTED_MANIPULATION, lambda: cases.assisted_params(True, abi.LINKS_BODY_COM), cases.constant_wrench(32)),
+    "assisted_zero_links": (abi.OBJECTIVE_ASSISTED_MANIPULATION, lambda: cases.assisted_params(False, abi.LINKS_ZERO), cases.constant_wrench(32)),
+    "assisted_no_forecast": (abi.OBJECTIVE_ASSISTED_MANIPULATION, lambda: cases.assisted_params(True, abi.LINKS_BODY_COM), None),
+}
+
+
+def _track_point_full():
+    tp = abi.default_track_point()
+    tp.enable_self_collision_avoidance, tp.enable_reach_limits, tp.link_position_mode = 1, 1, abi.LINKS_BODY_COM
+    return tp
+
+
+CASES["track_point_all_terms"] = (abi.OBJECTIVE_TRACK_POINT, _track_point_full, None)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("flags,tol", [(0, 1e-9), (1, 1e-9), (4, 2e-4)])
+def test_rollout_costs_match_oracle(oracle, hc, name, flags, tol):
+    objective, make, wrench = CASES[name]
+    params = make()
+    K, T = 48, 32
+    x0 = abi.huddled_state(10.0)
+    x0[12:24] = 0.05
+    costs, noise, _, _ = _oracle_costs(oracle, objective, params, K, T, x0, wrench, 5)
+    out = np.zeros(K + 2)
+    hc.host_rollouts(objective, flags, C.cast(C.byref(params), C.c_void_p), ol.ptr(x0), ol.ptr(np.zeros(12 * T)), ol.ptr(wrench) if wrench is not None else None,
+                     ol.ptr(noise), K + 2, T, 0.01, 1.0, ol.ptr(out), None)
+    assert (np.abs(out - costs) / np.abs(costs)).max() <= tol
+    if flags < 4:
+        assert out.argmin() == costs.argmin()
+
+
+def test_optimal_breakdown_matches_oracle(oracle, hc):
+    # per-term totals of the optimal re-rollout (logging/assisted_manipulation.cpp:58-103)
+    objective, make, wrench = CASES["assisted_energy_com"]
+    params = make()
+    K, T = 32, 32
+    x0 = abi.huddled_state(10.0)
+    _, _, bd, U = _oracle_costs(oracle, objective, params, K, T, x0, wrench, 9)
+    out, got = np.zeros(1), np.zeros(7)
+    hc.host_rollouts(objective, 0, C.cast(C.byref(params), C.c_void_p), ol.ptr(x0), ol.ptr(U), ol.ptr(wrench), ol.ptr(np.zeros(12 * T)), 1, T, 0.01, 1.0, ol.ptr(out), ol.ptr(got))
+    assert np.allclose(got, bd[:7], rtol=1e-9, atol=1e-9)
+    assert abs(out[0] - bd[7]) <= 1e-9 * abs(bd[7])
