@@ -98,7 +98,8 @@ _dp = C.POINTER(C.c_double)
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libmppi_b200.so")
+    # MPPI_B200_LIB selects an alternative build of the same library (kernel tuning experiments)
+    return os.environ.get("MPPI_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libmppi_b200.so")
 
 
 def load_library(path=None):

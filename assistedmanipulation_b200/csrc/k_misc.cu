@@ -44,9 +44,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 __device__ __forceinline__ void box_muller(unsigned a, unsigned b, float *z0, float *z1) {
     const float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;  // (0,1]
     const float u2 = ((float)b + 0.5f) * 2.3283064365386963e-10f;
-    const float r = sqrtf(-2.0f * __logf(u1));
+    // MUFU-based log / sqrt / sin / cos: the angle 2*pi*u2 - pi stays in [-pi, pi] where __sincosf is accurate to 2^-21
+    const float r = __fsqrt_rn(-2.0f * __logf(u1));
     float s, c;
-    sincospif(2.0f * u2, &s, &c);
+    __sincosf(6.283185307179586f * u2 - 3.14159265358979f, &s, &c);
     *z0 = r * c; *z1 = r * s;
 }
 
@@ -129,38 +130,39 @@ __global__ void k_select_kept(const __grid_constant__ DeviceState d) {
 // One thread per (rollout, step) column. Fresh columns are eps = L z (z ~ N(0, I) from Philox, or the
 // injected buffer); kept rollouts first move their surviving columns left by shift_by.
 // In-place shift is safe because a kept row is processed by ONE block that stages it in shared memory.
-template <class R, class RI> __device__ __forceinline__ void fresh_column(const DeviceState &d, const double *sL, long long kg, int t, R *dst) {
-    const int nu = d.nu;
+template <class R, class RI, int NU> __device__ __forceinline__ void fresh_column(const DeviceState &d, const double *sL, long long kg, int t, R *dst) {
+    constexpr int nu = NU;
     if (d.frame->noise_source != 0) {
         const RI *src = static_cast<const RI *>(d.injected) + ((size_t)(kg - d.k_begin) * d.T + t) * nu;
+#pragma unroll
         for (int i = 0; i < nu; i++) dst[i] = (R)src[i];
         return;
     }
-    float z[MAX_NU];
+    float z[(NU + 3) / 4 * 4];
     const unsigned long long col = (unsigned long long)kg * (unsigned long long)d.T + (unsigned long long)t;
     const uint2 key = make_uint2((unsigned)d.frame->seed, (unsigned)(d.frame->seed >> 32));
     const unsigned upd = (unsigned)d.frame->update_index;
 #pragma unroll
-    for (int b = 0; b < (MAX_NU + 3) / 4; b++) {
-        if (4 * b < nu) {
-            const uint4 r = philox4x32_10(make_uint4((unsigned)col, (unsigned)(col >> 32), (unsigned)b, upd), key);
-            box_muller(r.x, r.y, &z[4 * b], &z[4 * b + 1]);
-            box_muller(r.z, r.w, &z[4 * b + 2], &z[4 * b + 3]);
-        }
+    for (int b = 0; b < (NU + 3) / 4; b++) {
+        const uint4 r = philox4x32_10(make_uint4((unsigned)col, (unsigned)(col >> 32), (unsigned)b, upd), key);
+        box_muller(r.x, r.y, &z[4 * b], &z[4 * b + 1]);
+        box_muller(r.z, r.w, &z[4 * b + 2], &z[4 * b + 3]);
     }
     if (d.L_is_diagonal) {
 #pragma unroll
-        for (int i = 0; i < MAX_NU; i++) if (i < nu) dst[i] = (R)(d.Ldiag[i] * (double)z[i]);
+        for (int i = 0; i < nu; i++) dst[i] = (R)(d.Ldiag[i] * (double)z[i]);   // constant indices: Ldiag stays in the parameter bank
         return;
     }
+#pragma unroll
     for (int i = 0; i < nu; i++) {
         double s = 0.0;
+#pragma unroll
         for (int j = 0; j < nu; j++) s += sL[j * nu + i] * (double)z[j];
         dst[i] = (R)s;
     }
 }
 
-template <class R, class RI> __global__ void __launch_bounds__(256) k_sample(const __grid_constant__ DeviceState d) {
+template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sample(const __grid_constant__ DeviceState d) {
     // A block produces 256 consecutive columns = one contiguous span of 256*nu values: every thread
     // builds its column in shared memory, then the block streams the span out with 16-byte stores.
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -170,18 +172,20 @@ template <class R, class RI> __global__ void __launch_bounds__(256) k_sample(con
     const long long col0 = (long long)blockIdx.x * blockDim.x;
     const long long col = col0 + threadIdx.x;   // local column index
     const long long ncols = d.k_count * d.T;
-    const int nu = d.nu;
+    constexpr int nu = NU;
     R *noise = static_cast<R *>(d.noise);
     if (col < ncols) {
         const long long kl = col / d.T;
         const int t = (int)(col - kl * d.T);
         const long long kg = kl + d.k_begin;
-        R v[MAX_NU];
+        R v[NU];
         if (kg < 2 || d.kept[kl]) {   // static rollouts (k_prepare) and kept rollouts (k_shift_kept) keep their values
+#pragma unroll
             for (int i = 0; i < nu; i++) v[i] = noise[(size_t)col * nu + i];
         } else {
-            fresh_column<R, RI>(d, sL, kg, t, v);
+            fresh_column<R, RI, NU>(d, sL, kg, t, v);
         }
+#pragma unroll
         for (int i = 0; i < nu; i++) tile[threadIdx.x * nu + i] = v[i];
     }
     __syncthreads();
@@ -199,7 +203,7 @@ template <class R, class RI> __global__ void __launch_bounds__(256) k_sample(con
 }
 
 // kept rollouts: one block per kept rollout (mppi.cpp:243-252); nothing happens when shift_by <= 0
-template <class R, class RI> __global__ void k_shift_kept(const __grid_constant__ DeviceState d) {
+template <class R, class RI, int NU> __global__ void k_shift_kept(const __grid_constant__ DeviceState d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *row = reinterpret_cast<R *>(smem_raw);
     __shared__ double sL[MAX_NU * MAX_NU];
@@ -218,9 +222,10 @@ template <class R, class RI> __global__ void k_shift_kept(const __grid_constant_
         if (t < shifted) {
             for (int i = 0; i < d.nu; i++) noise[t * d.nu + i] = row[(t + shift) * d.nu + i];
         } else {
-            R v[MAX_NU];
-            fresh_column<R, RI>(d, sL, kg, t, v);
-            for (int i = 0; i < d.nu; i++) noise[t * d.nu + i] = v[i];
+            R v[NU];
+            fresh_column<R, RI, NU>(d, sL, kg, t, v);
+#pragma unroll
+            for (int i = 0; i < NU; i++) noise[t * NU + i] = v[i];
         }
     }
 }
@@ -354,7 +359,7 @@ __device__ __forceinline__ int sg_lower_bound(const double *tt, int len, double 
     return first;
 }
 
-__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ DeviceState d) {
+__global__ void __launch_bounds__(512) k_finish(const __grid_constant__ DeviceState d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sU = reinterpret_cast<double *>(smem_raw);   // nu*T working copy of m_optimal_control_shifted
     double *uu = sU + d.nu * d.T;                          // nu x Lw
@@ -380,29 +385,46 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ DeviceSt
         sU[e] = u;
     }
     if (!skip && d.sg_enabled) {
-        const int Lw = d.sg_len, w = d.sg_window;
+        const int Lw = d.sg_len, w = d.sg_window, ntaps = 2 * w + 1;
         for (int i = threadIdx.x; i < d.nu * Lw; i += blockDim.x) { uu[i] = d.sg_uu[i]; tt[i] = d.sg_tt[i]; }
-        for (int i = threadIdx.x; i < 2 * w + 1; i += blockDim.x) sw[i] = d.sg_weights[i];
+        for (int i = threadIdx.x; i < ntaps; i += blockDim.x) sw[i] = d.sg_weights[i];
         __syncthreads();
-        if (threadIdx.x < d.nu) {
-            double *u = uu + threadIdx.x * Lw, *tm = tt + threadIdx.x * Lw;
+        // One WARP per channel: the window bookkeeping is lane-parallel, only the T applications are
+        // sequential (each reads the value the previous one wrote), and each of those is a lane-parallel
+        // dot product over the 2w+1 taps.
+        const int ch = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (ch < d.nu) {
+            double *u = uu + ch * Lw, *tm = tt + ch * Lw;
             const double t0 = d.frame->time;
             // trim(t0): filter.cpp:34-67. start_idx is w before the first pass and w + T after any pass.
             const int start_idx = *d.sg_started ? w + d.T : w;
             int trim_idx = start_idx;
-            for (int i = 0; i < start_idx; i++) if (tm[i] >= t0) { trim_idx = i; break; }
+            for (int i = lane; i < start_idx; i += 32) if (tm[i] >= t0) { trim_idx = i; break; }  // first hit of this lane
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) trim_idx = min(trim_idx, __shfl_xor_sync(0xffffffffu, trim_idx, o));
             const int offset = trim_idx - w;
             if (offset > 0) {
                 // rotate left by offset, then refill the vacated tail with the last valid sample
-                for (int i = 0; i + offset < Lw; i++) { u[i] = u[i + offset]; tm[i] = tm[i + offset]; }
-                const double lu = u[Lw - offset - 1], lt = tm[Lw - offset - 1];
-                for (int i = Lw - offset; i < Lw; i++) { u[i] = lu; tm[i] = lt; }
+                const double lu = u[Lw - 1], lt = tm[Lw - 1];  // element that lands at Lw - offset - 1
+                for (int base = 0; base < Lw; base += 32) {
+                    const int i = base + lane;
+                    const bool in = i + offset < Lw;
+                    const double a = in ? u[i + offset] : lu, b = in ? tm[i + offset] : lt;
+                    __syncwarp();
+                    if (i < Lw) { u[i] = a; tm[i] = b; }
+                    __syncwarp();
+                }
             }
-            tm[w] = t0;
+            if (lane == 0) tm[w] = t0;
+            __syncwarp();
             // add_measurement x T (filter.cpp:69-90): final state = samples in [w, w+T), copies of the last beyond.
             // Times are compared with == / >= later: no FMA contraction, exactly m_rollout_time + i * m_time_step (mppi.cpp:430).
-            for (int i = 0; i < d.T; i++) { u[w + i] = sU[i * d.nu + threadIdx.x]; tm[w + i] = __dadd_rn(t0, __dmul_rn((double)i, d.dt)); }
-            for (int i = w + d.T; i < Lw; i++) { u[i] = u[w + d.T - 1]; tm[i] = tm[w + d.T - 1]; }
+            for (int i = lane; i < Lw - w; i += 32) {
+                const int k = i < d.T ? i : d.T - 1;
+                u[w + i] = sU[k * d.nu + ch];
+                tm[w + i] = __dadd_rn(t0, __dmul_rn((double)k, d.dt));
+            }
+            __syncwarp();
             // apply x T (filter.cpp:163-173): the filtered value is written ONE SLOT EARLIER than the sample
             for (int i = 0; i < d.T; i++) {
                 const double t = __dadd_rn(t0, __dmul_rn((double)i, d.dt));
@@ -410,11 +432,13 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ DeviceSt
                 int idx = w + i;
                 if (!(tm[idx] >= t && tm[idx - 1] < t)) idx = sg_lower_bound(tm, Lw, t);
                 const double *v = u + idx - w;
-                double res = sw[0] * v[0];
-#pragma unroll 4
-                for (int j = 1; j < 2 * w + 1; j++) res += sw[j] * v[j];
-                u[idx - 1] = res;
-                sU[i * d.nu + threadIdx.x] = res;
+                double res = 0.0;
+                for (int j = lane; j < ntaps; j += 32) res = fma(sw[j], v[j], res);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
+                __syncwarp();
+                if (lane == 0) { u[idx - 1] = res; sU[i * d.nu + ch] = res; }
+                __syncwarp();
             }
         }
         __syncthreads();
@@ -492,24 +516,27 @@ cudaError_t launch_select_kept(const DeviceState &d, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-template <class R> static cudaError_t sample_t(const DeviceState &d, cudaStream_t s, int *launches) {
+template <class R, class RI, int NU> static cudaError_t sample_tt(const DeviceState &d, cudaStream_t s, int *launches) {
     const size_t row = sizeof(R) * (size_t)d.nu * d.T;
     if (d.keep_best > 0) {
         if (row > 48 * 1024) {
-            cudaError_t e = d.injected_is_double ? cudaFuncSetAttribute(k_shift_kept<R, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row)
-                                                 : cudaFuncSetAttribute(k_shift_kept<R, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row);
+            cudaError_t e = cudaFuncSetAttribute(k_shift_kept<R, RI, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row);
             if (e != cudaSuccess) return e;
         }
-        if (d.injected_is_double) k_shift_kept<R, double><<<(unsigned)d.keep_best, 64, row, s>>>(d);
-        else k_shift_kept<R, R><<<(unsigned)d.keep_best, 64, row, s>>>(d);
+        k_shift_kept<R, RI, NU><<<(unsigned)d.keep_best, 64, row, s>>>(d);
         ++*launches;
     }
     const long long ncols = d.k_count * d.T;
     const unsigned grid = (unsigned)((ncols + 255) / 256);
-    const size_t tile = sizeof(R) * 256 * (size_t)d.nu;
-    if (d.injected_is_double) k_sample<R, double><<<grid, 256, tile, s>>>(d); else k_sample<R, R><<<grid, 256, tile, s>>>(d);
+    const size_t tile = sizeof(R) * 256 * (size_t)NU;
+    k_sample<R, RI, NU><<<grid, 256, tile, s>>>(d);
     ++*launches;
     return cudaGetLastError();
+}
+template <class R> static cudaError_t sample_t(const DeviceState &d, cudaStream_t s, int *launches) {
+    if (d.nu == 12) return d.injected_is_double ? sample_tt<R, double, 12>(d, s, launches) : sample_tt<R, R, 12>(d, s, launches);
+    if (d.nu == 2) return d.injected_is_double ? sample_tt<R, double, 2>(d, s, launches) : sample_tt<R, R, 2>(d, s, launches);
+    return cudaErrorInvalidValue;
 }
 cudaError_t launch_sample(const DeviceState &d, int precision, cudaStream_t s, int *launches) {
     return precision == 0 ? sample_t<double>(d, s, launches) : sample_t<float>(d, s, launches);
@@ -545,7 +572,7 @@ cudaError_t launch_finish(const DeviceState &d, cudaStream_t s) {
         cudaError_t e = cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_finish<<<1, 256, smem, s>>>(d);
+    k_finish<<<1, d.nu * 32 > 256 ? 512 : 256, smem, s>>>(d);
     return cudaGetLastError();
 }
 

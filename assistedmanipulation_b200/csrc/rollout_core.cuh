@@ -201,6 +201,26 @@ template <class R> MPPI_HD R assisted_cost(const AssistedP<R> &P, const R *q, co
     return cost;
 }
 
+// one step of a rollout's noise row: 12 values, 16-byte aligned (rows are multiples of 16 bytes)
+MPPI_HD void load_eps(const double *p, double *o) {
+#if defined(__CUDA_ARCH__)
+    const double2 *v = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+    for (int i = 0; i < 6; i++) { const double2 t = __ldg(v + i); o[2 * i] = t.x; o[2 * i + 1] = t.y; }
+#else
+    for (int i = 0; i < 12; i++) o[i] = p[i];
+#endif
+}
+MPPI_HD void load_eps(const float *p, float *o) {
+#if defined(__CUDA_ARCH__)
+    const float4 *v = reinterpret_cast<const float4 *>(p);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { const float4 t = __ldg(v + i); o[4 * i] = t.x; o[4 * i + 1] = t.y; o[4 * i + 2] = t.z; o[4 * i + 3] = t.w; }
+#else
+    for (int i = 0; i < 12; i++) o[i] = p[i];
+#endif
+}
+
 MPPI_HD double discount_pow(double g, int step) { return g == 1.0 ? 1.0 : pow(g, (double)step); }
 
 // Everything one rollout of the Franka+Ridgeback system needs that does not depend on the sample.
@@ -234,10 +254,13 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
         robot_kinematics<R, KF>(M, q, qd, K);
     }
     double total = 0.0;
+    R e_next[NJ];
+    load_eps(eps, e_next);
     for (int step = 0; step < in.T; ++step) {
         R u[NJ];
 #pragma unroll
-        for (int d = 0; d < NJ; d++) u[d] = in.U[step * NJ + d] + eps[step * NJ + d];
+        for (int d = 0; d < NJ; d++) u[d] = in.U[step * NJ + d] + e_next[d];
+        if (step + 1 < in.T) load_eps(eps + (step + 1) * NJ, e_next);  // next step's noise is in flight during this step
         R c;
         if constexpr (VAR == VAR_TP_LEAN || VAR == VAR_TP_FULL) c = track_point_cost<R>(P, q, K);
         else c = assisted_cost<R>(P, q, qd, energy, K, in.W ? in.W + step * 6 : nullptr, bd);

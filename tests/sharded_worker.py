@@ -1,0 +1,53 @@
+"""Worker for tests/test_gpu_sharded.py::test_nccl_two_gpus (launched by torch.distributed.run):
+each rank owns half of the rollouts on its own GPU; the library's NCCL all-reduces do the exchange.
+Rank 0 compares against a single-GPU engine and the oracle."""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import engine_lib as el  # noqa: E402
+import oracle_lib as ol  # noqa: E402
+from assistedmanipulation_b200 import abi  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+K, T, nu = 2046, 32, 12
+tp = abi.default_track_point()
+e = el.Engine(abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_TRACK_POINT, K, 0.32, dynamics_mode=abi.DYNAMICS_FUSED, device=local, rank=rank, world_size=world), tp)
+uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    buf = (C.c_ubyte * 128)()
+    assert e.lib.mppi_b200_comm_unique_id(buf) == 0
+    uid.copy_(torch.tensor(list(buf), dtype=torch.uint8))
+dist.broadcast(uid, 0)
+assert e.lib.mppi_b200_comm_init(e.h, C.c_char_p(bytes(uid.cpu().tolist()))) == 0, e.error()
+x0 = abi.huddled_state()
+Us = []
+for u in range(3):
+    assert e.update(x0, 0.05 * u, None, seed=5) == 0, e.error()
+    Us.append(e.read(abi.READ_OPTIMAL, nu * T))
+gathered = [None] * world
+dist.all_gather_object(gathered, Us)
+if rank == 0:
+    for other in gathered[1:]:
+        for a, b in zip(Us, other):
+            assert np.array_equal(a, b)
+    whole = el.Engine(abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_TRACK_POINT, K, 0.32, dynamics_mode=abi.DYNAMICS_FUSED, device=local), tp)
+    o = ol.Oracle(ol.load(), abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_TRACK_POINT, K, 0.32, threads=8), tp)
+    for u in range(3):
+        assert whole.update(x0, 0.05 * u, None, seed=5) == 0
+        Uw = whole.read(abi.READ_OPTIMAL, nu * T)
+        assert np.abs(Us[u] - Uw).max() <= 1e-12 * np.abs(Uw).max()
+        assert o.update(x0, 0.05 * u, None, whole.read(abi.READ_NOISE, (K + 2) * T * nu)) == 0
+        Uo = o.read(abi.READ_OPTIMAL, nu * T)
+        assert np.abs(Us[u] - Uo).max() <= 1e-9 * np.abs(Uo).max()
+    print("sharded ok", world, "ranks")
+e.close()
+dist.destroy_process_group()
