@@ -1,0 +1,51 @@
+"""The C++ facade (assistedmanipulation_b200/cpp: mppi::Trajectory / Dynamics / Cost with the
+reference's API, src/controller/mppi.hpp:267-474) driven like the reference's Actor, compared with the
+oracle on identical injected noise."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+import oracle_lib as ol
+from assistedmanipulation_b200 import abi
+from test_abi_cpu import build_facade_demo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("which", ["toy", "track", "assisted"])
+def test_facade_matches_oracle(oracle, tmp_path, which):
+    exe = build_facade_demo()
+    K, horison, updates = 126, 0.3, 4
+    T = 30
+    if which == "toy":
+        system, objective, params, nu, x0, wrench, sigma = abi.SYSTEM_TOY, abi.OBJECTIVE_TOY, abi.default_toy_objective(), 2, np.zeros(4), None, np.ones(2)
+    else:
+        system, nu, x0, sigma = abi.SYSTEM_FRANKA_RIDGEBACK, 12, abi.huddled_state(10.0), np.sqrt(abi.FRANKA_COVARIANCE_DIAG)
+        if which == "track":
+            objective, params, wrench = abi.OBJECTIVE_TRACK_POINT, abi.default_track_point(), None
+        else:
+            objective, params, wrench = abi.OBJECTIVE_ASSISTED_MANIPULATION, cases.assisted_params(True, abi.LINKS_BODY_COM), cases.constant_wrench(T)
+    R = K + 2
+    noise = np.random.default_rng(1).standard_normal((updates, R, T, nu)) * sigma
+    noise.tofile(str(tmp_path / "noise.bin"))
+    r = subprocess.run([exe, which, str(K), str(horison), str(updates), str(tmp_path / "noise.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "foreign_cost_refused 1" in r.stdout and "no device implementation" in r.stderr
+    rec = np.fromfile(str(tmp_path / "out.bin")).reshape(updates, nu * T + nu + 1 + R)
+    holder = abi.make_config(system, objective, K, horison, keep_best=20, threads=4, control_default=np.zeros(nu) if which != "toy" else None)
+    o = ol.Oracle(oracle, holder, params)
+    for u in range(updates):
+        assert o.update(x0, 0.05 * u, wrench, noise[u]) == 0
+        Uo = o.read(abi.READ_OPTIMAL, nu * T)
+        assert np.abs(rec[u, :nu * T] - Uo).max() <= 1e-9 * np.abs(Uo).max()
+        assert np.allclose(rec[u, nu * T:nu * T + nu], o.get(0.05 * u + 0.013), rtol=1e-9, atol=1e-9 * np.abs(Uo).max())
+        oc = o.read(abi.READ_OPTIMAL_COST, 1)[0]
+        assert abs(rec[u, nu * T + nu] - oc) <= 1e-8 * abs(oc)
+        assert np.allclose(rec[u, nu * T + nu + 1:], o.read(abi.READ_WEIGHTS, R), rtol=1e-8, atol=1e-14)
+    if which == "assisted":
+        got = np.array([float(x) for x in r.stdout.split("breakdown")[1].split("\n")[0].split()])
+        assert np.allclose(got, o.read(abi.READ_BREAKDOWN, 8)[:7], rtol=1e-8, atol=1e-8)
+    o.close()
