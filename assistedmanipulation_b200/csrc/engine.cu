@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -110,8 +111,8 @@ struct mppi_b200_engine {
     bool faithful = false;
     std::vector<unsigned char> params;  // objective block in kernel arithmetic
     cudaStream_t stream = nullptr, side = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_main_done = nullptr, ev_side_done = nullptr;
-    bool side_pending = false;
+    cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_main_done = nullptr, ev_side_done[2] = {nullptr, nullptr};
+    bool side_pending[2] = {false, false};
     // host mirrors (pinned)
     unsigned char *h_frame = nullptr;  // Frame + wrench
     double *h_U = nullptr;             // nu*T (stable copy of the published sequence for get())
@@ -121,8 +122,11 @@ struct mppi_b200_engine {
     // device allocations
     std::vector<void *> allocs;
     unsigned char *d_frame = nullptr;
-    unsigned char *d_frame_snap = nullptr;
-    double *d_U_snap = nullptr;
+    double *d_frame_snap[2] = {nullptr, nullptr};
+    double *d_U_snap[2] = {nullptr, nullptr};
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    int graph_launches = 0;
+    bool use_graphs = true;
     void *d_zero_row = nullptr;
     void *d_injected = nullptr;
     size_t noise_elems = 0;
@@ -181,7 +185,8 @@ void mppi_b200_destroy(mppi_b200_engine *e) {
     if (e->h_U) cudaFreeHost(e->h_U);
     if (e->h_result) cudaFreeHost(e->h_result);
     if (e->h_stats) cudaFreeHost(e->h_stats);
-    for (cudaEvent_t ev : {e->ev_start, e->ev_end, e->ev_main_done, e->ev_side_done}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {e->ev_start, e->ev_end, e->ev_main_done, e->ev_side_done[0], e->ev_side_done[1]}) if (ev) cudaEventDestroy(ev);
+    for (cudaGraphExec_t g : e->graph) if (g) cudaGraphExecDestroy(g);
     for (cudaEvent_t ev : e->ev_stage) if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->side) cudaStreamDestroy(e->side);
@@ -225,6 +230,7 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     e->cfg = *c;
     e->cfg.covariance = nullptr; e->cfg.control_min = nullptr; e->cfg.control_max = nullptr; e->cfg.control_default = nullptr;
     e->faithful = c->dynamics_mode == MPPI_B200_DYNAMICS_FAITHFUL;
+    if (const char *g = std::getenv("MPPI_B200_NO_GRAPH")) e->use_graphs = !(g[0] == '1');
     if (c->control_default) { e->has_default = true; e->control_default.assign(c->control_default, c->control_default + nu); }
     auto bail = [&](int code, const std::string &why) { mppi_b200_destroy(e); return fail_create(code, why); };
 #define CREATE_TRY(call) do { cudaError_t _c = (call); if (_c != cudaSuccess) return bail(MPPI_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_c)); } while (0)
@@ -269,7 +275,7 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     CREATE_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
     for (cudaEvent_t *ev : {&e->ev_start, &e->ev_end}) CREATE_TRY(cudaEventCreate(ev));
-    for (cudaEvent_t *ev : {&e->ev_main_done, &e->ev_side_done}) CREATE_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    for (cudaEvent_t *ev : {&e->ev_main_done, &e->ev_side_done[0], &e->ev_side_done[1]}) CREATE_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     CREATE_TRY(cudaMallocHost(&e->h_frame, e->frame_bytes));
     CREATE_TRY(cudaMallocHost(&e->h_U, n * sizeof(double)));
     CREATE_TRY(cudaMallocHost(&e->h_stats, 16 * sizeof(double)));
@@ -283,8 +289,12 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     bool ok = true;
     auto A = [&](auto *&ptr, size_t count) { using P = std::remove_reference_t<decltype(*ptr)>; ptr = dev_alloc<P>(e, count); ok = ok && ptr; };
     e->d_frame = dev_alloc<unsigned char>(e, e->frame_bytes); ok = ok && e->d_frame;
-    e->d_frame_snap = dev_alloc<unsigned char>(e, e->frame_bytes); ok = ok && e->d_frame_snap;
-    e->d_U_snap = dev_alloc<double>(e, n); ok = ok && e->d_U_snap;
+    for (int i = 0; i < 2; i++) {
+        e->d_frame_snap[i] = dev_alloc<double>(e, e->frame_bytes / 8); ok = ok && e->d_frame_snap[i];
+        e->d_U_snap[i] = dev_alloc<double>(e, n); ok = ok && e->d_U_snap[i];
+    }
+    d.frame_doubles = (int)(e->frame_bytes / 8);
+    d.frame_snap = e->d_frame_snap[0]; d.U_snap = e->d_U_snap[0];
     e->d_zero_row = dev_alloc<unsigned char>(e, n * esz); ok = ok && e->d_zero_row;
     d.frame = reinterpret_cast<const Frame *>(e->d_frame);
     d.wrench = reinterpret_cast<const double *>(e->d_frame + sizeof(Frame));
@@ -322,19 +332,19 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     return MPPI_B200_OK;
 }
 
-int mppi_b200_update_begin(mppi_b200_engine *e, const double *state, double time, const double *wrench, const void *noise, int32_t noise_source, uint64_t seed) {
-    if (!e || !state) return MPPI_B200_ERR_INVALID;
+// ---- one update = host bookkeeping -> [frame upload, K0..K5] -> optimal re-rollout on the side stream -------
+namespace {
+
+// mppi.cpp:194-201 evaluated in double on the host exactly as written, plus the pinned frame
+int host_prepare(mppi_b200_engine *e, const double *state, double time, const double *wrench, const void *noise, int32_t noise_source, uint64_t seed) {
     DeviceState &d = e->d;
-    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     if (noise_source != MPPI_B200_NOISE_PHILOX && !noise) return fail(e, MPPI_B200_ERR_INVALID, "noise buffer missing");
-    // mppi.cpp:194-201, evaluated in double on the host exactly as written
     const long long shift_by = (long long)((time - e->last_shift_time) / d.dt);
     if (shift_by > d.T) return fail(e, MPPI_B200_ERR_INVALID, "time advanced by more than the horizon (the reference indexes out of range here)");
     if (d.sg_enabled && time < e->sg_last_trim) return fail(e, MPPI_B200_ERR_TIME, "Resetting the window back in the past. Can reset only to larger times than last reset!!!");
     if (shift_by > 0) e->last_shift_time = time;
     e->shift_by = shift_by;
-
-    // the previous update's pinned frame must have been consumed: the stream was synchronised in finish
+    // the previous update's pinned frame has been consumed: finish waited for its stream work
     Frame *f = reinterpret_cast<Frame *>(e->h_frame);
     std::memset(f->x0, 0, sizeof f->x0);
     std::memcpy(f->x0, state, sizeof(double) * d.nx);
@@ -342,8 +352,14 @@ int mppi_b200_update_begin(mppi_b200_engine *e, const double *state, double time
     f->update_index = (unsigned long long)e->update_count;
     f->has_wrench = wrench != nullptr; f->noise_source = noise_source;
     if (wrench) std::memcpy(e->h_frame + sizeof(Frame), wrench, sizeof(double) * 6 * d.T);
+    // double-buffered snapshot for the side-stream re-rollout
+    const int slot = (int)(e->update_count & 1);
+    d.frame_snap = e->d_frame_snap[slot]; d.U_snap = e->d_U_snap[slot];
+    return MPPI_B200_OK;
+}
 
-    CUDA_TRY(e, cudaEventRecord(e->ev_start, e->stream));
+int enqueue_begin(mppi_b200_engine *e, const void *noise, int32_t noise_source) {
+    DeviceState &d = e->d;
     STAGE(e, 0);
     CUDA_TRY(e, cudaMemcpyAsync(e->d_frame, e->h_frame, e->frame_bytes, cudaMemcpyHostToDevice, e->stream));
     const int prec = e->cfg.precision;
@@ -369,13 +385,10 @@ int mppi_b200_update_begin(mppi_b200_engine *e, const double *state, double time
     STAGE(e, 4);
     CUDA_TRY(e, launch_minmax_publish(d, e->stream)); launches++;
     e->launches += launches;
-    e->in_update = true;
     return MPPI_B200_OK;
 }
 
-int mppi_b200_update_weights(mppi_b200_engine *e) {
-    if (!e || !e->in_update) return MPPI_B200_ERR_INVALID;
-    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+int enqueue_weights(mppi_b200_engine *e) {
     int launches = 1;
     CUDA_TRY(e, launch_weights(e->d, e->stream));
     STAGE(e, 5);
@@ -384,73 +397,144 @@ int mppi_b200_update_weights(mppi_b200_engine *e) {
     return MPPI_B200_OK;
 }
 
-int mppi_b200_update_finish(mppi_b200_engine *e) {
-    if (!e || !e->in_update) return MPPI_B200_ERR_INVALID;
-    DeviceState &d = e->d;
-    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
-    const size_t n = (size_t)d.nu * d.T;
+int enqueue_finish(mppi_b200_engine *e) {
     STAGE(e, 6);
-    CUDA_TRY(e, launch_finish(d, e->stream));
+    CUDA_TRY(e, launch_finish(e->d, e->stream));   // writes U and the update's scalars straight into host-mapped memory
     e->launches += 1;
     STAGE(e, 7);
-    // k_finish wrote the control sequence and the update's scalars straight into host-mapped memory
-    CUDA_TRY(e, cudaEventRecord(e->ev_end, e->stream));
-    STAGE(e, 8);
-    // Optimal re-rollout (Trajectory::filter, mppi.cpp:450-479) off the critical path: with no
-    // mppi::Filter attached (actor.cpp:100) it only produces the optimal cost and its per-term
-    // breakdown, so it runs on a side stream over a snapshot of this update's inputs.
-    if (e->side_pending) CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_side_done, 0));
-    CUDA_TRY(e, cudaMemcpyAsync(e->d_frame_snap, e->d_frame, e->frame_bytes, cudaMemcpyDeviceToDevice, e->stream));
-    CUDA_TRY(e, cudaMemcpyAsync(e->d_U_snap, d.U_shift, n * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+    return MPPI_B200_OK;
+}
+
+// Optimal re-rollout (Trajectory::filter, mppi.cpp:450-479) off the critical path: with no mppi::Filter
+// attached (actor.cpp:100) it only produces the optimal cost and its per-term breakdown, so it runs on a
+// side stream over the snapshot k_prepare / k_finish left in this update's slot.
+int launch_optimal(mppi_b200_engine *e) {
+    DeviceState &d = e->d;
+    const int slot = (int)(e->update_count & 1);
     CUDA_TRY(e, cudaEventRecord(e->ev_main_done, e->stream));
     CUDA_TRY(e, cudaStreamWaitEvent(e->side, e->ev_main_done, 0));
-    {
-        DeviceState o = d;
-        o.frame = reinterpret_cast<const Frame *>(e->d_frame_snap);
-        o.wrench = reinterpret_cast<const double *>(e->d_frame_snap + sizeof(Frame));
-        o.U_shift = e->d_U_snap;
-        o.noise = e->d_zero_row;
-        CUDA_TRY(e, launch_rollout(o, e->cfg.precision, e->variant, e->faithful, e->params.data(), true, e->side));
-        e->launches += 1;
-        CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 6, d.optimal_cost, sizeof(double), cudaMemcpyDeviceToHost, e->side));
-        CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 7, d.breakdown, 8 * sizeof(double), cudaMemcpyDeviceToHost, e->side));
-        CUDA_TRY(e, cudaEventRecord(e->ev_side_done, e->side));
-        e->side_pending = true;
-    }
+    DeviceState o = d;
+    o.frame = reinterpret_cast<const Frame *>(e->d_frame_snap[slot]);
+    o.wrench = e->d_frame_snap[slot] + sizeof(Frame) / sizeof(double);
+    o.U_shift = e->d_U_snap[slot];
+    o.noise = e->d_zero_row;
+    CUDA_TRY(e, launch_rollout(o, e->cfg.precision, e->variant, e->faithful, e->params.data(), true, e->side));
+    e->launches += 1;
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 6, d.optimal_cost, sizeof(double), cudaMemcpyDeviceToHost, e->side));
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 7, d.breakdown, 8 * sizeof(double), cudaMemcpyDeviceToHost, e->side));
+    CUDA_TRY(e, cudaEventRecord(e->ev_side_done[slot], e->side));
+    e->side_pending[slot] = true;
+    return MPPI_B200_OK;
+}
+
+// wait for the results, then the reference's end-of-update bookkeeping (mppi.cpp:178-186)
+int host_complete(mppi_b200_engine *e) {
+    DeviceState &d = e->d;
+    const size_t n = (size_t)d.nu * d.T;
     CUDA_TRY(e, cudaEventSynchronize(e->ev_end));
     cudaEventElapsedTime(&e->last_ms, e->ev_start, e->ev_end);
     if (e->profiling) {
         for (int i = 0; i < MPPI_B200_STAGES; i++) { float ms = 0.f; cudaEventElapsedTime(&ms, e->ev_stage[i], e->ev_stage[i + 1]); e->stage_s[i] = ms * 1e-3; }
     }
     e->in_update = false;
-    // mppi.cpp:368-370: no (or a single) valid rollout is an error; nothing is published
     std::memcpy(e->h_stats, e->h_result + n, 5 * sizeof(double));   // {-min, max, valid}, argmin, sum w
-    if (!(e->h_stats[2] >= 2.0)) {
-        return fail(e, MPPI_B200_ERR_ALL_NAN, "all nan rollouts");
-    }
+    // mppi.cpp:368-370: no (or a single) valid rollout is an error; nothing is published
+    if (!(e->h_stats[2] >= 2.0)) return fail(e, MPPI_B200_ERR_ALL_NAN, "all nan rollouts");
     std::memcpy(e->h_U, e->h_result, n * sizeof(double));
     std::memcpy(&e->argmin, e->h_stats + 3, sizeof(long long));
-    if (!(e->h_stats[1] + e->h_stats[0] < 1e-6)) { e->weights_total = e->h_stats[4]; e->weights_valid = true; }  // early return leaves the weights untouched
-    if (d.sg_enabled && !(e->h_stats[1] + e->h_stats[0] < 1e-6)) e->sg_last_trim = reinterpret_cast<Frame *>(e->h_frame)->time;
+    const bool early_return = e->h_stats[1] + e->h_stats[0] < 1e-6;  // max - min < 1e-6 (mppi.cpp:373-375)
+    if (!early_return) { e->weights_total = e->h_stats[4]; e->weights_valid = true; }
+    if (d.sg_enabled && !early_return) e->sg_last_trim = reinterpret_cast<Frame *>(e->h_frame)->time;
     e->last_rollout_time = reinterpret_cast<Frame *>(e->h_frame)->time;
     e->update_count++;
     return MPPI_B200_OK;
 }
 
+// the previous user of this update's snapshot slot (two updates ago) must have finished
+int wait_slot(mppi_b200_engine *e) {
+    const int slot = (int)(e->update_count & 1);
+    if (e->side_pending[slot]) CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_side_done[slot], 0));
+    return MPPI_B200_OK;
+}
+
+}  // namespace
+
+int mppi_b200_update_begin(mppi_b200_engine *e, const double *state, double time, const double *wrench, const void *noise, int32_t noise_source, uint64_t seed) {
+    if (!e || !state) return MPPI_B200_ERR_INVALID;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    int rc = host_prepare(e, state, time, wrench, noise, noise_source, seed);
+    if (rc) return rc;
+    if ((rc = wait_slot(e))) return rc;
+    CUDA_TRY(e, cudaEventRecord(e->ev_start, e->stream));
+    if ((rc = enqueue_begin(e, noise, noise_source))) return rc;
+    e->in_update = true;
+    return MPPI_B200_OK;
+}
+
+int mppi_b200_update_weights(mppi_b200_engine *e) {
+    if (!e || !e->in_update) return MPPI_B200_ERR_INVALID;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    return enqueue_weights(e);
+}
+
+int mppi_b200_update_finish(mppi_b200_engine *e) {
+    if (!e || !e->in_update) return MPPI_B200_ERR_INVALID;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    int rc = enqueue_finish(e);
+    if (rc) return rc;
+    CUDA_TRY(e, cudaEventRecord(e->ev_end, e->stream));
+    STAGE(e, 8);
+    if ((rc = launch_optimal(e))) return rc;
+    return host_complete(e);
+}
+
 int mppi_b200_update(mppi_b200_engine *e, const double *state, double time, const double *wrench, const void *noise, int32_t noise_source, uint64_t seed) {
-    int rc = mppi_b200_update_begin(e, state, time, wrench, noise, noise_source, seed);
-    if (rc) return rc;
-    if (e->comm) {
-        ncclResult_t r = g_nccl.AllReduce(e->d.minmax, e->d.minmax, 3, ncclDouble, ncclMax, e->comm, e->stream);
-        if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-reduce failed");
+    if (!e || !state) return MPPI_B200_ERR_INVALID;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    // Production path (in-kernel Philox, one GPU): the whole update is ONE CUDA graph launch. The kernels take
+    // no per-update arguments (everything varying lives in the frame), so the graph is captured once per
+    // snapshot slot and replayed.
+    const bool graph_ok = e->use_graphs && noise_source == MPPI_B200_NOISE_PHILOX && !e->comm && !e->profiling;
+    if (!graph_ok) {
+        int rc = mppi_b200_update_begin(e, state, time, wrench, noise, noise_source, seed);
+        if (rc) return rc;
+        if (e->comm) {
+            ncclResult_t r = g_nccl.AllReduce(e->d.minmax, e->d.minmax, 3, ncclDouble, ncclMax, e->comm, e->stream);
+            if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-reduce failed");
+        }
+        if ((rc = mppi_b200_update_weights(e))) return rc;
+        if (e->comm) {
+            ncclResult_t r = g_nccl.AllReduce(e->d.sums, e->d.sums, 1 + (size_t)e->d.nu * e->d.T, ncclDouble, ncclSum, e->comm, e->stream);
+            if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-reduce failed");
+        }
+        return mppi_b200_update_finish(e);
     }
-    rc = mppi_b200_update_weights(e);
+    int rc = host_prepare(e, state, time, wrench, noise, noise_source, seed);
     if (rc) return rc;
-    if (e->comm) {
-        ncclResult_t r = g_nccl.AllReduce(e->d.sums, e->d.sums, 1 + (size_t)e->d.nu * e->d.T, ncclDouble, ncclSum, e->comm, e->stream);
-        if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-reduce failed");
+    const int slot = (int)(e->update_count & 1);
+    if (!e->graph[slot]) {
+        cudaGraph_t g = nullptr;
+        const long long before = e->launches;
+        CUDA_TRY(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_begin(e, nullptr, MPPI_B200_NOISE_PHILOX);
+        if (!rc) rc = enqueue_weights(e);
+        if (!rc) rc = enqueue_finish(e);
+        cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+        e->graph_launches = (int)(e->launches - before);
+        e->launches = before;
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (ce != cudaSuccess) return fail(e, MPPI_B200_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&e->graph[slot], g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) return fail(e, MPPI_B200_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
     }
-    return mppi_b200_update_finish(e);
+    if ((rc = wait_slot(e))) return rc;
+    CUDA_TRY(e, cudaEventRecord(e->ev_start, e->stream));
+    CUDA_TRY(e, cudaGraphLaunch(e->graph[slot], e->stream));
+    CUDA_TRY(e, cudaEventRecord(e->ev_end, e->stream));
+    e->launches += e->graph_launches;
+    if ((rc = launch_optimal(e))) return rc;
+    return host_complete(e);
 }
 
 int mppi_b200_reduce_buffers(mppi_b200_engine *e, void **minmax, size_t *minmax_count, void **sums, size_t *sums_count) {

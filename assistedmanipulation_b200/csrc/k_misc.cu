@@ -56,6 +56,7 @@ __device__ __forceinline__ void box_muller(unsigned a, unsigned b, float *z0, fl
 template <class R> __global__ void k_prepare(const __grid_constant__ DeviceState d) {
     const int n = d.nu * d.T;
     const long long shift = d.frame->shift_by;
+    for (int i = threadIdx.x; i < d.frame_doubles; i += blockDim.x) d.frame_snap[i] = reinterpret_cast<const double *>(d.frame)[i];
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
         if (shift > 0) {
             const int t = e / d.nu, dd = e - t * d.nu;
@@ -455,6 +456,7 @@ __global__ void __launch_bounds__(512) k_finish(const __grid_constant__ DeviceSt
         }
         d.U_shift[e] = u;
         d.U[e] = u;        // publication: m_optimal_control = m_optimal_control_shifted (mppi.cpp:178-182)
+        d.U_snap[e] = u;   // input of the optimal re-rollout (side stream)
         d.result[e] = u;   // host-mapped copy, visible to the caller when the stream completes
     }
 }
