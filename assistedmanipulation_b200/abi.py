@@ -91,6 +91,7 @@ EXPORTS = [
     "mppi_b200_query", "mppi_b200_last_update_device_seconds", "mppi_b200_default_track_point",
     "mppi_b200_default_assisted_manipulation", "mppi_b200_default_toy_objective",
     "mppi_b200_set_profiling", "mppi_b200_stage_seconds", "mppi_b200_measure_fma_peak",
+    "mppi_b200_update_launch", "mppi_b200_update_wait",
 ]
 STAGES = ("h2d", "warm_start_shift", "sample", "rollout", "weights", "weighted_sum", "finish", "d2h")
 
@@ -120,6 +121,10 @@ def load_library(path=None):
     lib.mppi_b200_update.restype = C.c_int
     lib.mppi_b200_update_begin.argtypes = upd
     lib.mppi_b200_update_begin.restype = C.c_int
+    lib.mppi_b200_update_launch.argtypes = upd
+    lib.mppi_b200_update_launch.restype = C.c_int
+    lib.mppi_b200_update_wait.argtypes = [C.c_void_p]
+    lib.mppi_b200_update_wait.restype = C.c_int
     for f in (lib.mppi_b200_update_weights, lib.mppi_b200_update_finish, lib.mppi_b200_synchronize):
         f.argtypes = [C.c_void_p]
         f.restype = C.c_int

@@ -32,6 +32,7 @@ struct Nccl {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool load(std::string *why) {
@@ -42,9 +43,10 @@ struct Nccl {
         GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
         CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
         AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
+        AllGather = (decltype(AllGather))dlsym(handle, "ncclAllGather");
         CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
         GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
-        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { *why = "libnccl lacks required symbols"; return false; }
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !AllGather || !CommDestroy) { *why = "libnccl lacks required symbols"; return false; }
         return true;
     }
 };
@@ -214,7 +216,6 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     if (c->threads <= 0) return fail_create(MPPI_B200_ERR_INVALID, "trajectory threads must be positive nonzero");
     if (c->precision != MPPI_B200_FP64 && c->precision != MPPI_B200_FP32) return fail_create(MPPI_B200_ERR_INVALID, "precision");
     if (c->world_size < 1 || c->rank < 0 || c->rank >= c->world_size) return fail_create(MPPI_B200_ERR_INVALID, "rank / world_size");
-    if (c->world_size > 1 && c->keep_best_rollouts > 0) return fail_create(MPPI_B200_ERR_UNSUPPORTED, "keep_best_rollouts > 0 is not available for a sharded rollout set yet");
     if (!(c->time_step > 0) || !(c->horison > 0)) return fail_create(MPPI_B200_ERR_INVALID, "time_step and horison must be positive");
     if (c->smoothing && c->smoothing_window > (unsigned)MAX_WINDOW) return fail_create(MPPI_B200_ERR_UNSUPPORTED, "smoothing window too large");
     const int T = (int)std::ceil(c->horison / c->time_step);  // mppi.cpp:85
@@ -300,6 +301,8 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     d.wrench = reinterpret_cast<const double *>(e->d_frame + sizeof(Frame));
     A(d.U, n); A(d.U_shift, n); A(d.costs, (size_t)d.k_count); A(d.weights, (size_t)d.k_count);
     A(d.kept, (size_t)d.k_count); A(d.kept_list, (size_t)std::max<long long>(d.keep_best, 1));
+    d.world = c->world_size;
+    A(d.cand, (size_t)2 * std::max<long long>(d.keep_best, 1)); A(d.cand_all, (size_t)2 * std::max<long long>(d.keep_best, 1) * c->world_size);
     A(d.minmax_enc, 2); A(d.valid_count, 1); A(d.argmin, 1); A(d.minmax, 4); A(d.sums, 1 + n);
     d.weight_blocks = (int)((d.k_count + 255) / 256);
     int sms = 148;
@@ -376,7 +379,17 @@ int enqueue_begin(mppi_b200_engine *e, const void *noise, int32_t noise_source) 
     }
     int launches = 0;
     STAGE(e, 1);
-    if (d.keep_best > 0) { CUDA_TRY(e, launch_select_kept(d, e->stream)); launches++; }
+    if (d.keep_best > 0) {
+        CUDA_TRY(e, launch_select_kept(d, e->stream)); launches++;
+        if (d.world > 1) {
+            // warm start over a sharded set: all-gather every rank's best candidates, merge identically everywhere
+            if (!e->comm) return fail(e, MPPI_B200_ERR_UNSUPPORTED, "keep_best_rollouts > 0 on a sharded rollout set needs the in-library NCCL exchange (mppi_b200_comm_init)");
+            const long long keep = std::min<long long>(d.keep_best, d.K_total - 2);
+            ncclResult_t r = g_nccl.AllGather(d.cand, d.cand_all, (size_t)2 * keep, ncclDouble, e->comm, e->stream);
+            if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-gather failed");
+            CUDA_TRY(e, launch_merge_kept(d, e->stream)); launches++;
+        }
+    }
     CUDA_TRY(e, launch_prepare(d, prec, e->stream)); launches++;
     STAGE(e, 2);
     CUDA_TRY(e, launch_sample(d, prec, e->stream, &launches));
@@ -488,31 +501,17 @@ int mppi_b200_update_finish(mppi_b200_engine *e) {
     return host_complete(e);
 }
 
-int mppi_b200_update(mppi_b200_engine *e, const double *state, double time, const double *wrench, const void *noise, int32_t noise_source, uint64_t seed) {
-    if (!e || !state) return MPPI_B200_ERR_INVALID;
+int mppi_b200_update_launch(mppi_b200_engine *e, const double *state, double time, const double *wrench, const void *noise, int32_t noise_source, uint64_t seed) {
+    if (!e || !state || e->in_update) return MPPI_B200_ERR_INVALID;
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     // Production path (in-kernel Philox, one GPU): the whole update is ONE CUDA graph launch. The kernels take
     // no per-update arguments (everything varying lives in the frame), so the graph is captured once per
     // snapshot slot and replayed.
     const bool graph_ok = e->use_graphs && noise_source == MPPI_B200_NOISE_PHILOX && !e->comm && !e->profiling;
-    if (!graph_ok) {
-        int rc = mppi_b200_update_begin(e, state, time, wrench, noise, noise_source, seed);
-        if (rc) return rc;
-        if (e->comm) {
-            ncclResult_t r = g_nccl.AllReduce(e->d.minmax, e->d.minmax, 3, ncclDouble, ncclMax, e->comm, e->stream);
-            if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-reduce failed");
-        }
-        if ((rc = mppi_b200_update_weights(e))) return rc;
-        if (e->comm) {
-            ncclResult_t r = g_nccl.AllReduce(e->d.sums, e->d.sums, 1 + (size_t)e->d.nu * e->d.T, ncclDouble, ncclSum, e->comm, e->stream);
-            if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-reduce failed");
-        }
-        return mppi_b200_update_finish(e);
-    }
     int rc = host_prepare(e, state, time, wrench, noise, noise_source, seed);
     if (rc) return rc;
     const int slot = (int)(e->update_count & 1);
-    if (!e->graph[slot]) {
+    if (graph_ok && !e->graph[slot]) {
         cudaGraph_t g = nullptr;
         const long long before = e->launches;
         CUDA_TRY(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
@@ -530,11 +529,38 @@ int mppi_b200_update(mppi_b200_engine *e, const double *state, double time, cons
     }
     if ((rc = wait_slot(e))) return rc;
     CUDA_TRY(e, cudaEventRecord(e->ev_start, e->stream));
-    CUDA_TRY(e, cudaGraphLaunch(e->graph[slot], e->stream));
+    if (graph_ok) {
+        CUDA_TRY(e, cudaGraphLaunch(e->graph[slot], e->stream));
+        e->launches += e->graph_launches;
+    } else {
+        if ((rc = enqueue_begin(e, noise, noise_source))) return rc;
+        if (e->comm) {
+            ncclResult_t r = g_nccl.AllReduce(e->d.minmax, e->d.minmax, 3, ncclDouble, ncclMax, e->comm, e->stream);
+            if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-reduce failed");
+        }
+        if ((rc = enqueue_weights(e))) return rc;
+        if (e->comm) {
+            ncclResult_t r = g_nccl.AllReduce(e->d.sums, e->d.sums, 1 + (size_t)e->d.nu * e->d.T, ncclDouble, ncclSum, e->comm, e->stream);
+            if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-reduce failed");
+        }
+        if ((rc = enqueue_finish(e))) return rc;
+    }
     CUDA_TRY(e, cudaEventRecord(e->ev_end, e->stream));
-    e->launches += e->graph_launches;
+    STAGE(e, 8);
     if ((rc = launch_optimal(e))) return rc;
+    e->in_update = true;
+    return MPPI_B200_OK;
+}
+
+int mppi_b200_update_wait(mppi_b200_engine *e) {
+    if (!e || !e->in_update) return MPPI_B200_ERR_INVALID;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     return host_complete(e);
+}
+
+int mppi_b200_update(mppi_b200_engine *e, const double *state, double time, const double *wrench, const void *noise, int32_t noise_source, uint64_t seed) {
+    const int rc = mppi_b200_update_launch(e, state, time, wrench, noise, noise_source, seed);
+    return rc ? rc : mppi_b200_update_wait(e);
 }
 
 int mppi_b200_reduce_buffers(mppi_b200_engine *e, void **minmax, size_t *minmax_count, void **sums, size_t *sums_count) {

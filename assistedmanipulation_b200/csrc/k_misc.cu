@@ -80,25 +80,25 @@ template <class R> __global__ void k_prepare(const __grid_constant__ DeviceState
 // ---- warm start: the keep_best lowest-cost rollouts of the PREVIOUS update (stable order) -----------
 // mppi.cpp:222-253. One block; each round finds the smallest (cost, index) pair that is strictly
 // greater than the previous pick, which enumerates the stable sort order without sorting.
-__global__ void k_select_kept(const __grid_constant__ DeviceState d) {
+// Enumerates, in stable-sort order, the `keep` smallest (key, index) pairs of a candidate list: each round
+// finds the smallest pair strictly greater than the previous pick. One block.
+template <class GetKey, class GetIdx, class Emit>
+__device__ __forceinline__ void select_smallest(long long count, long long keep, GetKey key_of, GetIdx idx_of, Emit emit) {
     __shared__ unsigned long long s_key[32];
     __shared__ long long s_idx[32];
     __shared__ unsigned long long last_key;
     __shared__ long long last_idx;
-    const long long first = 2;  // s_static_rollouts
-    for (long long k = threadIdx.x; k < d.k_count; k += blockDim.x) d.kept[k] = 0;
     if (threadIdx.x == 0) { last_key = 0; last_idx = -1; }
     __syncthreads();
-    const long long keep = d.keep_best < d.K_total - 2 ? d.keep_best : d.K_total - 2;
     for (long long round = 0; round < keep; round++) {
         unsigned long long best = 0xffffffffffffffffull; long long bi = 0x7fffffffffffffffll;
         const unsigned long long lk = last_key; const long long li = last_idx;
-        for (long long k = first + threadIdx.x; k < d.k_count; k += blockDim.x) {
-            double c = d.costs[k];
-            if (c != c) c = CUDART_INF;  // NaN sorts last (SURVEY A-2)
-            const unsigned long long key = encode_ordered(c);
-            const bool after = (key > lk) || (key == lk && k > li);
-            if (after && (key < best || (key == best && k < bi))) { best = key; bi = k; }
+        for (long long k = threadIdx.x; k < count; k += blockDim.x) {
+            const long long gi = idx_of(k);
+            if (gi < 2) continue;  // the two static rollouts are never candidates (mppi.cpp:222)
+            const unsigned long long key = key_of(k);
+            const bool after = (key > lk) || (key == lk && gi > li);
+            if (after && (key < best || (key == best && gi < bi))) { best = key; bi = gi; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -118,13 +118,45 @@ __global__ void k_select_kept(const __grid_constant__ DeviceState d) {
                 const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (ok < best || (ok == best && oi < bi)) { best = ok; bi = oi; }
             }
-            if (threadIdx.x == 0) {
-                last_key = best; last_idx = bi;
-                if (bi != 0x7fffffffffffffffll) { d.kept[bi] = 1; d.kept_list[round] = bi + d.k_begin; }
-            }
+            if (threadIdx.x == 0) { last_key = best; last_idx = bi; emit(round, best, bi); }
         }
         __syncthreads();
     }
+}
+
+// mppi.cpp:222-253 on this rank's rollouts. With one rank the picks ARE the kept set; with several the picks
+// are this rank's candidates, all-gathered and merged by k_merge_kept.
+__global__ void k_select_kept(const __grid_constant__ DeviceState d) {
+    for (long long k = threadIdx.x; k < d.k_count; k += blockDim.x) d.kept[k] = 0;
+    __syncthreads();
+    const long long keep = d.keep_best < d.K_total - 2 ? d.keep_best : d.K_total - 2;
+    select_smallest(
+        d.k_count, keep,
+        [&](long long k) { double c = d.costs[k]; if (c != c) c = CUDART_INF; return encode_ordered(c); },  // NaN sorts last (SURVEY A-2)
+        [&](long long k) { return k + d.k_begin; },
+        [&](long long round, unsigned long long key, long long gi) {
+            const bool found = gi != 0x7fffffffffffffffll;
+            if (d.world == 1) {
+                if (found) { d.kept[gi - d.k_begin] = 1; d.kept_list[round] = gi; }
+            } else {
+                d.cand[2 * round] = found ? decode_ordered(key) : CUDART_INF;
+                d.cand[2 * round + 1] = __longlong_as_double(found ? gi : 0x7fffffffffffffffll);
+            }
+        });
+}
+
+// every rank merges the same world x keep candidate list into the global kept set
+__global__ void k_merge_kept(const __grid_constant__ DeviceState d) {
+    const long long keep = d.keep_best < d.K_total - 2 ? d.keep_best : d.K_total - 2;
+    select_smallest(
+        (long long)d.world * keep, keep,
+        [&](long long k) { return encode_ordered(d.cand_all[2 * k]); },
+        [&](long long k) { const long long gi = __double_as_longlong(d.cand_all[2 * k + 1]); return gi == 0x7fffffffffffffffll ? -1 : gi; },
+        [&](long long round, unsigned long long, long long gi) {
+            if (gi == 0x7fffffffffffffffll) return;
+            d.kept_list[round] = gi;
+            if (gi >= d.k_begin && gi < d.k_begin + d.k_count) d.kept[gi - d.k_begin] = 1;
+        });
 }
 
 // ---- K1 sample -----------------------------------------------------------------------------------
@@ -515,6 +547,10 @@ cudaError_t launch_prepare(const DeviceState &d, int precision, cudaStream_t s) 
 
 cudaError_t launch_select_kept(const DeviceState &d, cudaStream_t s) {
     k_select_kept<<<1, 1024, 0, s>>>(d);
+    return cudaGetLastError();
+}
+cudaError_t launch_merge_kept(const DeviceState &d, cudaStream_t s) {
+    k_merge_kept<<<1, 256, 0, s>>>(d);
     return cudaGetLastError();
 }
 

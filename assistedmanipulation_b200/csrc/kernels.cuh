@@ -47,6 +47,9 @@ struct DeviceState {
     double *weights;       // k_count (unnormalised until finish)
     unsigned char *kept;   // k_count flags for the warm start
     long long *kept_list;  // keep_best global indices, sorted order
+    int world;             // ranks sharing the rollout set
+    double *cand;          // this rank's keep_best best (cost, global index bits) pairs — all-gathered when sharded
+    double *cand_all;      // world x keep_best pairs
     unsigned long long *minmax_enc;  // [2] order-preserving encodings for atomicMin / atomicMax
     int *valid_count;      // number of non-NaN local rollouts
     long long *argmin;     // global index of the best rollout
@@ -84,6 +87,7 @@ cudaError_t upload_robot_model();  // once per device
 
 cudaError_t launch_prepare(const DeviceState &d, int precision, cudaStream_t s);
 cudaError_t launch_select_kept(const DeviceState &d, cudaStream_t s);
+cudaError_t launch_merge_kept(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_sample(const DeviceState &d, int precision, cudaStream_t s, int *launches);
 // objective params: pointer to the host-side block in kernel arithmetic (ToyP/TrackPointP/AssistedP<R>)
 cudaError_t launch_rollout(const DeviceState &d, int precision, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s);

@@ -33,7 +33,7 @@ from assistedmanipulation_b200 import abi  # noqa: E402
 
 # Algorithmic work per rollout-step: Featherstone operation counts at n = 12 one-dof
 # joints — ABA 4641 + RNEA 1880 + second-order FK / frames / WORLD jacobian ~2300 + cost + Euler + tank.
-FLOPS_PER_STEP = {"cfg2": 9000.0, "cfg3": 9500.0, "toy": 25.0}
+FLOPS_PER_STEP = {"cfg2": 9000.0, "cfg3": 9500.0, "toy": 25.0, "cfg4_f32": 9000.0, "cfg4_f64": 9000.0}
 
 
 def workload(name, n_gpus):
@@ -48,6 +48,12 @@ def workload(name, n_gpus):
     if name == "toy":
         return dict(name="toy_double_integrator_K1024xT100_fp64", system=abi.SYSTEM_TOY, objective=abi.OBJECTIVE_TOY, params=abi.default_toy_objective(),
                     K=1024 * n_gpus, horison=1.0, precision=abi.FP64, dtype="f64", x0=np.zeros(4), wrench=None)
+    if name in ("cfg4_f32", "cfg4_f64"):
+        # BASELINE.json config 4: K = 1 048 576 x T = 64 sharded over the ranks (total work fixed: strong scaling)
+        f32 = name.endswith("f32")
+        return dict(name="franka_ridgeback_trackpoint_K1048576xT64_" + ("fp32" if f32 else "fp64"), system=abi.SYSTEM_FRANKA_RIDGEBACK,
+                    objective=abi.OBJECTIVE_TRACK_POINT, params=abi.default_track_point(), K=1048576, horison=0.64,
+                    precision=abi.FP32 if f32 else abi.FP64, dtype="f32" if f32 else "f64", x0=abi.huddled_state(), wrench=None, scaling="strong")
     raise SystemExit("unknown workload " + name)
 
 
@@ -102,6 +108,84 @@ def run_oracle(wl, steps, warmup, threads, budget_s=None):
     return np.array(times), T, R, phases
 
 
+def bench_controllers(args, rank, world, local_rank, n_gpus, dist, torch, el):
+    """BASELINE.json config 5: 256 independent Franka+Ridgeback controllers (K=1024 x T=64 each, assisted-
+    manipulation objective, FP32 fast mode, per-controller state and forecast-wrench table), 256/N per GPU,
+    no collective. One tick = every controller updates once: all launches first, then all waits, so the
+    updates overlap on the device (mppi_b200_update_launch / _wait)."""
+    import cases
+    total, K, T = 256, 1024, 64
+    mine = list(range(rank, total, world))
+    params = cases.assisted_params(True, abi.LINKS_BODY_COM)
+    engines, states, wrenches = [], [], []
+    for c in mine:
+        h = abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_ASSISTED_MANIPULATION, K, 0.64, precision=abi.FP32, dynamics_mode=abi.DYNAMICS_FUSED,
+                            keep_best=0, device=local_rank)
+        engines.append(el.Engine(h, params))
+        x0 = abi.huddled_state(10.0)
+        x0[0] += 0.002 * c; x0[1] -= 0.001 * c; x0[2] += 0.003 * c     # per-controller base offset
+        states.append(np.ascontiguousarray(x0))
+        ang = 2 * np.pi * c / total + 0.5 * np.arange(T) * 0.01        # a force vector that turns over the horizon
+        w = np.zeros((T, 6)); w[:, 0] = 10 * np.cos(ang); w[:, 1] = 10 * np.sin(ang)
+        wrenches.append(np.ascontiguousarray(w))
+    lib = engines[0].lib
+
+    def tick(step):
+        for e, x, w in zip(engines, states, wrenches):
+            rc = lib.mppi_b200_update_launch(e.h, el.ptr(x), 0.05 * step, el.ptr(w), None, abi.NOISE_PHILOX, 1)
+            assert rc == 0, e.error()
+        for e in engines:
+            rc = lib.mppi_b200_update_wait(e.h)
+            assert rc == 0, e.error()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step = 0
+    for _ in range(args.warmup):
+        tick(step); step += 1
+    launches0 = sum(e.query(abi.QUERY_KERNEL_LAUNCHES) for e in engines)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ticks = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        tick(step); step += 1
+        ticks.append(time.perf_counter() - t0)
+    barrier()
+    sampler.stop_flag = True
+    sampler.join()
+    launches = sum(e.query(abi.QUERY_KERNEL_LAUNCHES) for e in engines) - launches0
+    dev = np.array([e.device_seconds() for e in engines])
+    t_wall = float(np.sum(ticks))
+    if world > 1:
+        tt = torch.tensor([t_wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_wall = float(tt[0])
+        dist.destroy_process_group()
+    for e in engines:
+        e.close()
+    if rank != 0:
+        return 0
+    units = total * (K + 2) * T * args.steps
+    ticks = np.array(ticks)
+    line = {"metric": "rollout-steps/s", "value": units / t_wall, "unit": "rollout-steps/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_wall / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "256_controllers_franka_ridgeback_assisted_K1024xT64_fp32", "controllers": total, "controllers_per_gpu": len(mine),
+                       "rollouts": K, "steps_per_rollout": T, "noise": "in-kernel Philox4x32-10", "parallelism": "controllers split over %d GPU(s), no collective" % world,
+                       "timing": "host clock around one tick (launch all controllers, wait for all); per-controller states and wrench tables come from host memory every tick"},
+            "clocks": sampler.result(),
+            "e2e": {"value": units / t_wall, "unit": "rollout-steps/s", "h2d_bytes_per_step": int(len(mine) * 8 * (40 + 6 * T)), "d2h_bytes_per_step": int(len(mine) * 8 * (12 * T + 5)),
+                    "tick_latency_us": {"p50": float(np.median(ticks) * 1e6), "p99": float(np.percentile(ticks, 99) * 1e6)}},
+            "gpu_launches": int(launches),
+            "per_controller_device_update_us": {"p50": float(np.median(dev) * 1e6), "max": float(dev.max() * 1e6)}}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -117,7 +201,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = max(args.gpus, 1)
     args.warmup = max(args.warmup, 3)
-    wl = workload(args.workload, n_gpus)
+    wl = workload(args.workload if args.workload != "cfg5" else "cfg3", n_gpus)
     host_threads = os.cpu_count() or 1
 
     if args.impl == "reference":
@@ -144,6 +228,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.workload == "cfg5":
+        return bench_controllers(args, rank, world, local_rank, n_gpus, dist, torch, el)
     holder = abi.make_config(wl["system"], wl["objective"], wl["K"], wl["horison"], precision=wl["precision"], dynamics_mode=abi.DYNAMICS_FUSED,
                              keep_best=0, device=local_rank, rank=rank, world_size=world)
     e = el.Engine(holder, wl["params"])
@@ -231,7 +317,7 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     line = {
         "metric": "rollout-steps/s", "value": units / t_dev, "unit": "rollout-steps/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+        "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": wl.get("scaling", "weak"), "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
         "config": {"workload": wl["name"], "rollouts": wl["K"], "static_rollouts": 2, "steps_per_rollout": T, "time_step": 0.01, "update_cadence_s": 0.05,
                    "noise": "in-kernel Philox4x32-10", "dynamics_mode": "fused", "keep_best_rollouts": 0,
                    "parallelism": "rollouts sharded over %d GPU(s); NCCL all-reduce of [-min,max] and [sum w, sum w*eps]" % world,

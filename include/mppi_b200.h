@@ -180,6 +180,14 @@ const char *mppi_b200_last_error(const mppi_b200_engine *engine);
 int mppi_b200_update(mppi_b200_engine *engine, const double *state, double time, const double *wrench,
                      const void *noise, int32_t noise_source, uint64_t seed);
 
+/* Asynchronous form of mppi_b200_update for many independent controllers on one device (BASELINE.json
+ * config 5): _launch enqueues the whole update on the engine's own stream and returns; _wait blocks until
+ * that engine's control sequence is on the host. Launch all engines, then wait for all: their updates
+ * overlap on the GPU. Exactly one _wait per _launch. */
+int mppi_b200_update_launch(mppi_b200_engine *engine, const double *state, double time, const double *wrench,
+                            const void *noise, int32_t noise_source, uint64_t seed);
+int mppi_b200_update_wait(mppi_b200_engine *engine);
+
 /* The same update split at its two exchange points, for rollout sets sharded over engines
  * (one per GPU): begin -> [all-reduce MAX of minmax buffer] -> weights -> [all-reduce SUM of sums
  * buffer] -> finish. All asynchronous on the engine stream until finish returns. */

@@ -20,7 +20,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 K, T, nu = 2046, 32, 12
 tp = abi.default_track_point()
-e = el.Engine(abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_TRACK_POINT, K, 0.32, dynamics_mode=abi.DYNAMICS_FUSED, device=local, rank=rank, world_size=world), tp)
+e = el.Engine(abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_TRACK_POINT, K, 0.32, dynamics_mode=abi.DYNAMICS_FUSED, device=local, rank=rank, world_size=world, keep_best=20), tp)
 uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
 if rank == 0:
     buf = (C.c_ubyte * 128)()
@@ -29,21 +29,23 @@ if rank == 0:
 dist.broadcast(uid, 0)
 assert e.lib.mppi_b200_comm_init(e.h, C.c_char_p(bytes(uid.cpu().tolist()))) == 0, e.error()
 x0 = abi.huddled_state()
-Us = []
-for u in range(3):
+Us, kept = [], []
+for u in range(4):
     assert e.update(x0, 0.05 * u, None, seed=5) == 0, e.error()
     Us.append(e.read(abi.READ_OPTIMAL, nu * T))
+    kept.append(e.read(abi.READ_KEPT, 20, np.int64))
 gathered = [None] * world
 dist.all_gather_object(gathered, Us)
 if rank == 0:
     for other in gathered[1:]:
         for a, b in zip(Us, other):
             assert np.array_equal(a, b)
-    whole = el.Engine(abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_TRACK_POINT, K, 0.32, dynamics_mode=abi.DYNAMICS_FUSED, device=local), tp)
-    o = ol.Oracle(ol.load(), abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_TRACK_POINT, K, 0.32, threads=8), tp)
-    for u in range(3):
+    whole = el.Engine(abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_TRACK_POINT, K, 0.32, dynamics_mode=abi.DYNAMICS_FUSED, device=local, keep_best=20), tp)
+    o = ol.Oracle(ol.load(), abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_TRACK_POINT, K, 0.32, threads=8, keep_best=20), tp)
+    for u in range(4):
         assert whole.update(x0, 0.05 * u, None, seed=5) == 0
         Uw = whole.read(abi.READ_OPTIMAL, nu * T)
+        assert np.array_equal(kept[u], whole.read(abi.READ_KEPT, 20, np.int64))   # the kept set is bit exact across shardings
         assert np.abs(Us[u] - Uw).max() <= 1e-12 * np.abs(Uw).max()
         assert o.update(x0, 0.05 * u, None, whole.read(abi.READ_NOISE, (K + 2) * T * nu)) == 0
         Uo = o.read(abi.READ_OPTIMAL, nu * T)

@@ -102,12 +102,14 @@ def test_two_shards_on_one_gpu(oracle, source):
     o.close()
 
 
-def test_sharded_keep_best_is_rejected():
+def test_sharded_keep_best_needs_the_library_exchange():
+    # the warm start over a sharded set all-gathers candidates through the library's communicator
     import engine_lib as el
     h = abi.make_config(abi.SYSTEM_TOY, abi.OBJECTIVE_TOY, 64, 0.2, keep_best=4, rank=0, world_size=2)
-    out = C.c_void_p()
-    p = abi.default_toy_objective()
-    assert el.lib().mppi_b200_create(C.byref(h.cfg), C.cast(C.byref(p), C.c_void_p), C.sizeof(p), C.byref(out)) == abi.ERR_UNSUPPORTED
+    e = el.Engine(h, abi.default_toy_objective())
+    st = np.zeros(4)
+    assert e.lib.mppi_b200_update_begin(e.h, el.ptr(st), 0.0, None, None, abi.NOISE_PHILOX, 0) == abi.ERR_UNSUPPORTED
+    e.close()
 
 
 def test_nccl_two_gpus():
