@@ -245,6 +245,11 @@ def main():
     T, R = e.query(abi.QUERY_STEP_COUNT), e.query(abi.QUERY_ROLLOUT_COUNT)
     nu = e.query(abi.QUERY_CONTROL_DOF)
     flush = None if args.no_l2_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    # the L2 flush is enqueued on the ENGINE's stream (ordered before the update, outside its CUDA-event
+    # window), so no host synchronisation is needed between timed iterations and the ranks stay in step
+    sp = C.c_void_p()
+    assert e.lib.mppi_b200_stream(e.h, C.byref(sp)) == 0
+    engine_stream = torch.cuda.ExternalStream(sp.value, device=torch.device("cuda", local_rank))
 
     def barrier():
         if world > 1:
@@ -264,8 +269,11 @@ def main():
     t_region0 = time.perf_counter()
     for _ in range(args.steps):
         if flush is not None:
-            flush.fill_(step & 0xff)          # evict L2 between timed iterations
-            torch.cuda.synchronize()
+            with torch.cuda.stream(engine_stream):
+                flush.fill_(step & 0xff)      # evict L2 between timed iterations
+            engine_stream.synchronize()       # keep the flush out of the host-clock (e2e) window too
+        if world > 1:
+            dist.barrier()                    # ranks enter the step together: the in-step all-reduces then measure exchange cost, not host skew
         t0 = time.perf_counter()
         rc = e.update(x0, 0.05 * step, wrench, seed=1)   # host state in, host control sequence out
         t1 = time.perf_counter()
