@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_ALL_NAN, ERR_TIME, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
 SYSTEM_TOY, SYSTEM_FRANKA_RIDGEBACK = 0, 1
@@ -23,7 +23,7 @@ NOISE_PHILOX, NOISE_HOST, NOISE_DEVICE = 0, 1, 2
 (READ_OPTIMAL, READ_COSTS, READ_WEIGHTS, READ_GRADIENT, READ_NOISE, READ_MINMAX, READ_OPTIMAL_COST,
  READ_BREAKDOWN, READ_KEPT) = range(9)
 (QUERY_STEP_COUNT, QUERY_ROLLOUT_COUNT, QUERY_LOCAL_BEGIN, QUERY_LOCAL_COUNT, QUERY_UPDATE_COUNT,
- QUERY_KERNEL_LAUNCHES, QUERY_ARGMIN, QUERY_SHIFT_BY, QUERY_STATE_DOF, QUERY_CONTROL_DOF) = range(10)
+ QUERY_KERNEL_LAUNCHES, QUERY_ARGMIN, QUERY_SHIFT_BY, QUERY_STATE_DOF, QUERY_CONTROL_DOF, QUERY_BATCH) = range(11)
 
 
 class Barrier(C.Structure):
@@ -80,7 +80,7 @@ class Config(C.Structure):
                 ("control_min", C.POINTER(C.c_double)), ("control_max", C.POINTER(C.c_double)),
                 ("control_default", C.POINTER(C.c_double)),
                 ("smoothing", C.c_int32), ("smoothing_window", C.c_uint32), ("smoothing_order", C.c_uint32),
-                ("threads", C.c_int32)]
+                ("threads", C.c_int32), ("batch", C.c_int32)]
 
 
 EXPORTS = [
@@ -182,7 +182,7 @@ class ConfigHolder:
 def make_config(system, objective, rollouts, horison, *, precision=FP64, dynamics_mode=DYNAMICS_FAITHFUL,
                 keep_best=0, time_step=0.01, gradient_step=2.0, cost_scale=10.0, discount=1.0,
                 covariance=None, control_min=None, control_max=None, control_bound=True,
-                control_default=None, smoothing=(10, 1), threads=1, device=0, rank=0, world_size=1):
+                control_default=None, smoothing=(10, 1), threads=1, device=0, rank=0, world_size=1, batch=1):
     """mppi::Configuration with the defaults of src/test/case/base.hpp:68-100."""
     if system == SYSTEM_TOY:
         nx, nu = 4, 2
@@ -216,6 +216,7 @@ def make_config(system, objective, rollouts, horison, *, precision=FP64, dynamic
     c.smoothing = int(smoothing is not None)
     c.smoothing_window, c.smoothing_order = smoothing if smoothing is not None else (0, 0)
     c.threads = threads
+    c.batch = batch
     return ConfigHolder(c, (cov, cmin, cmax, cdef))
 
 

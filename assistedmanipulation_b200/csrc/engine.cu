@@ -133,18 +133,19 @@ struct mppi_b200_engine {
     void *d_injected = nullptr;
     size_t noise_elems = 0;
     // reference bookkeeping
+    int batch = 1;
     double last_shift_time = 0.0, last_rollout_time = 0.0, sg_last_trim = -1.0;
     long long shift_by = 0, update_count = 0, launches = 0;
     bool in_update = false;
     std::vector<double> control_default;
     bool has_default = false;
-    long long argmin = 0;
+    std::vector<long long> argmin;       // per controller
     ncclComm_t comm = nullptr;
     std::string error;
     float last_ms = 0.f;
     bool profiling = false;
-    double weights_total = 1.0;
-    bool weights_valid = false;
+    std::vector<double> weights_total;   // per controller
+    std::vector<char> weights_valid;
     cudaEvent_t ev_stage[MPPI_B200_STAGES + 1] = {};
     double stage_s[MPPI_B200_STAGES] = {};
 };
@@ -216,6 +217,9 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     if (c->threads <= 0) return fail_create(MPPI_B200_ERR_INVALID, "trajectory threads must be positive nonzero");
     if (c->precision != MPPI_B200_FP64 && c->precision != MPPI_B200_FP32) return fail_create(MPPI_B200_ERR_INVALID, "precision");
     if (c->world_size < 1 || c->rank < 0 || c->rank >= c->world_size) return fail_create(MPPI_B200_ERR_INVALID, "rank / world_size");
+    if (c->batch < 0) return fail_create(MPPI_B200_ERR_INVALID, "batch");
+    if (c->batch > 1 && c->world_size > 1) return fail_create(MPPI_B200_ERR_UNSUPPORTED, "a batched engine cannot also be sharded: give each GPU its own batch");
+    if (c->batch > 65535) return fail_create(MPPI_B200_ERR_UNSUPPORTED, "batch exceeds the grid's y extent");
     if (!(c->time_step > 0) || !(c->horison > 0)) return fail_create(MPPI_B200_ERR_INVALID, "time_step and horison must be positive");
     if (c->smoothing && c->smoothing_window > (unsigned)MAX_WINDOW) return fail_create(MPPI_B200_ERR_UNSUPPORTED, "smoothing window too large");
     const int T = (int)std::ceil(c->horison / c->time_step);  // mppi.cpp:85
@@ -260,6 +264,9 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     }
 
     DeviceState &d = e->d;
+    const int B = c->batch > 1 ? c->batch : 1;
+    e->batch = B; d.batch = B; d.elem_bytes = f64 ? 8 : 4;
+    e->argmin.assign(B, 0); e->weights_total.assign(B, 1.0); e->weights_valid.assign(B, 0);
     d.nu = nu; d.nx = nx; d.T = T;
     d.K_total = c->rollouts + 2;
     // contiguous shards in global index order
@@ -270,29 +277,31 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     d.bound = c->control_bound;
     for (int i = 0; i < nu; i++) { d.cmin[i] = c->control_min[i]; d.cmax[i] = c->control_max[i]; }
     const size_t n = (size_t)nu * T, esz = f64 ? 8 : 4;
-    e->noise_elems = (size_t)d.k_count * n;
-    e->frame_bytes = sizeof(Frame) + sizeof(double) * 6 * T;
+    e->noise_elems = (size_t)d.k_count * n * B;
+    e->frame_bytes = sizeof(Frame) + sizeof(double) * 6 * T;   // per controller
 
     CREATE_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
     for (cudaEvent_t *ev : {&e->ev_start, &e->ev_end}) CREATE_TRY(cudaEventCreate(ev));
     for (cudaEvent_t *ev : {&e->ev_main_done, &e->ev_side_done[0], &e->ev_side_done[1]}) CREATE_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
-    CREATE_TRY(cudaMallocHost(&e->h_frame, e->frame_bytes));
-    CREATE_TRY(cudaMallocHost(&e->h_U, n * sizeof(double)));
-    CREATE_TRY(cudaMallocHost(&e->h_stats, 16 * sizeof(double)));
-    CREATE_TRY(cudaHostAlloc(&e->h_result, (n + 8) * sizeof(double), cudaHostAllocMapped));
-    std::memset(e->h_result, 0, (n + 8) * sizeof(double));
+    CREATE_TRY(cudaMallocHost(&e->h_frame, e->frame_bytes * B));
+    CREATE_TRY(cudaMallocHost(&e->h_U, n * B * sizeof(double)));
+    CREATE_TRY(cudaMallocHost(&e->h_stats, 16 * B * sizeof(double)));
+    CREATE_TRY(cudaHostAlloc(&e->h_result, (n + 8) * B * sizeof(double), cudaHostAllocMapped));
+    std::memset(e->h_result, 0, (n + 8) * B * sizeof(double));
     CREATE_TRY(cudaHostGetDevicePointer((void **)&d.result, e->h_result, 0));
-    std::memset(e->h_frame, 0, e->frame_bytes);
-    std::memset(e->h_U, 0, n * sizeof(double));
-    std::memset(e->h_stats, 0, 16 * sizeof(double));
+    std::memset(e->h_frame, 0, e->frame_bytes * B);
+    std::memset(e->h_U, 0, n * B * sizeof(double));
+    std::memset(e->h_stats, 0, 16 * B * sizeof(double));
 
     bool ok = true;
-    auto A = [&](auto *&ptr, size_t count) { using P = std::remove_reference_t<decltype(*ptr)>; ptr = dev_alloc<P>(e, count); ok = ok && ptr; };
-    e->d_frame = dev_alloc<unsigned char>(e, e->frame_bytes); ok = ok && e->d_frame;
+    // per-controller buffers are laid out [controller][...] (kernels.cuh controller_view)
+    auto A = [&](auto *&ptr, size_t count) { using P = std::remove_reference_t<decltype(*ptr)>; ptr = dev_alloc<P>(e, count * B); ok = ok && ptr; };
+    auto A1 = [&](auto *&ptr, size_t count) { using P = std::remove_reference_t<decltype(*ptr)>; ptr = dev_alloc<P>(e, count); ok = ok && ptr; };
+    e->d_frame = dev_alloc<unsigned char>(e, e->frame_bytes * B); ok = ok && e->d_frame;
     for (int i = 0; i < 2; i++) {
-        e->d_frame_snap[i] = dev_alloc<double>(e, e->frame_bytes / 8); ok = ok && e->d_frame_snap[i];
-        e->d_U_snap[i] = dev_alloc<double>(e, n); ok = ok && e->d_U_snap[i];
+        e->d_frame_snap[i] = dev_alloc<double>(e, e->frame_bytes / 8 * B); ok = ok && e->d_frame_snap[i];
+        e->d_U_snap[i] = dev_alloc<double>(e, n * B); ok = ok && e->d_U_snap[i];
     }
     d.frame_doubles = (int)(e->frame_bytes / 8);
     d.frame_snap = e->d_frame_snap[0]; d.U_snap = e->d_U_snap[0];
@@ -307,15 +316,16 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     d.weight_blocks = (int)((d.k_count + 255) / 256);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    d.grad_blocks = (int)std::min<long long>(d.k_count, 2LL * sms);
+    // few rollouts: fewer partial rows for the second stage; many: two blocks per SM
+    d.grad_blocks = (int)std::min<long long>(std::max<long long>(d.k_count / 32, 1), 2LL * sms);
     A(d.wsum_partial, (size_t)d.weight_blocks); A(d.grad_partial, (size_t)d.grad_blocks * n);
-    A(d.gradient, n); A(d.skip, 1); A(d.L, (size_t)nu * nu); A(d.optimal_cost, 1); A(d.breakdown, 8);
+    A(d.gradient, n); A(d.skip, 1); A1(d.L, (size_t)nu * nu); A(d.optimal_cost, 1); A(d.breakdown, 8);
     d.noise = dev_alloc<unsigned char>(e, e->noise_elems * esz); ok = ok && d.noise;
     d.injected = nullptr; d.injected_is_double = 0;
     d.sg_enabled = c->smoothing ? 1 : 0;
     d.sg_window = (int)c->smoothing_window;
     d.sg_len = T + 2 * d.sg_window + 1;
-    A(d.sg_uu, (size_t)nu * d.sg_len); A(d.sg_tt, (size_t)nu * d.sg_len); A(d.sg_weights, (size_t)2 * d.sg_window + 1); A(d.sg_started, 1);
+    A(d.sg_uu, (size_t)nu * d.sg_len); A(d.sg_tt, (size_t)nu * d.sg_len); A1(d.sg_weights, (size_t)2 * d.sg_window + 1); A(d.sg_started, (size_t)nu);
     if (!ok) return bail(MPPI_B200_ERR_CUDA, "device allocation failed");
 
     const std::vector<double> L = noise_transform(nu, c->covariance);
@@ -325,7 +335,7 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     if (c->smoothing) {
         const std::vector<double> w = sg_weights(d.sg_window, (int)c->smoothing_order);
         CREATE_TRY(cudaMemcpy(d.sg_weights, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
-        std::vector<double> tt((size_t)nu * d.sg_len, -1.0);  // filter.cpp:30-32: times start at -1
+        std::vector<double> tt((size_t)nu * d.sg_len * B, -1.0);  // filter.cpp:30-32: times start at -1
         CREATE_TRY(cudaMemcpy(d.sg_tt, tt.data(), tt.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
     CREATE_TRY(cudaDeviceSynchronize());
@@ -347,14 +357,17 @@ int host_prepare(mppi_b200_engine *e, const double *state, double time, const do
     if (d.sg_enabled && time < e->sg_last_trim) return fail(e, MPPI_B200_ERR_TIME, "Resetting the window back in the past. Can reset only to larger times than last reset!!!");
     if (shift_by > 0) e->last_shift_time = time;
     e->shift_by = shift_by;
-    // the previous update's pinned frame has been consumed: finish waited for its stream work
-    Frame *f = reinterpret_cast<Frame *>(e->h_frame);
-    std::memset(f->x0, 0, sizeof f->x0);
-    std::memcpy(f->x0, state, sizeof(double) * d.nx);
-    f->time = time; f->sg_prev_trim = 0.0; f->shift_by = shift_by; f->seed = seed;
-    f->update_index = (unsigned long long)e->update_count;
-    f->has_wrench = wrench != nullptr; f->noise_source = noise_source;
-    if (wrench) std::memcpy(e->h_frame + sizeof(Frame), wrench, sizeof(double) * 6 * d.T);
+    // the previous update's pinned frames have been consumed: finish waited for its stream work
+    for (int c = 0; c < e->batch; c++) {
+        unsigned char *base = e->h_frame + (size_t)c * e->frame_bytes;
+        Frame *f = reinterpret_cast<Frame *>(base);
+        std::memset(f->x0, 0, sizeof f->x0);
+        std::memcpy(f->x0, state + (size_t)c * d.nx, sizeof(double) * d.nx);
+        f->time = time; f->sg_prev_trim = 0.0; f->shift_by = shift_by; f->seed = seed + (uint64_t)c;
+        f->update_index = (unsigned long long)e->update_count;
+        f->has_wrench = wrench != nullptr; f->noise_source = noise_source;
+        if (wrench) std::memcpy(base + sizeof(Frame), wrench + (size_t)c * 6 * d.T, sizeof(double) * 6 * d.T);
+    }
     // double-buffered snapshot for the side-stream re-rollout
     const int slot = (int)(e->update_count & 1);
     d.frame_snap = e->d_frame_snap[slot]; d.U_snap = e->d_U_snap[slot];
@@ -364,12 +377,12 @@ int host_prepare(mppi_b200_engine *e, const double *state, double time, const do
 int enqueue_begin(mppi_b200_engine *e, const void *noise, int32_t noise_source) {
     DeviceState &d = e->d;
     STAGE(e, 0);
-    CUDA_TRY(e, cudaMemcpyAsync(e->d_frame, e->h_frame, e->frame_bytes, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_frame, e->h_frame, e->frame_bytes * e->batch, cudaMemcpyHostToDevice, e->stream));
     const int prec = e->cfg.precision;
     if (noise_source == MPPI_B200_NOISE_HOST) {
         if (!e->d_injected) { e->d_injected = dev_alloc<double>(e, e->noise_elems, false); if (!e->d_injected) return fail(e, MPPI_B200_ERR_CUDA, "device allocation failed"); }
         // host layout [(K+2)][T][nu] doubles; this engine takes its own shard
-        const double *src = static_cast<const double *>(noise) + (size_t)d.k_begin * d.nu * d.T;
+        const double *src = static_cast<const double *>(noise) + (size_t)d.k_begin * d.nu * d.T;   // (batched engines are never sharded: k_begin = 0)
         CUDA_TRY(e, cudaMemcpyAsync(e->d_injected, src, e->noise_elems * sizeof(double), cudaMemcpyHostToDevice, e->stream));
         d.injected = e->d_injected; d.injected_is_double = 1;
     } else if (noise_source == MPPI_B200_NOISE_DEVICE) {
@@ -396,7 +409,7 @@ int enqueue_begin(mppi_b200_engine *e, const void *noise, int32_t noise_source) 
     STAGE(e, 3);
     CUDA_TRY(e, launch_rollout(d, prec, e->variant, e->faithful, e->params.data(), false, e->stream)); launches++;
     STAGE(e, 4);
-    CUDA_TRY(e, launch_minmax_publish(d, e->stream)); launches++;
+    if (d.world > 1) { CUDA_TRY(e, launch_minmax_publish(d, e->stream)); launches++; }  // exchange buffer for the MAX all-reduce
     e->launches += launches;
     return MPPI_B200_OK;
 }
@@ -433,8 +446,9 @@ int launch_optimal(mppi_b200_engine *e) {
     o.noise = e->d_zero_row;
     CUDA_TRY(e, launch_rollout(o, e->cfg.precision, e->variant, e->faithful, e->params.data(), true, e->side));
     e->launches += 1;
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 6, d.optimal_cost, sizeof(double), cudaMemcpyDeviceToHost, e->side));
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 7, d.breakdown, 8 * sizeof(double), cudaMemcpyDeviceToHost, e->side));
+    // h_stats: [5 x batch] update scalars | [batch] optimal cost | [8 x batch] breakdown
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 5 * e->batch, d.optimal_cost, e->batch * sizeof(double), cudaMemcpyDeviceToHost, e->side));
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 6 * e->batch, d.breakdown, 8 * e->batch * sizeof(double), cudaMemcpyDeviceToHost, e->side));
     CUDA_TRY(e, cudaEventRecord(e->ev_side_done[slot], e->side));
     e->side_pending[slot] = true;
     return MPPI_B200_OK;
@@ -450,16 +464,23 @@ int host_complete(mppi_b200_engine *e) {
         for (int i = 0; i < MPPI_B200_STAGES; i++) { float ms = 0.f; cudaEventElapsedTime(&ms, e->ev_stage[i], e->ev_stage[i + 1]); e->stage_s[i] = ms * 1e-3; }
     }
     e->in_update = false;
-    std::memcpy(e->h_stats, e->h_result + n, 5 * sizeof(double));   // {-min, max, valid}, argmin, sum w
-    // mppi.cpp:368-370: no (or a single) valid rollout is an error; nothing is published
-    if (!(e->h_stats[2] >= 2.0)) return fail(e, MPPI_B200_ERR_ALL_NAN, "all nan rollouts");
-    std::memcpy(e->h_U, e->h_result, n * sizeof(double));
-    std::memcpy(&e->argmin, e->h_stats + 3, sizeof(long long));
-    const bool early_return = e->h_stats[1] + e->h_stats[0] < 1e-6;  // max - min < 1e-6 (mppi.cpp:373-375)
-    if (!early_return) { e->weights_total = e->h_stats[4]; e->weights_valid = true; }
-    if (d.sg_enabled && !early_return) e->sg_last_trim = reinterpret_cast<Frame *>(e->h_frame)->time;
+    bool all_nan = false, smoothed = false;
+    for (int c = 0; c < e->batch; c++) {
+        const double *res = e->h_result + (size_t)c * (n + 8);
+        double *st = e->h_stats + 5 * c;
+        std::memcpy(st, res + n, 5 * sizeof(double));   // {-min, max, valid}, argmin, sum w
+        // mppi.cpp:368-370: no (or a single) valid rollout is an error; nothing is published for that controller
+        if (!(st[2] >= 2.0)) { all_nan = true; continue; }
+        std::memcpy(e->h_U + (size_t)c * n, res, n * sizeof(double));
+        std::memcpy(&e->argmin[c], st + 3, sizeof(long long));
+        const bool early_return = st[1] + st[0] < 1e-6;  // max - min < 1e-6 (mppi.cpp:373-375): weights left untouched
+        if (!early_return) { e->weights_total[c] = st[4]; e->weights_valid[c] = 1; smoothed = true; }
+    }
+    if (all_nan && e->batch == 1) return fail(e, MPPI_B200_ERR_ALL_NAN, "all nan rollouts");
+    if (d.sg_enabled && smoothed) e->sg_last_trim = reinterpret_cast<Frame *>(e->h_frame)->time;
     e->last_rollout_time = reinterpret_cast<Frame *>(e->h_frame)->time;
     e->update_count++;
+    if (all_nan) return fail(e, MPPI_B200_ERR_ALL_NAN, "all nan rollouts (in at least one controller of the batch)");
     return MPPI_B200_OK;
 }
 
@@ -614,14 +635,18 @@ int mppi_b200_get(mppi_b200_engine *e, double *control, double time) {
     if (!e || !control) return MPPI_B200_ERR_INVALID;
     const int nu = e->d.nu, T = e->d.T;
     if (time < e->last_rollout_time) return fail(e, MPPI_B200_ERR_INVALID, "time >= m_last_rollout_time (assert, mppi.cpp:483)");
-    double t = (time - e->last_rollout_time) / e->d.dt;
-    const int lower = (int)t, upper = lower + 1;
-    if (upper >= T) {
-        for (int i = 0; i < nu; i++) control[i] = e->has_default ? e->control_default[i] : e->h_U[(size_t)(T - 1) * nu + i];
-        return MPPI_B200_OK;
+    const double t0 = (time - e->last_rollout_time) / e->d.dt;
+    const int lower = (int)t0, upper = lower + 1;
+    for (int c = 0; c < e->batch; c++) {
+        const double *U = e->h_U + (size_t)c * nu * T;
+        double *out = control + (size_t)c * nu;
+        if (upper >= T) {
+            for (int i = 0; i < nu; i++) out[i] = e->has_default ? e->control_default[i] : U[(size_t)(T - 1) * nu + i];
+            continue;
+        }
+        const double t = t0 - lower;
+        for (int i = 0; i < nu; i++) out[i] = (1.0 - t) * U[(size_t)lower * nu + i] + t * U[(size_t)upper * nu + i];
     }
-    t -= lower;
-    for (int i = 0; i < nu; i++) control[i] = (1.0 - t) * e->h_U[(size_t)lower * nu + i] + t * e->h_U[(size_t)upper * nu + i];
     return MPPI_B200_OK;
 }
 
@@ -630,37 +655,41 @@ int mppi_b200_read(mppi_b200_engine *e, int32_t what, void *dst, size_t bytes) {
     DeviceState &d = e->d;
     int rc = mppi_b200_synchronize(e);
     if (rc) return rc;
-    const size_t n = (size_t)d.nu * d.T, K = (size_t)d.k_count;
+    const size_t B = (size_t)e->batch, n = (size_t)d.nu * d.T, K = (size_t)d.k_count;
     auto need = [&](size_t b) { return bytes == b; };
     switch (what) {
-        case MPPI_B200_READ_OPTIMAL: if (!need(n * 8)) break; std::memcpy(dst, e->h_U, bytes); return MPPI_B200_OK;
-        case MPPI_B200_READ_COSTS: if (!need(K * 8)) break; CUDA_TRY(e, cudaMemcpy(dst, d.costs, bytes, cudaMemcpyDeviceToHost)); return MPPI_B200_OK;
+        case MPPI_B200_READ_OPTIMAL: if (!need(B * n * 8)) break; std::memcpy(dst, e->h_U, bytes); return MPPI_B200_OK;
+        case MPPI_B200_READ_COSTS: if (!need(B * K * 8)) break; CUDA_TRY(e, cudaMemcpy(dst, d.costs, bytes, cudaMemcpyDeviceToHost)); return MPPI_B200_OK;
         case MPPI_B200_READ_WEIGHTS: {
             // the device keeps exp(-cost_scale (c - min)/(max - min)); the division by the total of
             // mppi.cpp:403-408 is applied here (the weighted sum divides once, in k_finish)
-            if (!need(K * 8)) break;
+            if (!need(B * K * 8)) break;
             CUDA_TRY(e, cudaMemcpy(dst, d.weights, bytes, cudaMemcpyDeviceToHost));
             double *w = static_cast<double *>(dst);
-            const double total = e->weights_total;
-            if (e->weights_valid) for (size_t i = 0; i < K; i++) w[i] = w[i] / total;
+            for (size_t c = 0; c < B; c++)
+                if (e->weights_valid[c]) for (size_t i = 0; i < K; i++) w[c * K + i] = w[c * K + i] / e->weights_total[c];
             return MPPI_B200_OK;
         }
-        case MPPI_B200_READ_GRADIENT: if (!need(n * 8)) break; CUDA_TRY(e, cudaMemcpy(dst, d.gradient, bytes, cudaMemcpyDeviceToHost)); return MPPI_B200_OK;
+        case MPPI_B200_READ_GRADIENT: if (!need(B * n * 8)) break; CUDA_TRY(e, cudaMemcpy(dst, d.gradient, bytes, cudaMemcpyDeviceToHost)); return MPPI_B200_OK;
         case MPPI_B200_READ_NOISE: {
-            if (!need(K * n * 8)) break;
+            if (!need(B * K * n * 8)) break;
             if (e->cfg.precision == MPPI_B200_FP64) { CUDA_TRY(e, cudaMemcpy(dst, d.noise, bytes, cudaMemcpyDeviceToHost)); return MPPI_B200_OK; }
-            std::vector<float> tmp(K * n);
+            std::vector<float> tmp(B * K * n);
             CUDA_TRY(e, cudaMemcpy(tmp.data(), d.noise, tmp.size() * 4, cudaMemcpyDeviceToHost));
             double *o = static_cast<double *>(dst);
             for (size_t i = 0; i < tmp.size(); i++) o[i] = (double)tmp[i];
             return MPPI_B200_OK;
         }
-        case MPPI_B200_READ_MINMAX: if (!need(16)) break; static_cast<double *>(dst)[0] = -e->h_stats[0]; static_cast<double *>(dst)[1] = e->h_stats[1]; return MPPI_B200_OK;
-        case MPPI_B200_READ_OPTIMAL_COST: if (!need(8)) break; static_cast<double *>(dst)[0] = e->h_stats[6]; return MPPI_B200_OK;
-        case MPPI_B200_READ_BREAKDOWN: if (!need(64)) break; std::memcpy(dst, e->h_stats + 7, 64); return MPPI_B200_OK;
+        case MPPI_B200_READ_MINMAX: {
+            if (!need(B * 16)) break;
+            for (size_t c = 0; c < B; c++) { static_cast<double *>(dst)[2 * c] = -e->h_stats[5 * c]; static_cast<double *>(dst)[2 * c + 1] = e->h_stats[5 * c + 1]; }
+            return MPPI_B200_OK;
+        }
+        case MPPI_B200_READ_OPTIMAL_COST: if (!need(B * 8)) break; std::memcpy(dst, e->h_stats + 5 * B, bytes); return MPPI_B200_OK;
+        case MPPI_B200_READ_BREAKDOWN: if (!need(B * 64)) break; std::memcpy(dst, e->h_stats + 6 * B, bytes); return MPPI_B200_OK;
         case MPPI_B200_READ_KEPT: {
             const size_t k = bytes / 8;
-            if (bytes % 8 || k > (size_t)d.keep_best) break;
+            if (bytes % 8 || k > B * (size_t)std::max<long long>(d.keep_best, 1)) break;
             CUDA_TRY(e, cudaMemcpy(dst, d.kept_list, bytes, cudaMemcpyDeviceToHost));
             return MPPI_B200_OK;
         }
@@ -677,7 +706,8 @@ int mppi_b200_query(mppi_b200_engine *e, int32_t what, int64_t *value) {
         case MPPI_B200_QUERY_LOCAL_COUNT: *value = e->d.k_count; return 0;
         case MPPI_B200_QUERY_UPDATE_COUNT: *value = e->update_count; return 0;
         case MPPI_B200_QUERY_KERNEL_LAUNCHES: *value = e->launches; return 0;
-        case MPPI_B200_QUERY_ARGMIN: *value = e->argmin; return 0;
+        case MPPI_B200_QUERY_ARGMIN: *value = e->argmin[0]; return 0;
+        case MPPI_B200_QUERY_BATCH: *value = e->batch; return 0;
         case MPPI_B200_QUERY_SHIFT_BY: *value = e->shift_by; return 0;
         case MPPI_B200_QUERY_STATE_DOF: *value = e->d.nx; return 0;
         case MPPI_B200_QUERY_CONTROL_DOF: *value = e->d.nu; return 0;

@@ -53,7 +53,8 @@ __device__ __forceinline__ void box_muller(unsigned a, unsigned b, float *z0, fl
 
 // ---- prepare: time shift of the optimal control, rollout 1 = -U_prev, reset of the reductions -------
 // mppi.cpp:194-206 (shift), :269 (rollout[1].noise = -m_optimal_control, the UNSHIFTED optimum).
-template <class R> __global__ void k_prepare(const __grid_constant__ DeviceState d) {
+template <class R> __global__ void k_prepare(const __grid_constant__ DeviceState dg) {
+    const DeviceState d = controller_view(dg, blockIdx.y);
     const int n = d.nu * d.T;
     const long long shift = d.frame->shift_by;
     for (int i = threadIdx.x; i < d.frame_doubles; i += blockDim.x) d.frame_snap[i] = reinterpret_cast<const double *>(d.frame)[i];
@@ -126,7 +127,8 @@ __device__ __forceinline__ void select_smallest(long long count, long long keep,
 
 // mppi.cpp:222-253 on this rank's rollouts. With one rank the picks ARE the kept set; with several the picks
 // are this rank's candidates, all-gathered and merged by k_merge_kept.
-__global__ void k_select_kept(const __grid_constant__ DeviceState d) {
+__global__ void k_select_kept(const __grid_constant__ DeviceState dg) {
+    const DeviceState d = controller_view(dg, blockIdx.y);
     for (long long k = threadIdx.x; k < d.k_count; k += blockDim.x) d.kept[k] = 0;
     __syncthreads();
     const long long keep = d.keep_best < d.K_total - 2 ? d.keep_best : d.K_total - 2;
@@ -146,7 +148,8 @@ __global__ void k_select_kept(const __grid_constant__ DeviceState d) {
 }
 
 // every rank merges the same world x keep candidate list into the global kept set
-__global__ void k_merge_kept(const __grid_constant__ DeviceState d) {
+__global__ void k_merge_kept(const __grid_constant__ DeviceState dg) {
+    const DeviceState d = controller_view(dg, blockIdx.y);
     const long long keep = d.keep_best < d.K_total - 2 ? d.keep_best : d.K_total - 2;
     select_smallest(
         (long long)d.world * keep, keep,
@@ -195,7 +198,8 @@ template <class R, class RI, int NU> __device__ __forceinline__ void fresh_colum
     }
 }
 
-template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sample(const __grid_constant__ DeviceState d) {
+template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sample(const __grid_constant__ DeviceState dg) {
+    const DeviceState d = controller_view(dg, blockIdx.y);
     // A block produces 256 consecutive columns = one contiguous span of 256*nu values: every thread
     // builds its column in shared memory, then the block streams the span out with 16-byte stores.
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -236,7 +240,8 @@ template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sa
 }
 
 // kept rollouts: one block per kept rollout (mppi.cpp:243-252); nothing happens when shift_by <= 0
-template <class R, class RI, int NU> __global__ void k_shift_kept(const __grid_constant__ DeviceState d) {
+template <class R, class RI, int NU> __global__ void k_shift_kept(const __grid_constant__ DeviceState dg) {
+    const DeviceState d = controller_view(dg, blockIdx.y);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *row = reinterpret_cast<R *>(smem_raw);
     __shared__ double sL[MAX_NU * MAX_NU];
@@ -265,7 +270,8 @@ template <class R, class RI, int NU> __global__ void k_shift_kept(const __grid_c
 
 // ---- K3 ---------------------------------------------------------------------------------------------
 // publish {-min, max, valid} into the exchange buffer (all-reduced with MAX when sharded)
-__global__ void k_minmax_publish(const __grid_constant__ DeviceState d) {
+__global__ void k_minmax_publish(const __grid_constant__ DeviceState dg) {
+    const DeviceState d = controller_view(dg, blockIdx.y);
     if (threadIdx.x == 0) {
         const int n = *d.valid_count;
         d.minmax[0] = n > 0 ? -decode_ordered(d.minmax_enc[0]) : -CUDART_INF;
@@ -275,11 +281,23 @@ __global__ void k_minmax_publish(const __grid_constant__ DeviceState d) {
 }
 
 // w_k = exp(-cost_scale (c_k - min) / (max - min)), NaN -> 0 (mppi.cpp:381-397); block partial sums
-__global__ void __launch_bounds__(256) k_weights(const __grid_constant__ DeviceState d) {
+__global__ void __launch_bounds__(256) k_weights(const __grid_constant__ DeviceState dg) {
+    const DeviceState d = controller_view(dg, blockIdx.y);
     __shared__ double s_part[8];
-    const double minimum = -d.minmax[0], maximum = d.minmax[1];
+    double mm0, mm1, mm2;
+    if (d.world == 1) {
+        // single rank: no exchange, every block decodes the running min / max itself (no publish kernel)
+        const int nvalid = *d.valid_count;
+        mm0 = nvalid > 0 ? -decode_ordered(d.minmax_enc[0]) : -CUDART_INF;
+        mm1 = nvalid > 0 ? decode_ordered(d.minmax_enc[1]) : -CUDART_INF;
+        mm2 = nvalid >= 2 ? 2.0 : (double)nvalid;
+        if (blockIdx.x == 0 && threadIdx.x == 0) { d.minmax[0] = mm0; d.minmax[1] = mm1; d.minmax[2] = mm2; }
+    } else {
+        mm0 = d.minmax[0]; mm1 = d.minmax[1]; mm2 = d.minmax[2];
+    }
+    const double minimum = -mm0, maximum = mm1;
     const double difference = maximum - minimum;
-    const bool bad = !(d.minmax[2] >= 2.0) || !(difference >= 1e-6);  // all-NaN / early return (mppi.cpp:368-375)
+    const bool bad = !(mm2 >= 2.0) || !(difference >= 1e-6);  // all-NaN / early return (mppi.cpp:368-375)
     if (bad) {
         if (blockIdx.x == 0 && threadIdx.x == 0) *d.skip = 1;
     }
@@ -316,7 +334,8 @@ __device__ __forceinline__ void fma_vec(double *acc, double w, const float4 &v) 
     acc[0] = fma(w, (double)v.x, acc[0]); acc[1] = fma(w, (double)v.y, acc[1]); acc[2] = fma(w, (double)v.z, acc[2]); acc[3] = fma(w, (double)v.w, acc[3]);
 }
 
-template <class R> __global__ void __launch_bounds__(512) k_gradient(const __grid_constant__ DeviceState d) {
+template <class R> __global__ void __launch_bounds__(512) k_gradient(const __grid_constant__ DeviceState dg) {
+    const DeviceState d = controller_view(dg, blockIdx.y);
     typedef typename Vec16<R>::type V;
     constexpr int VN = Vec16<R>::n;
     if (*d.skip) return;
@@ -344,39 +363,42 @@ template <class R> __global__ void __launch_bounds__(512) k_gradient(const __gri
 }
 
 // fixed-order combination of the partials into the exchange buffer sums = {sum w, sum w*eps}.
-// Block = 32 elements x 8 slices of the partial rows; slice sums are combined in slice order.
-__global__ void __launch_bounds__(256) k_gradient_reduce(const __grid_constant__ DeviceState d) {
-    __shared__ double part[8][33];
+// Block = 32 elements x 32 slices of the partial rows (every thread has at most a few loads, all in
+// flight at once); slice sums are combined in slice order.
+__global__ void __launch_bounds__(1024) k_gradient_reduce(const __grid_constant__ DeviceState dg) {
+    const DeviceState d = controller_view(dg, blockIdx.y);
+    __shared__ double part[32][33];
     if (*d.skip) return;
     const int n = d.nu * d.T;
+    const int rows = d.grad_blocks;
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + lane;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (e < n) {
         int b = slice;
-        for (; b + 24 < d.grad_blocks; b += 32) {
+        for (; b + 96 < rows; b += 128) {
             s0 += d.grad_partial[(size_t)b * n + e];
-            s1 += d.grad_partial[(size_t)(b + 8) * n + e];
-            s2 += d.grad_partial[(size_t)(b + 16) * n + e];
-            s3 += d.grad_partial[(size_t)(b + 24) * n + e];
+            s1 += d.grad_partial[(size_t)(b + 32) * n + e];
+            s2 += d.grad_partial[(size_t)(b + 64) * n + e];
+            s3 += d.grad_partial[(size_t)(b + 96) * n + e];
         }
-        for (; b < d.grad_blocks; b += 8) s0 += d.grad_partial[(size_t)b * n + e];
+        for (; b < rows; b += 32) s0 += d.grad_partial[(size_t)b * n + e];
     }
     part[slice][lane] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (slice == 0 && e < n) {
         double s = part[0][lane];
 #pragma unroll
-        for (int i = 1; i < 8; i++) s += part[i][lane];
+        for (int i = 1; i < 32; i++) s += part[i][lane];
         d.sums[1 + e] = s;
     }
-    if (blockIdx.x == 0 && threadIdx.x < 32) {
+    if (blockIdx.x == 0 && slice == 1) {
         // sum of the weights: warp-strided partial sums, then a fixed-order shuffle tree
         double s = 0.0;
-        for (int b = threadIdx.x; b < d.weight_blocks; b += 32) s += d.wsum_partial[b];
+        for (int b = lane; b < d.weight_blocks; b += 32) s += d.wsum_partial[b];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (threadIdx.x == 0) d.sums[0] = s;
+        if (lane == 0) d.sums[0] = s;
     }
 }
 
@@ -392,45 +414,47 @@ __device__ __forceinline__ int sg_lower_bound(const double *tt, int len, double 
     return first;
 }
 
-__global__ void __launch_bounds__(512) k_finish(const __grid_constant__ DeviceState d) {
+__global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DeviceState dg) {
+    const DeviceState d = controller_view(dg, blockIdx.y);
+    // One BLOCK per control channel (channels are independent, mppi.cpp:424-447): the elementwise work runs over the
+    // channel's T entries, the window recurrence on warp 0 with its own scheduler.
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *sU = reinterpret_cast<double *>(smem_raw);   // nu*T working copy of m_optimal_control_shifted
-    double *uu = sU + d.nu * d.T;                          // nu x Lw
-    double *tt = uu + d.nu * d.sg_len;                     // nu x Lw
-    double *sw = tt + d.nu * d.sg_len;                     // 2w+1 taps
-    const int n = d.nu * d.T;
+    double *sU = reinterpret_cast<double *>(smem_raw);   // T working values of this channel
+    double *u = sU + d.T;                                  // Lw window samples
+    double *tm = u + d.sg_len;                             // Lw window times
+    double *sw = tm + d.sg_len;                            // 2w+1 taps
+    const int n = d.nu * d.T, ch = blockIdx.x;
     const int skip = *d.skip;
     const bool dead = !(d.minmax[2] >= 2.0);  // "all nan rollouts" (mppi.cpp:368-370): the reference throws before publishing
-    if (threadIdx.x == 0) {
+    if (ch == 0 && threadIdx.x == 0) {
         d.result[n + 0] = d.minmax[0]; d.result[n + 1] = d.minmax[1]; d.result[n + 2] = d.minmax[2];
         d.result[n + 3] = __longlong_as_double(*d.argmin);
         d.result[n + 4] = d.sums[0];
     }
     if (dead) return;
     const double total = d.sums[0];
-    for (int e = threadIdx.x; e < n; e += blockDim.x) {
-        double u = d.U_shift[e];
+    for (int t = threadIdx.x; t < d.T; t += blockDim.x) {
+        const int e = t * d.nu + ch;
+        double v = d.U_shift[e];
         if (!skip) {
             const double g = d.sums[1 + e] / total;   // weights are normalised by the total (mppi.cpp:403-408)
             d.gradient[e] = g;
-            u += g * d.gradient_step;
+            v += g * d.gradient_step;
         }
-        sU[e] = u;
+        sU[t] = v;
     }
     if (!skip && d.sg_enabled) {
         const int Lw = d.sg_len, w = d.sg_window, ntaps = 2 * w + 1;
-        for (int i = threadIdx.x; i < d.nu * Lw; i += blockDim.x) { uu[i] = d.sg_uu[i]; tt[i] = d.sg_tt[i]; }
+        for (int i = threadIdx.x; i < Lw; i += blockDim.x) { u[i] = d.sg_uu[ch * Lw + i]; tm[i] = d.sg_tt[ch * Lw + i]; }
         for (int i = threadIdx.x; i < ntaps; i += blockDim.x) sw[i] = d.sg_weights[i];
         __syncthreads();
-        // One WARP per channel: the window bookkeeping is lane-parallel, only the T applications are
-        // sequential (each reads the value the previous one wrote), and each of those is a lane-parallel
-        // dot product over the 2w+1 taps.
-        const int ch = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        if (ch < d.nu) {
-            double *u = uu + ch * Lw, *tm = tt + ch * Lw;
+        // Warp 0: the window bookkeeping is lane-parallel, only the T applications are sequential (each reads the
+        // value the previous one wrote), and each of those is a lane-parallel dot product over the 2w+1 taps.
+        const int lane = threadIdx.x & 31;
+        if (threadIdx.x < 32) {
             const double t0 = d.frame->time;
             // trim(t0): filter.cpp:34-67. start_idx is w before the first pass and w + T after any pass.
-            const int start_idx = *d.sg_started ? w + d.T : w;
+            const int start_idx = d.sg_started[ch] ? w + d.T : w;
             int trim_idx = start_idx;
             for (int i = lane; i < start_idx; i += 32) if (tm[i] >= t0) { trim_idx = i; break; }  // first hit of this lane
 #pragma unroll
@@ -454,42 +478,43 @@ __global__ void __launch_bounds__(512) k_finish(const __grid_constant__ DeviceSt
             // Times are compared with == / >= later: no FMA contraction, exactly m_rollout_time + i * m_time_step (mppi.cpp:430).
             for (int i = lane; i < Lw - w; i += 32) {
                 const int k = i < d.T ? i : d.T - 1;
-                u[w + i] = sU[k * d.nu + ch];
+                u[w + i] = sU[k];
                 tm[w + i] = __dadd_rn(t0, __dmul_rn((double)k, d.dt));
             }
             __syncwarp();
             // apply x T (filter.cpp:163-173): the filtered value is written ONE SLOT EARLIER than the sample
+            const double my_w0 = lane < ntaps ? sw[lane] : 0.0;
             for (int i = 0; i < d.T; i++) {
                 const double t = __dadd_rn(t0, __dmul_rn((double)i, d.dt));
                 // std::lower_bound over the (sorted) times; the common answer w + i is verified, else searched
                 int idx = w + i;
                 if (!(tm[idx] >= t && tm[idx - 1] < t)) idx = sg_lower_bound(tm, Lw, t);
                 const double *v = u + idx - w;
-                double res = 0.0;
-                for (int j = lane; j < ntaps; j += 32) res = fma(sw[j], v[j], res);
+                double res = lane < ntaps ? my_w0 * v[lane] : 0.0;
+                for (int j = lane + 32; j < ntaps; j += 32) res = fma(sw[j], v[j], res);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
                 __syncwarp();
-                if (lane == 0) { u[idx - 1] = res; sU[i * d.nu + ch] = res; }
+                if (lane == 0) { u[idx - 1] = res; sU[i] = res; }
                 __syncwarp();
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < d.nu * Lw; i += blockDim.x) { d.sg_uu[i] = uu[i]; d.sg_tt[i] = tt[i]; }
-        if (threadIdx.x == 0) *d.sg_started = 1;
+        for (int i = threadIdx.x; i < Lw; i += blockDim.x) { d.sg_uu[ch * Lw + i] = u[i]; d.sg_tt[ch * Lw + i] = tm[i]; }
+        if (threadIdx.x == 0) d.sg_started[ch] = 1;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < n; e += blockDim.x) {
-        double u = sU[e];
+    for (int t = threadIdx.x; t < d.T; t += blockDim.x) {
+        const int e = t * d.nu + ch;
+        double v = sU[t];
         if (!skip && d.bound) {
-            const int dd = e % d.nu;
-            u = std_min(u, d.cmax[dd]);   // cwiseMin(max).cwiseMax(min), mppi.cpp:443-447; std::min / std::max NaN semantics
-            u = std_max(u, d.cmin[dd]);
+            v = std_min(v, d.cmax[ch]);   // cwiseMin(max).cwiseMax(min), mppi.cpp:443-447; std::min / std::max NaN semantics
+            v = std_max(v, d.cmin[ch]);
         }
-        d.U_shift[e] = u;
-        d.U[e] = u;        // publication: m_optimal_control = m_optimal_control_shifted (mppi.cpp:178-182)
-        d.U_snap[e] = u;   // input of the optimal re-rollout (side stream)
-        d.result[e] = u;   // host-mapped copy, visible to the caller when the stream completes
+        d.U_shift[e] = v;
+        d.U[e] = v;        // publication: m_optimal_control = m_optimal_control_shifted (mppi.cpp:178-182)
+        d.U_snap[e] = v;   // input of the optimal re-rollout (side stream)
+        d.result[e] = v;   // host-mapped copy, visible to the caller when the stream completes
     }
 }
 
@@ -541,12 +566,12 @@ cudaError_t measure_fma_peak(int precision, double *tflops) {
 
 // ---- launchers -----------------------------------------------------------------------------------------
 cudaError_t launch_prepare(const DeviceState &d, int precision, cudaStream_t s) {
-    if (precision == 0) k_prepare<double><<<1, 256, 0, s>>>(d); else k_prepare<float><<<1, 256, 0, s>>>(d);
+    if (precision == 0) k_prepare<double><<<dim3(1, d.batch), 256, 0, s>>>(d); else k_prepare<float><<<dim3(1, d.batch), 256, 0, s>>>(d);
     return cudaGetLastError();
 }
 
 cudaError_t launch_select_kept(const DeviceState &d, cudaStream_t s) {
-    k_select_kept<<<1, 1024, 0, s>>>(d);
+    k_select_kept<<<dim3(1, d.batch), 1024, 0, s>>>(d);
     return cudaGetLastError();
 }
 cudaError_t launch_merge_kept(const DeviceState &d, cudaStream_t s) {
@@ -561,13 +586,13 @@ template <class R, class RI, int NU> static cudaError_t sample_tt(const DeviceSt
             cudaError_t e = cudaFuncSetAttribute(k_shift_kept<R, RI, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row);
             if (e != cudaSuccess) return e;
         }
-        k_shift_kept<R, RI, NU><<<(unsigned)d.keep_best, 64, row, s>>>(d);
+        k_shift_kept<R, RI, NU><<<dim3((unsigned)d.keep_best, d.batch), 64, row, s>>>(d);
         ++*launches;
     }
     const long long ncols = d.k_count * d.T;
     const unsigned grid = (unsigned)((ncols + 255) / 256);
     const size_t tile = sizeof(R) * 256 * (size_t)NU;
-    k_sample<R, RI, NU><<<grid, 256, tile, s>>>(d);
+    k_sample<R, RI, NU><<<dim3(grid, d.batch), 256, tile, s>>>(d);
     ++*launches;
     return cudaGetLastError();
 }
@@ -590,7 +615,7 @@ cudaError_t launch_minmax_publish(const DeviceState &d, cudaStream_t s) {
 }
 
 cudaError_t launch_weights(const DeviceState &d, cudaStream_t s) {
-    k_weights<<<d.weight_blocks, 256, 0, s>>>(d);
+    k_weights<<<dim3(d.weight_blocks, d.batch), 256, 0, s>>>(d);
     return cudaGetLastError();
 }
 
@@ -598,19 +623,19 @@ cudaError_t launch_gradient(const DeviceState &d, int precision, cudaStream_t s,
     const int n = d.nu * d.T;
     const int nvec = n / (precision == 0 ? 2 : 4);
     const int threads = std::min(512, ((nvec + 127) / 128) * 128);
-    if (precision == 0) k_gradient<double><<<d.grad_blocks, threads, 0, s>>>(d); else k_gradient<float><<<d.grad_blocks, threads, 0, s>>>(d);
-    k_gradient_reduce<<<(n + 31) / 32, 256, 0, s>>>(d);
+    if (precision == 0) k_gradient<double><<<dim3(d.grad_blocks, d.batch), threads, 0, s>>>(d); else k_gradient<float><<<dim3(d.grad_blocks, d.batch), threads, 0, s>>>(d);
+    k_gradient_reduce<<<dim3((n + 31) / 32, d.batch), 1024, 0, s>>>(d);
     *launches += 2;
     return cudaGetLastError();
 }
 
 cudaError_t launch_finish(const DeviceState &d, cudaStream_t s) {
-    const size_t smem = sizeof(double) * ((size_t)d.nu * d.T + 2 * (size_t)d.nu * d.sg_len + 2 * (size_t)d.sg_window + 1);
+    const size_t smem = sizeof(double) * ((size_t)d.T + 2 * (size_t)d.sg_len + 2 * (size_t)d.sg_window + 1);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_finish<<<1, d.nu * 32 > 256 ? 512 : 256, smem, s>>>(d);
+    k_finish<<<dim3(d.nu, d.batch), 64, smem, s>>>(d);
     return cudaGetLastError();
 }
 

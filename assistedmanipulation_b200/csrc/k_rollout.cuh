@@ -25,23 +25,29 @@ __device__ __forceinline__ double decode_ordered(unsigned long long e) {
 
 template <class R, int VAR, bool FAITHFUL, class ParamsT>
 __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ DeviceState d, const __grid_constant__ ParamsT P, int optimal_only) {
+    // blockIdx.y = controller of a batched engine. Only the handful of buffers this kernel touches are offset
+    // by hand (a full controller_view copy of the state costs ~40 registers here, i.e. a resident warp per SM).
+    const size_t c = blockIdx.y;
+    const size_t n = (size_t)d.nu * d.T;
+    const Frame *frame = reinterpret_cast<const Frame *>(reinterpret_cast<const double *>(d.frame) + c * d.frame_doubles);
+    const double *wrench = d.wrench + c * d.frame_doubles;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *sU = reinterpret_cast<R *>(smem_raw);        // nu*T
     R *sW = sU + d.nu * d.T;                         // 6*T
     R *sx = sW + 6 * d.T;                            // 32
-    const double *Usrc = d.U_shift;
+    const double *Usrc = d.U_shift + c * n;
     for (int i = threadIdx.x; i < d.nu * d.T; i += blockDim.x) sU[i] = (R)Usrc[i];
-    const int has_w = d.frame->has_wrench;
-    for (int i = threadIdx.x; i < 6 * d.T; i += blockDim.x) sW[i] = has_w ? (R)d.wrench[i] : R(0);
-    for (int i = threadIdx.x; i < 32; i += blockDim.x) sx[i] = (R)d.frame->x0[i];
+    const int has_w = frame->has_wrench;
+    for (int i = threadIdx.x; i < 6 * d.T; i += blockDim.x) sW[i] = has_w ? (R)wrench[i] : R(0);
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) sx[i] = (R)frame->x0[i];
     __syncthreads();
 
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double cost = 0.0;
     bool active = optimal_only ? (k == 0) : (k < d.k_count);
     if (active) {
-        // the optimal re-rollout (Trajectory::filter, mppi.cpp:450-479) reads a row of zeros
-        const R *eps = static_cast<const R *>(d.noise) + (size_t)k * d.T * d.nu;
+        // the optimal re-rollout (Trajectory::filter, mppi.cpp:450-479) reads a row of zeros shared by all controllers
+        const R *eps = static_cast<const R *>(d.noise) + (optimal_only ? (size_t)0 : (c * (size_t)d.k_count + (size_t)k) * n);
         if constexpr (VAR == VAR_TOY) {
             cost = rollout_toy<R>(P, sx, sU, eps, d.T, (R)d.dt, d.discount);
         } else {
@@ -50,11 +56,11 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ DeviceS
             double bd[7] = {0, 0, 0, 0, 0, 0, 0};
             cost = rollout_franka<R, VAR, FAITHFUL>(MPPI_DEVICE_MODEL, MPPI_DEVICE_FAST_MODEL, P, in, eps, optimal_only ? bd : nullptr);
             if (optimal_only) {
-                for (int i = 0; i < 7; i++) d.breakdown[i] = bd[i];
-                d.breakdown[7] = cost;
+                for (int i = 0; i < 7; i++) d.breakdown[8 * c + i] = bd[i];
+                d.breakdown[8 * c + 7] = cost;
             }
         }
-        if (optimal_only) d.optimal_cost[0] = cost; else d.costs[k] = cost;
+        if (optimal_only) d.optimal_cost[c] = cost; else d.costs[c * (size_t)d.k_count + k] = cost;
     }
     if (optimal_only) return;
 
@@ -70,9 +76,9 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ DeviceS
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
     if ((threadIdx.x & 31) == 0 && cnt > 0) {
-        atomicMin(&d.minmax_enc[0], encode_ordered(mn));
-        atomicMax(&d.minmax_enc[1], encode_ordered(mx));
-        atomicAdd(d.valid_count, cnt);
+        atomicMin(&d.minmax_enc[2 * c], encode_ordered(mn));
+        atomicMax(&d.minmax_enc[2 * c + 1], encode_ordered(mx));
+        atomicAdd(d.valid_count + c, cnt);
     }
 }
 
@@ -89,7 +95,7 @@ cudaError_t launch_rollout_t(const DeviceState &d, const void *params, bool opti
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<(unsigned)grid, block, smem, s>>>(d, P, optimal_only ? 1 : 0);
+    kern<<<dim3((unsigned)grid, d.batch), block, smem, s>>>(d, P, optimal_only ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -30,6 +30,8 @@ struct Frame {
 // Device-resident state of one engine (pointers only; owned by the engine).
 struct DeviceState {
     // geometry
+    int batch;             // independent controllers sharing this engine (blockIdx.y); 1 = a single mppi::Trajectory
+    int elem_bytes;        // sizeof(kernel real)
     int nu, nx, T;
     long long K_total;     // K + 2
     long long k_begin;     // first global rollout index owned by this engine
@@ -68,7 +70,7 @@ struct DeviceState {
     double *sg_uu, *sg_tt;
     double *sg_weights;    // 2*window+1
     int sg_enabled, sg_window, sg_len;
-    int *sg_started;       // 0 until the first smoothing pass (window start_idx = w), then start_idx = w + T
+    int *sg_started;       // per channel: 0 until the first smoothing pass (window start_idx = w), then start_idx = w + T
     // constants
     double dt, gradient_step, cost_scale, discount;
     int bound;
@@ -82,6 +84,33 @@ struct DeviceState {
     double *optimal_cost;  // [1]
     double *breakdown;     // [8]
 };
+
+#if defined(__CUDACC__)
+// The buffers of controller c of a batched engine: every per-controller buffer is laid out
+// [controller][...], so a kernel block with blockIdx.y = c works on a shifted view and is otherwise
+// unaware of the batch.
+__device__ __forceinline__ DeviceState controller_view(const DeviceState &g, int c) {
+    if (g.batch <= 1) return g;
+    DeviceState d = g;
+    const size_t n = (size_t)g.nu * g.T, K = (size_t)g.k_count, keep = g.keep_best > 0 ? (size_t)g.keep_best : 1;
+    d.frame = reinterpret_cast<const Frame *>(reinterpret_cast<const double *>(g.frame) + (size_t)c * g.frame_doubles);
+    d.wrench = g.wrench + (size_t)c * g.frame_doubles;
+    d.U = g.U + c * n; d.U_shift = g.U_shift + c * n; d.gradient = g.gradient + c * n; d.U_snap = g.U_snap + c * n;
+    d.noise = static_cast<unsigned char *>(g.noise) + (size_t)c * K * n * g.elem_bytes;
+    if (g.injected) d.injected = static_cast<const unsigned char *>(g.injected) + (size_t)c * K * n * (g.injected_is_double ? 8 : g.elem_bytes);
+    d.costs = g.costs + c * K; d.weights = g.weights + c * K; d.kept = g.kept + c * K;
+    d.kept_list = g.kept_list + c * keep;
+    d.minmax_enc = g.minmax_enc + 2 * c; d.valid_count = g.valid_count + c; d.argmin = g.argmin + c;
+    d.minmax = g.minmax + 4 * c; d.sums = g.sums + c * (1 + n);
+    d.wsum_partial = g.wsum_partial + (size_t)c * g.weight_blocks; d.grad_partial = g.grad_partial + (size_t)c * g.grad_blocks * n;
+    d.skip = g.skip + c;
+    d.sg_uu = g.sg_uu + (size_t)c * g.nu * g.sg_len; d.sg_tt = g.sg_tt + (size_t)c * g.nu * g.sg_len; d.sg_started = g.sg_started + c * g.nu;
+    d.frame_snap = g.frame_snap + (size_t)c * g.frame_doubles;
+    d.result = g.result + c * (n + 8);
+    d.optimal_cost = g.optimal_cost + c; d.breakdown = g.breakdown + 8 * c;
+    return d;
+}
+#endif
 
 cudaError_t upload_robot_model();  // once per device
 

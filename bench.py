@@ -117,26 +117,36 @@ def bench_controllers(args, rank, world, local_rank, n_gpus, dist, torch, el):
     total, K, T = 256, 1024, 64
     mine = list(range(rank, total, world))
     params = cases.assisted_params(True, abi.LINKS_BODY_COM)
-    engines, states, wrenches = [], [], []
+    states, wrenches = [], []
     for c in mine:
-        h = abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_ASSISTED_MANIPULATION, K, 0.64, precision=abi.FP32, dynamics_mode=abi.DYNAMICS_FUSED,
-                            keep_best=0, device=local_rank)
-        engines.append(el.Engine(h, params))
         x0 = abi.huddled_state(10.0)
         x0[0] += 0.002 * c; x0[1] -= 0.001 * c; x0[2] += 0.003 * c     # per-controller base offset
-        states.append(np.ascontiguousarray(x0))
+        states.append(x0)
         ang = 2 * np.pi * c / total + 0.5 * np.arange(T) * 0.01        # a force vector that turns over the horizon
         w = np.zeros((T, 6)); w[:, 0] = 10 * np.cos(ang); w[:, 1] = 10 * np.sin(ang)
-        wrenches.append(np.ascontiguousarray(w))
+        wrenches.append(w)
+    states, wrenches = np.ascontiguousarray(np.stack(states)), np.ascontiguousarray(np.stack(wrenches))
+    if args.separate_engines:
+        # one engine (own streams, own CUDA graph) per controller, overlapped with update_launch / update_wait
+        mk = lambda: abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_ASSISTED_MANIPULATION, K, 0.64, precision=abi.FP32,
+                                     dynamics_mode=abi.DYNAMICS_FUSED, keep_best=0, device=local_rank)
+        engines = [el.Engine(mk(), params) for _ in mine]
+    else:
+        # ONE batched engine: every kernel runs once with blockIdx.y = controller
+        engines = [el.Engine(abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_ASSISTED_MANIPULATION, K, 0.64, precision=abi.FP32,
+                                             dynamics_mode=abi.DYNAMICS_FUSED, keep_best=0, device=local_rank, batch=len(mine)), params)]
     lib = engines[0].lib
 
     def tick(step):
-        for e, x, w in zip(engines, states, wrenches):
-            rc = lib.mppi_b200_update_launch(e.h, el.ptr(x), 0.05 * step, el.ptr(w), None, abi.NOISE_PHILOX, 1)
-            assert rc == 0, e.error()
-        for e in engines:
-            rc = lib.mppi_b200_update_wait(e.h)
-            assert rc == 0, e.error()
+        if args.separate_engines:
+            for i, e in enumerate(engines):
+                rc = lib.mppi_b200_update_launch(e.h, el.ptr(states[i]), 0.05 * step, el.ptr(wrenches[i]), None, abi.NOISE_PHILOX, 1 + i)
+                assert rc == 0, e.error()
+            for e in engines:
+                rc = lib.mppi_b200_update_wait(e.h)
+                assert rc == 0, e.error()
+        else:
+            assert engines[0].update(states, 0.05 * step, wrenches, seed=1) == 0, engines[0].error()
 
     def barrier():
         if world > 1:
@@ -175,7 +185,7 @@ def bench_controllers(args, rank, world, local_rank, n_gpus, dist, torch, el):
     line = {"metric": "rollout-steps/s", "value": units / t_wall, "unit": "rollout-steps/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_wall / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "256_controllers_franka_ridgeback_assisted_K1024xT64_fp32", "controllers": total, "controllers_per_gpu": len(mine),
-                       "rollouts": K, "steps_per_rollout": T, "noise": "in-kernel Philox4x32-10", "parallelism": "controllers split over %d GPU(s), no collective" % world,
+                       "rollouts": K, "steps_per_rollout": T, "noise": "in-kernel Philox4x32-10", "parallelism": "controllers split over %d GPU(s), no collective; %s" % (world, "one engine per controller, overlapped streams" if args.separate_engines else "one batched engine per GPU (blockIdx.y = controller)"),
                        "timing": "host clock around one tick (launch all controllers, wait for all); per-controller states and wrench tables come from host memory every tick"},
             "clocks": sampler.result(),
             "e2e": {"value": units / t_wall, "unit": "rollout-steps/s", "h2d_bytes_per_step": int(len(mine) * 8 * (40 + 6 * T)), "d2h_bytes_per_step": int(len(mine) * 8 * (12 * T + 5)),
@@ -195,6 +205,7 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
+    ap.add_argument("--separate-engines", action="store_true", help="cfg5: one engine per controller instead of one batched engine")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

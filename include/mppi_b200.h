@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MPPI_B200_ABI_VERSION 1
+#define MPPI_B200_ABI_VERSION 2
 
 /* error codes */
 #define MPPI_B200_OK 0
@@ -160,6 +160,11 @@ typedef struct mppi_b200_config {
     uint32_t smoothing_window;
     uint32_t smoothing_order;
     int32_t threads; /* validated like mppi.cpp:66 (> 0); the CUDA grid replaces the pool */
+    /* Number of independent controllers that share this configuration and run as ONE grid (BASELINE.json
+     * config 5). 0 or 1 = a single mppi::Trajectory. With batch = B every per-update input and every
+     * read-back is the concatenation over controllers: state B x state_dof, wrench B x T x 6, noise
+     * B x (K+2) x T x nu, mppi_b200_get B x control_dof, ...; controller c draws Philox noise with seed + c. */
+    int32_t batch;
 } mppi_b200_config;
 
 typedef struct mppi_b200_engine mppi_b200_engine;
@@ -231,6 +236,7 @@ int mppi_b200_read(mppi_b200_engine *engine, int32_t what, void *dst, size_t byt
 #define MPPI_B200_QUERY_SHIFT_BY 7
 #define MPPI_B200_QUERY_STATE_DOF 8
 #define MPPI_B200_QUERY_CONTROL_DOF 9
+#define MPPI_B200_QUERY_BATCH 10
 int mppi_b200_query(mppi_b200_engine *engine, int32_t what, int64_t *value);
 
 /* time of the kernels of the last update on the device, seconds (CUDA events on the engine stream) */

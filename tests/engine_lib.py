@@ -62,7 +62,7 @@ class Engine:
         return out
 
     def get(self, time):
-        out = np.zeros(self.query(abi.QUERY_CONTROL_DOF))
+        out = np.zeros(self.query(abi.QUERY_CONTROL_DOF) * self.query(abi.QUERY_BATCH))
         assert self.lib.mppi_b200_get(self.h, ptr(out), time) == 0
         return out
 
