@@ -17,7 +17,11 @@
 #include <iostream>
 #include <memory>
 #include <mutex>
+#include <algorithm>
+#include <limits>
+#include <numeric>
 #include <optional>
+#include <random>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -106,6 +110,58 @@ struct DeviceBoundCost {
 
 }  // namespace mppi_b200
 
+namespace mppi_b200 {
+
+// controller/gaussian.hpp:12-90 restated for the reference-RNG mode of the facade: std::mt19937 with its
+// default seed, std::normal_distribution<double>, transform = V * sqrt(Lambda) of the covariance with the
+// eigenvalues in ascending order (SelfAdjointEigenSolver). Host code: it only feeds the injected-noise
+// path, so that closed-loop traces can be compared with a real reference build sample for sample.
+class ReferenceGaussian {
+public:
+    ReferenceGaussian(int n, const double *covariance /* n x n column-major */) : m_n(n), m_transform((std::size_t)n * n, 0.0) {
+        std::vector<double> a(covariance, covariance + (std::size_t)n * n), V((std::size_t)n * n, 0.0), ev((std::size_t)n);
+        auto A = [&](int r, int c) -> double & { return a[(std::size_t)c * n + r]; };
+        auto E = [&](int r, int c) -> double & { return V[(std::size_t)c * n + r]; };
+        for (int i = 0; i < n; i++) E(i, i) = 1.0;
+        for (int sweep = 0; sweep < 64; sweep++) {  // cyclic Jacobi; exact for the diagonal covariances of base.hpp:79-83
+            double off = 0.0;
+            for (int p = 0; p < n; p++) for (int q = p + 1; q < n; q++) off += A(p, q) * A(p, q);
+            if (off == 0.0) break;
+            for (int p = 0; p < n; p++)
+                for (int q = p + 1; q < n; q++) {
+                    if (A(p, q) == 0.0) continue;
+                    const double theta = (A(q, q) - A(p, p)) / (2.0 * A(p, q));
+                    const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                    const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                    for (int k = 0; k < n; k++) { const double x = A(k, p), y = A(k, q); A(k, p) = c * x - s * y; A(k, q) = s * x + c * y; }
+                    for (int k = 0; k < n; k++) { const double x = A(p, k), y = A(q, k); A(p, k) = c * x - s * y; A(q, k) = s * x + c * y; }
+                    for (int k = 0; k < n; k++) { const double x = E(k, p), y = E(k, q); E(k, p) = c * x - s * y; E(k, q) = s * x + c * y; }
+                }
+        }
+        for (int i = 0; i < n; i++) ev[(std::size_t)i] = A(i, i);
+        for (int i = 0; i < n - 1; i++) {  // Eigen sorts with a selection sort that swaps
+            int k = 0;
+            for (int j = 1; j < n - i; j++) if (ev[(std::size_t)(i + j)] < ev[(std::size_t)(i + k)]) k = j;
+            if (k > 0) { std::swap(ev[(std::size_t)i], ev[(std::size_t)(i + k)]); for (int r = 0; r < n; r++) std::swap(E(r, i), E(r, i + k)); }
+        }
+        for (int c = 0; c < n; c++) for (int r = 0; r < n; r++) m_transform[(std::size_t)c * n + r] = E(r, c) * std::sqrt(ev[(std::size_t)c]);
+    }
+    // gaussian.hpp:70-75: mean + transform * z, z drawn element by element
+    void operator()(double *out) {
+        std::vector<double> z((std::size_t)m_n);
+        for (auto &v : z) v = m_distribution(m_generator);
+        for (int r = 0; r < m_n; r++) out[r] = 0.0;
+        for (int c = 0; c < m_n; c++) for (int r = 0; r < m_n; r++) out[r] += m_transform[(std::size_t)c * m_n + r] * z[(std::size_t)c];
+    }
+private:
+    int m_n;
+    std::vector<double> m_transform;
+    std::mt19937 m_generator;
+    std::normal_distribution<double> m_distribution{0, 1};
+};
+
+}  // namespace mppi_b200
+
 namespace mppi {
 
 class Trajectory {
@@ -175,8 +231,9 @@ public:
         bool have = true;
         for (int k = 0; k < m_step_count && have; k++) have = m_device_dynamics->forecast_wrench(time + k * m_time_step, &m_wrench[(std::size_t)6 * k]);
         if (have && m_step_count > 0) wrench = m_wrench.data();
-        const void *noise = m_injected;
-        const int source = m_injected ? MPPI_B200_NOISE_HOST : MPPI_B200_NOISE_PHILOX;
+        if (m_reference_rng) sample_like_the_reference(time);
+        const void *noise = m_reference_rng ? m_reference_noise.data() : m_injected;
+        const int source = noise ? MPPI_B200_NOISE_HOST : MPPI_B200_NOISE_PHILOX;
         int rc;
         {
             std::scoped_lock lock(m_optimal_control_mutex);  // get() may run concurrently (mppi.cpp:179,492)
@@ -226,6 +283,10 @@ public:
     // would draw a fresh column; nullptr returns to in-kernel Philox.
     void set_injected_noise(const double *noise) { m_injected = noise; }
     void set_seed(std::uint64_t seed) { m_seed = seed; }
+    // Reference-RNG mode: the noise is drawn on the host with the reference's generator in the reference's
+    // order (kept rollouts' new tail columns first, then every resampled rollout, both in cost order,
+    // mppi.cpp:222-262) and injected; the device then reproduces a reference build sample for sample.
+    void use_reference_rng(bool on) { m_reference_rng = on; }
     mppi_b200_engine *engine() { return m_engine; }
 
 private:
@@ -237,7 +298,32 @@ private:
           m_rollout_count((int)(configuration.rollouts + s_static_rollouts)), m_state_dof(m_dynamics->get_state_dof()), m_control_dof(m_dynamics->get_control_dof()),
           m_rollout_state(m_dynamics->get_state_dof()), m_weights(m_rollout_count), m_gradient(m_control_dof, m_step_count), m_optimal_control(m_control_dof, m_step_count),
           m_wrench((std::size_t)6 * m_step_count, 0.0) {
+        m_covariance = configuration.covariance;
+        m_keep_best = configuration.keep_best_rollouts;
         m_rollout_state.setZero(); m_weights.setZero(); m_gradient.setZero(); m_optimal_control.setZero();
+    }
+
+    void sample_like_the_reference(double time) {
+        const std::size_t nu = (std::size_t)m_control_dof, T = (std::size_t)m_step_count, R = (std::size_t)m_rollout_count;
+        if (!m_gaussian) m_gaussian = std::make_unique<mppi_b200::ReferenceGaussian>(m_control_dof, m_covariance.data());
+        m_reference_noise.assign(R * T * nu, 0.0);
+        // mppi.cpp:194-201
+        const std::int64_t shift_by = (std::int64_t)((time - m_last_shift_time) / m_time_step);
+        if (shift_by > 0) m_last_shift_time = time;
+        const std::int64_t shifted = (std::int64_t)T - shift_by;
+        // mppi.cpp:222-231: indices 2.. sorted by the PREVIOUS update's costs, stable
+        std::vector<double> costs(R, 0.0);
+        if (m_update_count > 0) mppi_b200_read(m_engine, MPPI_B200_READ_COSTS, costs.data(), R * sizeof(double));
+        std::vector<std::size_t> order(R - 2);
+        std::iota(order.begin(), order.end(), (std::size_t)2);
+        auto key = [&](std::size_t i) { return std::isnan(costs[i]) ? std::numeric_limits<double>::infinity() : costs[i]; };
+        std::stable_sort(order.begin(), order.end(), [&](std::size_t l, std::size_t r) { return key(l) < key(r); });
+        const std::size_t keep = std::min<std::size_t>((std::size_t)m_keep_best, order.size());
+        if (shift_by > 0)
+            for (std::size_t i = 0; i < keep; i++)
+                for (std::size_t c = (std::size_t)std::max<std::int64_t>(shifted, 0); c < T; c++) (*m_gaussian)(&m_reference_noise[(order[i] * T + c) * nu]);
+        for (std::size_t i = keep; i < order.size(); i++)
+            for (std::size_t c = 0; c < T; c++) (*m_gaussian)(&m_reference_noise[(order[i] * T + c) * nu]);
     }
 
     void refresh() {
@@ -278,6 +364,12 @@ private:
     std::vector<double> m_wrench;
     std::mutex m_optimal_control_mutex;
     const double *m_injected = nullptr;
+    bool m_reference_rng = false;
+    std::unique_ptr<mppi_b200::ReferenceGaussian> m_gaussian;
+    std::vector<double> m_reference_noise;
+    MatrixXd m_covariance;
+    std::int64_t m_keep_best = 0;
+    double m_last_shift_time = 0.0;
     std::uint64_t m_seed = 0x5EED0000ull;
     bool m_stale = true;
 };

@@ -17,8 +17,14 @@ int main(int argc, char **argv) {
     const double horison = std::atof(argv[3]);
     const int updates = std::atoi(argv[4]);
     mppi::Configuration c;
-    c.rollouts = K; c.keep_best_rollouts = 20; c.time_step = 0.01; c.horison = horison; c.gradient_step = 2.0; c.cost_scale = 10.0; c.cost_discount_factor = 1.0;
-    c.control_bound = true; c.smoothing = mppi::Configuration::Smoothing{10, 1}; c.threads = 1;
+    // optional 7th.. arguments: keep_best, smoothing (0/1), cadence, x0 values for the toy, "refrng"
+    const long keep_best = argc > 7 ? std::atol(argv[7]) : 20;
+    const bool smoothing = argc > 8 ? std::atoi(argv[8]) != 0 : true;
+    const double cadence = argc > 9 ? std::atof(argv[9]) : 0.05;
+    const bool refrng = argc > 10 && std::strcmp(argv[10], "refrng") == 0;
+    c.rollouts = K; c.keep_best_rollouts = keep_best; c.time_step = 0.01; c.horison = horison; c.gradient_step = 2.0; c.cost_scale = 10.0; c.cost_discount_factor = 1.0;
+    c.control_bound = true; c.threads = 1;
+    if (smoothing) c.smoothing = mppi::Configuration::Smoothing{10, 1};
     std::unique_ptr<mppi::Dynamics> dyn; std::unique_ptr<mppi::Cost> cost;
     VectorXd x0;
     if (which == "toy") {
@@ -29,6 +35,7 @@ int main(int argc, char **argv) {
         dyn = mppi_b200::DoubleIntegrator::create();
         cost = mppi_b200::PointCost::create(mppi_b200::PointCost::default_configuration());
         x0 = VectorXd(4);
+        for (int i = 0; i < 4 && 11 + i < argc; i++) x0[i] = std::atof(argv[11 + i]);
     } else {
         const double var[12] = {0.1, 0.1, 0.2, 7.5, 7.5, 7.5, 7.5, 7.5, 7.5, 7.5, 0.0, 0.0};           // base.hpp:79-83
         const double lim[12] = {0.5, 0.5, 1.0, 100, 100, 100, 100, 100, 100, 100, 0.05, 0.05};          // base.hpp:85-94
@@ -39,7 +46,7 @@ int main(int argc, char **argv) {
         x0 = VectorXd(31);
         const double q[12] = {0.2, 0.2, kPi / 4, 0.0, kPi / 5, 0.0, -kPi / 2, 0.0, 2, kPi / 4, 0.025, 0.025};  // state.cpp:15-19
         for (int i = 0; i < 12; i++) x0[i] = q[i];
-        x0[30] = 10.0;
+        x0[30] = argc > 11 ? std::atof(argv[11]) : 10.0;
         if (which == "track") {
             dyn = FrankaRidgeback::PinocchioDynamics::create();
             cost = FrankaRidgeback::TrackPoint::create(FrankaRidgeback::TrackPoint::default_configuration());
@@ -52,6 +59,7 @@ int main(int argc, char **argv) {
     }
     auto trajectory = mppi::Trajectory::create(c, std::move(dyn), std::move(cost));
     if (!trajectory) return 3;
+    trajectory->use_reference_rng(refrng);
     const std::size_t nu = trajectory->get_control_dof(), T = trajectory->get_step_count(), R = trajectory->get_rollout_count();
     std::vector<double> noise;
     if (std::strcmp(argv[5], "-") != 0) {
@@ -63,10 +71,10 @@ int main(int argc, char **argv) {
     std::ofstream out(argv[6], std::ios::binary);
     for (int u = 0; u < updates; u++) {
         if (!noise.empty()) trajectory->set_injected_noise(noise.data() + (std::size_t)u * R * T * nu);
-        trajectory->update(x0, 0.05 * u);
+        trajectory->update(x0, cadence * u);
         const MatrixXd &U = trajectory->trajectory();
         out.write(reinterpret_cast<const char *>(U.data()), (std::streamsize)(nu * T * 8));
-        VectorXd ctl = (*trajectory)(0.05 * u + 0.013);
+        VectorXd ctl = (*trajectory)(cadence * u + 0.013);
         out.write(reinterpret_cast<const char *>(ctl.data()), (std::streamsize)(nu * 8));
         const double oc = trajectory->get_optimal_total_cost();
         out.write(reinterpret_cast<const char *>(&oc), 8);

@@ -49,3 +49,36 @@ def test_facade_matches_oracle(oracle, tmp_path, which):
         got = np.array([float(x) for x in r.stdout.split("breakdown")[1].split("\n")[0].split()])
         assert np.allclose(got, o.read(abi.READ_BREAKDOWN, 8)[:7], rtol=1e-8, atol=1e-8)
     o.close()
+
+
+GOLDEN_ARGS = {
+    # case -> (which, K, horison, updates, keep, smoothing, cadence, extra x0 args)
+    "toy_k100_nosmooth": ("toy", 100, 1.0, 6, 0, 0, 0.05, ["0", "0", "0", "0"]),
+    "toy_k253_keep20": ("toy", 253, 1.0, 6, 20, 1, 0.05, ["0.1", "-0.2", "0.3", "0.0"]),
+    "toy_k50_oddcadence": ("toy", 50, 0.3, 8, 20, 1, 0.013, ["0", "0", "0", "0"]),
+    "franka_trackpoint_k50": ("track", 50, 0.3, 5, 20, 1, 0.05, ["100.0"]),
+    "franka_assisted_k60": ("assisted", 60, 0.3, 5, 20, 1, 0.05, ["10.0"]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_ARGS))
+def test_reference_rng_mode_reproduces_the_reference_build(golden, tmp_path, name):
+    """End to end against the REFERENCE ITSELF: tests/golden/ref_mppi.npz holds what the reference's own
+    mppi.cpp / filter.cpp / gaussian.hpp (compiled unmodified, oracle/_ref) published over several closed-loop
+    updates with its mt19937 sampling. The facade in reference-RNG mode draws the same stream on the host,
+    the device does everything else; the control sequences must agree to 1e-9."""
+    which, K, horison, updates, keep, smoothing, cadence, extra = GOLDEN_ARGS[name]
+    exe = build_facade_demo()
+    r = subprocess.run([exe, which, str(K), str(horison), str(updates), "-", str(tmp_path / "out.bin"), str(keep), str(smoothing), str(cadence), "refrng"] + extra,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    nu = 2 if which == "toy" else 12
+    T, R = int(np.ceil(horison / 0.01)), K + 2
+    rec = np.fromfile(str(tmp_path / "out.bin")).reshape(updates, nu * T + nu + 1 + R)
+    U_ref, w_ref, oc_ref, get_ref = golden[name + "/optimal"], golden[name + "/weights"], golden[name + "/optimal_cost"], golden[name + "/get"]
+    for u in range(updates):
+        scale = np.abs(U_ref[u]).max()
+        assert np.abs(rec[u, :nu * T] - U_ref[u]).max() <= 1e-9 * scale, (u, np.abs(rec[u, :nu * T] - U_ref[u]).max() / scale)
+        assert np.allclose(rec[u, nu * T:nu * T + nu], get_ref[u], rtol=1e-9, atol=1e-9 * scale)
+        assert abs(rec[u, nu * T + nu] - oc_ref[u, 0]) <= 1e-8 * abs(oc_ref[u, 0])
+        assert np.allclose(rec[u, nu * T + nu + 1:], w_ref[u], rtol=1e-8, atol=1e-14)
