@@ -1,0 +1,39 @@
+"""Every kernel variant (systems x objectives x FP64/FP32 x FAITHFUL/FUSED x single/batched) runs a few
+updates with keep-best, smoothing, Philox and injected noise without error and publishes finite controls
+(compute-sanitizer is closed on this pool; this is the broad exercise, parity is in test_gpu_parity.py)."""
+import numpy as np
+import pytest
+
+import cases
+from assistedmanipulation_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+RUNS = [
+    ("toy", abi.SYSTEM_TOY, abi.OBJECTIVE_TOY, abi.default_toy_objective, 70, 0.24, lambda: np.zeros(4), None, 2, 1),
+    ("track", abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_TRACK_POINT, abi.default_track_point, 70, 0.2, abi.huddled_state, None, 12, 1),
+    ("assisted", abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_ASSISTED_MANIPULATION, lambda: cases.assisted_params(True, abi.LINKS_BODY_COM), 70, 0.2,
+     lambda: abi.huddled_state(10.0), cases.constant_wrench(20), 12, 1),
+    ("assisted_batch3", abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_ASSISTED_MANIPULATION, lambda: cases.assisted_params(False, abi.LINKS_ZERO), 40, 0.2,
+     lambda: abi.huddled_state(10.0), cases.constant_wrench(20), 12, 3),
+]
+
+
+@pytest.mark.parametrize("run", RUNS, ids=[r[0] for r in RUNS])
+@pytest.mark.parametrize("precision", [abi.FP64, abi.FP32])
+@pytest.mark.parametrize("mode", [abi.DYNAMICS_FUSED, abi.DYNAMICS_FAITHFUL])
+def test_variant_runs(run, precision, mode):
+    import engine_lib as el
+    _, system, objective, params, K, horison, x0, w, nu, batch = run
+    e = el.Engine(abi.make_config(system, objective, K, horison, keep_best=8, precision=precision, dynamics_mode=mode, batch=batch), params())
+    T = e.query(abi.QUERY_STEP_COUNT)
+    xs = np.stack([x0()] * batch)
+    ws = None if w is None else np.stack([w] * batch)
+    rng = np.random.default_rng(0)
+    for u in range(3):
+        noise = rng.standard_normal((batch, K + 2, T, nu)) if u == 1 else None
+        assert e.update(xs, 0.05 * u, ws, noise, seed=1) == 0, e.error()
+        U = e.read(abi.READ_OPTIMAL, batch * nu * T)
+        assert np.all(np.isfinite(U))
+    assert np.all(np.isfinite(e.read(abi.READ_OPTIMAL_COST, batch)))
+    e.close()
