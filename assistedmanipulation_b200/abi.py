@@ -83,6 +83,14 @@ class Config(C.Structure):
                 ("threads", C.c_int32), ("batch", C.c_int32)]
 
 
+class ForecastConfig(C.Structure):
+    """mppi_b200_forecast_config (reference Forecast::Configuration, forecast.hpp:388-413)."""
+    _fields_ = [("type", C.c_int32), ("batch", C.c_int32), ("device", C.c_int32), ("order", C.c_uint32),
+                ("time_step", C.c_double), ("horison", C.c_double), ("window", C.c_double)]
+
+
+FORECAST_LOCF, FORECAST_AVERAGE, FORECAST_KALMAN = 0, 1, 2
+
 EXPORTS = [
     "mppi_b200_create", "mppi_b200_destroy", "mppi_b200_last_error", "mppi_b200_update",
     "mppi_b200_update_begin", "mppi_b200_update_weights", "mppi_b200_update_finish",
@@ -92,6 +100,9 @@ EXPORTS = [
     "mppi_b200_default_assisted_manipulation", "mppi_b200_default_toy_objective",
     "mppi_b200_set_profiling", "mppi_b200_stage_seconds", "mppi_b200_measure_fma_peak",
     "mppi_b200_update_launch", "mppi_b200_update_wait",
+    "mppi_b200_forecast_create", "mppi_b200_forecast_destroy", "mppi_b200_forecast_last_error",
+    "mppi_b200_forecast_update", "mppi_b200_forecast_update_time", "mppi_b200_forecast_table",
+    "mppi_b200_forecast_table_device", "mppi_b200_set_wrench_device",
 ]
 STAGES = ("h2d", "warm_start_shift", "sample", "rollout", "weights", "weighted_sum", "finish", "d2h")
 
@@ -154,6 +165,22 @@ def load_library(path=None):
     lib.mppi_b200_default_track_point.argtypes = [C.POINTER(TrackPoint)]
     lib.mppi_b200_default_assisted_manipulation.argtypes = [C.POINTER(AssistedManipulation)]
     lib.mppi_b200_default_toy_objective.argtypes = [C.POINTER(ToyObjective)]
+    lib.mppi_b200_forecast_create.argtypes = [C.POINTER(ForecastConfig), _dp, C.POINTER(C.c_void_p)]
+    lib.mppi_b200_forecast_create.restype = C.c_int
+    lib.mppi_b200_forecast_destroy.argtypes = [C.c_void_p]
+    lib.mppi_b200_forecast_destroy.restype = None
+    lib.mppi_b200_forecast_last_error.argtypes = [C.c_void_p]
+    lib.mppi_b200_forecast_last_error.restype = C.c_char_p
+    lib.mppi_b200_forecast_update.argtypes = [C.c_void_p, _dp, C.c_double]
+    lib.mppi_b200_forecast_update.restype = C.c_int
+    lib.mppi_b200_forecast_update_time.argtypes = [C.c_void_p, C.c_double]
+    lib.mppi_b200_forecast_update_time.restype = C.c_int
+    lib.mppi_b200_forecast_table.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int32, _dp]
+    lib.mppi_b200_forecast_table.restype = C.c_int
+    lib.mppi_b200_forecast_table_device.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.mppi_b200_forecast_table_device.restype = C.c_int
+    lib.mppi_b200_set_wrench_device.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mppi_b200_set_wrench_device.restype = C.c_int
     return lib
 
 

@@ -129,6 +129,7 @@ struct mppi_b200_engine {
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     int graph_launches = 0;
     bool use_graphs = true;
+    const double *wrench_device = nullptr;   // forecast table left on the device by the forecast producer (batch x T x 6)
     void *d_zero_row = nullptr;
     void *d_injected = nullptr;
     size_t noise_elems = 0;
@@ -365,8 +366,8 @@ int host_prepare(mppi_b200_engine *e, const double *state, double time, const do
         std::memcpy(f->x0, state + (size_t)c * d.nx, sizeof(double) * d.nx);
         f->time = time; f->sg_prev_trim = 0.0; f->shift_by = shift_by; f->seed = seed + (uint64_t)c;
         f->update_index = (unsigned long long)e->update_count;
-        f->has_wrench = wrench != nullptr; f->noise_source = noise_source;
-        if (wrench) std::memcpy(base + sizeof(Frame), wrench + (size_t)c * 6 * d.T, sizeof(double) * 6 * d.T);
+        f->has_wrench = wrench != nullptr || e->wrench_device != nullptr; f->noise_source = noise_source;
+        if (wrench && !e->wrench_device) std::memcpy(base + sizeof(Frame), wrench + (size_t)c * 6 * d.T, sizeof(double) * 6 * d.T);
     }
     // double-buffered snapshot for the side-stream re-rollout
     const int slot = (int)(e->update_count & 1);
@@ -378,6 +379,8 @@ int enqueue_begin(mppi_b200_engine *e, const void *noise, int32_t noise_source) 
     DeviceState &d = e->d;
     STAGE(e, 0);
     CUDA_TRY(e, cudaMemcpyAsync(e->d_frame, e->h_frame, e->frame_bytes * e->batch, cudaMemcpyHostToDevice, e->stream));
+    if (e->wrench_device)   // the forecast producer's table goes straight into the frames' wrench rows
+        CUDA_TRY(e, cudaMemcpy2DAsync(e->d_frame + sizeof(Frame), e->frame_bytes, e->wrench_device, sizeof(double) * 6 * d.T, sizeof(double) * 6 * d.T, e->batch, cudaMemcpyDeviceToDevice, e->stream));
     const int prec = e->cfg.precision;
     if (noise_source == MPPI_B200_NOISE_HOST) {
         if (!e->d_injected) { e->d_injected = dev_alloc<double>(e, e->noise_elems, false); if (!e->d_injected) return fail(e, MPPI_B200_ERR_CUDA, "device allocation failed"); }
@@ -492,6 +495,19 @@ int wait_slot(mppi_b200_engine *e) {
 }
 
 }  // namespace
+
+int mppi_b200_set_wrench_device(mppi_b200_engine *e, const double *device_table) {
+    if (!e) return MPPI_B200_ERR_INVALID;
+    if (e->d.nx != 31) return fail(e, MPPI_B200_ERR_UNSUPPORTED, "the toy system has no wrench forecast");
+    if (device_table != e->wrench_device) {
+        // the copy's source address is part of the captured update: capture again on the next launch
+        CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+        CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+        for (cudaGraphExec_t &g : e->graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+        e->wrench_device = device_table;
+    }
+    return MPPI_B200_OK;
+}
 
 int mppi_b200_update_begin(mppi_b200_engine *e, const double *state, double time, const double *wrench, const void *noise, int32_t noise_source, uint64_t seed) {
     if (!e || !state) return MPPI_B200_ERR_INVALID;

@@ -261,6 +261,45 @@ void mppi_b200_default_track_point(mppi_b200_track_point *out);
 void mppi_b200_default_assisted_manipulation(mppi_b200_assisted_manipulation *out);
 void mppi_b200_default_toy_objective(mppi_b200_toy_objective *out);
 
+/* ---- Wrench forecast producer: the table W[t] the objective consumes --------------------
+ * Batched device implementation of the reference's forecasters for 6-component wrenches
+ * (src/controller/forecast.{hpp,cpp}: LOCFForecast :62-140, AverageForecast cpp:41-128, KalmanForecast
+ * cpp:130-367 over KalmanFilter kalman.cpp:89-152). One object holds `batch` independent forecasters that
+ * share a configuration; every call acts on all of them. */
+#define MPPI_B200_FORECAST_LOCF 0     /* Forecast::Configuration::Type, forecast.hpp:391-396 */
+#define MPPI_B200_FORECAST_AVERAGE 1
+#define MPPI_B200_FORECAST_KALMAN 2
+
+typedef struct mppi_b200_forecast_config {
+    int32_t type;      /* MPPI_B200_FORECAST_* */
+    int32_t batch;     /* forecasters (>= 1) */
+    int32_t device;
+    uint32_t order;    /* KalmanForecast::Configuration::order (0..2) */
+    double time_step;  /* KalmanForecast::Configuration::time_step */
+    double horison;    /* LOCF / Kalman horison */
+    double window;     /* AverageForecast::Configuration::window */
+} mppi_b200_forecast_config;
+
+typedef struct mppi_b200_forecast mppi_b200_forecast;
+
+/* initial: batch x 6 (LOCF observation / Kalman initial_state) or NULL for zeros */
+int mppi_b200_forecast_create(const mppi_b200_forecast_config *config, const double *initial, mppi_b200_forecast **forecast);
+void mppi_b200_forecast_destroy(mppi_b200_forecast *forecast);
+/* message of the last failed call on this object (NULL: of the last failed create on this thread) */
+const char *mppi_b200_forecast_last_error(const mppi_b200_forecast *forecast);
+/* Forecast::update(measurement, time) for every forecaster; measurements: host, batch x 6 */
+int mppi_b200_forecast_update(mppi_b200_forecast *forecast, const double *measurements, double time);
+/* Forecast::update(time) */
+int mppi_b200_forecast_update_time(mppi_b200_forecast *forecast, double time);
+/* Forecast::forecast(time + k * time_step).head(6) for k < steps: host table, batch x steps x 6 */
+int mppi_b200_forecast_table(mppi_b200_forecast *forecast, double time, double time_step, int32_t steps, double *table);
+/* The same table left on the device (valid until the next call on this object); hand it to
+ * mppi_b200_set_wrench_device so a batched engine consumes it without a host round trip. */
+int mppi_b200_forecast_table_device(mppi_b200_forecast *forecast, double time, double time_step, int32_t steps, const double **device_table);
+/* From now on the engine takes its forecast wrench table (batch x T x 6, FP64) from this device address instead
+ * of the `wrench` argument of mppi_b200_update; NULL restores the host argument. */
+int mppi_b200_set_wrench_device(mppi_b200_engine *engine, const double *device_table);
+
 /* Host-side Philox4x32-10 + Box–Muller exactly as the sampling kernel evaluates it is NOT
  * provided: the engine's generated noise is read back with MPPI_B200_READ_NOISE instead. */
 

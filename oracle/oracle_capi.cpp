@@ -6,6 +6,7 @@
 #include <string>
 
 #include "systems.hpp"
+#include "forecast_oracle.hpp"
 
 using namespace oracle;
 
@@ -216,6 +217,25 @@ uint64_t oracle_count_step_flops(int objective, const void *params, uint64_t *ou
     c.step(u2, Counted(0.01));
     if (out6) { out6[0] = OpCount::addsub; out6[1] = OpCount::mul; out6[2] = OpCount::div; out6[3] = OpCount::sqrt_; out6[4] = OpCount::trans; out6[5] = OpCount::cmp; }
     return OpCount::flops();
+}
+
+// ---- wrench forecast producer ------------------------------------------------------
+// type: 0 LOCF, 1 AVERAGE, 2 KALMAN (Forecast::Configuration::Type, forecast.hpp:391-396)
+void *oracle_forecast_create(int type, int states, double horison_or_window, double time_step, unsigned order, const double *initial) {
+    std::vector<double> init(states, 0.0);
+    if (initial) init.assign(initial, initial + states);
+    ForecastOracle *f = nullptr;
+    if (type == 0) f = new LocfOracle(init, horison_or_window);
+    else if (type == 1) f = new AverageOracle((unsigned)states, horison_or_window);
+    else f = new KalmanOracle((unsigned)states, time_step, horison_or_window, order, init);
+    return f;
+}
+void oracle_forecast_destroy(void *h) { delete static_cast<ForecastOracle *>(h); }
+void oracle_forecast_update(void *h, const double *m, int n, double time) { static_cast<ForecastOracle *>(h)->update(std::vector<double>(m, m + n), time); }
+void oracle_forecast_update_time(void *h, double time) { static_cast<ForecastOracle *>(h)->update(time); }
+void oracle_forecast_get(void *h, double time, double *out, int n) {
+    const std::vector<double> v = static_cast<ForecastOracle *>(h)->forecast(time);
+    for (int i = 0; i < n && i < (int)v.size(); i++) out[i] = v[(size_t)i];
 }
 
 }  // extern "C"

@@ -4,3 +4,4 @@
 #include <Eigen/Core>
 using VectorXd = Eigen::VectorXd;
 using MatrixXd = Eigen::MatrixXd;
+using Vector6d = Eigen::Vector6;

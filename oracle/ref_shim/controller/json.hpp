@@ -2,3 +2,7 @@
 // JSON conversions are host configuration plumbing outside the hot path.
 #pragma once
 #define NLOHMANN_DEFINE_TYPE_INTRUSIVE(...)
+#define NLOHMANN_JSON_SERIALIZE_ENUM(...)
+#include <optional>
+#include <string>
+#include <iostream>
