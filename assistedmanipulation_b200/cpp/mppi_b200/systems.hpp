@@ -9,6 +9,7 @@
 #pragma once
 #include <array>
 
+#include "mppi_b200/forecast.hpp"
 #include "mppi_b200/trajectory.hpp"
 
 namespace mppi_b200 {
@@ -64,13 +65,20 @@ public:
     // pinocchio_dynamics.hpp:56-61
     static Configuration default_configuration() { return Configuration{"", "panda_grasp_joint", 10.0}; }
     using WrenchForecast = std::function<std::array<double, 6>(double time)>;
-    static std::unique_ptr<PinocchioDynamics> create() { return create(default_configuration(), nullptr); }
-    static std::unique_ptr<PinocchioDynamics> create(Configuration configuration, WrenchForecast forecast = nullptr) {
+    static std::unique_ptr<PinocchioDynamics> create() { return create(default_configuration(), WrenchForecast(nullptr)); }
+    static std::unique_ptr<PinocchioDynamics> create(Configuration configuration) { return create(configuration, WrenchForecast(nullptr)); }
+    static std::unique_ptr<PinocchioDynamics> create(Configuration configuration, WrenchForecast forecast) {
         // the kinematic tree is the one extracted from model/robot.urdf at build time (csrc/robot_model.h)
         if (configuration.end_effector_frame != "panda_grasp_joint") { std::cerr << "mppi_b200: end effector frame must be panda_grasp_joint" << std::endl; return nullptr; }
         return std::unique_ptr<PinocchioDynamics>(new PinocchioDynamics(configuration, std::move(forecast)));
     }
-    std::unique_ptr<mppi::Dynamics> copy() override { return create(m_configuration, m_forecast); }
+    // The wrench forecast handle as a device producer (mppi_b200/forecast.hpp): its table never leaves the device.
+    static std::unique_ptr<PinocchioDynamics> create(Configuration configuration, std::shared_ptr<Forecast> wrench_forecast) {
+        auto dynamics = create(configuration, WrenchForecast(nullptr));
+        if (dynamics) dynamics->m_device_forecast = std::move(wrench_forecast);
+        return dynamics;
+    }
+    std::unique_ptr<mppi::Dynamics> copy() override { auto c = create(m_configuration, m_forecast); if (c) c->m_device_forecast = m_device_forecast; return c; }
     mppi::Ref<VectorXd> step(const VectorXd &, double) override { mppi_b200::host_call("PinocchioDynamics::step"); }
     void set_state(const VectorXd &s, double) override { m_state = s; }
     mppi::Ref<VectorXd> get_state() override { return m_state; }
@@ -83,7 +91,11 @@ public:
         for (int i = 0; i < 6; i++) w[i] = v[(std::size_t)i];
         return true;
     }
+    const double *forecast_table_device(double time, double time_step, int steps) const override {
+        return m_device_forecast ? m_device_forecast->table_device(time, time_step, steps) : nullptr;
+    }
 private:
+    std::shared_ptr<Forecast> m_device_forecast;
     PinocchioDynamics(const Configuration &c, WrenchForecast f) : m_configuration(c), m_forecast(std::move(f)) {}
     Configuration m_configuration;
     WrenchForecast m_forecast;

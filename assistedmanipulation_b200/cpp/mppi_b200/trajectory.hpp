@@ -99,6 +99,8 @@ struct DeviceBoundDynamics {
     virtual int device_system() const = 0;
     // forecast->get_end_effector_wrench(time).head(6) (dynamics.hpp:275-278); false = no forecast handle
     virtual bool forecast_wrench(double /*time*/, double * /*wrench6*/) const { return false; }
+    // the same T x 6 table produced on the device by the forecast producer (forecast.hpp), or nullptr
+    virtual const double *forecast_table_device(double /*time*/, double /*time_step*/, int /*steps*/) const { return nullptr; }
 };
 struct DeviceBoundCost {
     virtual ~DeviceBoundCost() = default;
@@ -228,7 +230,9 @@ public:
     void update(const Ref<VectorXd> state, double time) {
         for (int i = 0; i < m_state_dof; i++) m_rollout_state[i] = state[i];
         const double *wrench = nullptr;
-        bool have = true;
+        const double *device_table = m_device_dynamics->forecast_table_device(time, m_time_step, m_step_count);
+        if (mppi_b200_set_wrench_device(m_engine, device_table) != MPPI_B200_OK && device_table) throw std::runtime_error(mppi_b200_last_error(m_engine));
+        bool have = device_table == nullptr;
         for (int k = 0; k < m_step_count && have; k++) have = m_device_dynamics->forecast_wrench(time + k * m_time_step, &m_wrench[(std::size_t)6 * k]);
         if (have && m_step_count > 0) wrench = m_wrench.data();
         if (m_reference_rng) sample_like_the_reference(time);

@@ -241,11 +241,15 @@ __global__ void k_table(ForecastState f, double time, double dt, int tsteps) {
         if (!(t_query > last + f.horison)) {
             double t = (t_query - last) / f.time_step;
             int lower = (int)t;
-            if (lower < 0) lower = 0;
-            if (lower > f.steps - 1) lower = f.steps - 1;   // the reference reads one column past the table exactly at the horizon
-            t -= (int)t;
+            t -= lower;
+            // the reference indexes its table with these unchecked (forecast.cpp:353-366): one column past the
+            // end exactly at the horizon (weight 0) and before the start for a query older than the last
+            // measurement. Here: the last column, and the estimate itself.
+            if (lower < 0) { lower = 0; t = 0.0; }
+            if (lower > f.steps) lower = f.steps;
+            const int upper = lower + 1 > f.steps ? f.steps : lower + 1;
             const double *pred = f.pred + (size_t)c * (f.steps + 1) * f.S;
-            v = (1.0 - t) * pred[(size_t)lower * f.S + j] + t * pred[(size_t)(lower + 1) * f.S + j];
+            v = (1.0 - t) * pred[(size_t)lower * f.S + j] + t * pred[(size_t)upper * f.S + j];
         }
     }
     f.table[((size_t)c * tsteps + k) * OBS + j] = v;

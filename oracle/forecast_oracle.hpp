@@ -172,8 +172,13 @@ struct KalmanOracle : ForecastOracle {
     std::vector<double> forecast(double time) override {  // forecast.cpp:342-367
         if (time > last_update + horison) return std::vector<double>(6, 0.0);
         double t = (time - last_update) / time_step;
-        const int lower = (int)t, upper = lower + 1;
+        int lower = (int)t;
         t -= lower;
+        // unchecked in the reference (one column past the table exactly at the horizon, weight 0; negative for a
+        // query older than the last measurement): clamp instead of reading out of bounds
+        if (lower < 0) { lower = 0; t = 0.0; }
+        if (lower > (int)steps) lower = (int)steps;
+        const int upper = std::min(lower + 1, (int)steps);
         std::vector<double> out(6);
         for (int k = 0; k < 6; k++) out[(std::size_t)k] = (1.0 - t) * prediction(k, lower) + t * prediction(k, upper);
         return out;

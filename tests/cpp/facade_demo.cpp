@@ -50,6 +50,17 @@ int main(int argc, char **argv) {
         if (which == "track") {
             dyn = FrankaRidgeback::PinocchioDynamics::create();
             cost = FrankaRidgeback::TrackPoint::create(FrankaRidgeback::TrackPoint::default_configuration());
+        } else if (which == "assisted_locf") {
+            // the wrench forecast as a device producer: last observation carried forward (forecast.hpp:62-140)
+            LOCFForecast::Configuration lc; lc.observation = VectorXd(6); lc.horison = 1e9;
+            std::shared_ptr<Forecast> forecast = LOCFForecast::create(lc);
+            if (!forecast) { std::fprintf(stderr, "forecast create failed\n"); return 3; }
+            VectorXd w(6); w[0] = 10.0;
+            forecast->update(w, 0.0);
+            dyn = FrankaRidgeback::PinocchioDynamics::create(FrankaRidgeback::PinocchioDynamics::default_configuration(), forecast);
+            auto p = FrankaRidgeback::AssistedManipulation::default_configuration();
+            p.enable_energy_limit = 1; p.link_position_mode = MPPI_B200_LINKS_BODY_COM;
+            cost = FrankaRidgeback::AssistedManipulation::create(p);
         } else {
             dyn = FrankaRidgeback::PinocchioDynamics::create(FrankaRidgeback::PinocchioDynamics::default_configuration(), [](double) { return std::array<double, 6>{10.0, 0, 0, 0, 0, 0}; });
             auto p = FrankaRidgeback::AssistedManipulation::default_configuration();
@@ -81,7 +92,7 @@ int main(int argc, char **argv) {
         const auto &w = trajectory->get_weights();
         out.write(reinterpret_cast<const char *>(w.data()), (std::streamsize)(R * 8));
     }
-    if (which == "assisted") {
+    if (which == "assisted" || which == "assisted_locf") {
         const auto &am = dynamic_cast<const FrankaRidgeback::AssistedManipulation &>(trajectory->get_optimal_cost());
         std::printf("breakdown %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", am.get_joint_limit_cost(), am.get_self_collision_cost(), am.get_workspace_cost(),
                     am.get_energy_tank_cost(), am.get_joint_velocity_cost(), am.get_trajectory_cost(), am.get_manipulability_cost());

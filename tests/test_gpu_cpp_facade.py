@@ -15,7 +15,7 @@ from test_abi_cpu import build_facade_demo
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("which", ["toy", "track", "assisted"])
+@pytest.mark.parametrize("which", ["toy", "track", "assisted", "assisted_locf"])
 def test_facade_matches_oracle(oracle, tmp_path, which):
     exe = build_facade_demo()
     K, horison, updates = 126, 0.3, 4
@@ -45,7 +45,7 @@ def test_facade_matches_oracle(oracle, tmp_path, which):
         oc = o.read(abi.READ_OPTIMAL_COST, 1)[0]
         assert abs(rec[u, nu * T + nu] - oc) <= 1e-8 * abs(oc)
         assert np.allclose(rec[u, nu * T + nu + 1:], o.read(abi.READ_WEIGHTS, R), rtol=1e-8, atol=1e-14)
-    if which == "assisted":
+    if which.startswith("assisted"):
         got = np.array([float(x) for x in r.stdout.split("breakdown")[1].split("\n")[0].split()])
         assert np.allclose(got, o.read(abi.READ_BREAKDOWN, 8)[:7], rtol=1e-8, atol=1e-8)
     o.close()
