@@ -136,8 +136,25 @@ def bench_controllers(args, rank, world, local_rank, n_gpus, dist, torch, el):
         engines = [el.Engine(abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_ASSISTED_MANIPULATION, K, 0.64, precision=abi.FP32,
                                              dynamics_mode=abi.DYNAMICS_FUSED, keep_best=0, device=local_rank, batch=len(mine)), params)]
     lib = engines[0].lib
+    forecaster = None
+    if args.forecast != "table":
+        # the wrench table is produced on the device from each controller's MEASURED wrench by the
+        # batched forecast producer (Kalman order 1, the simulation's default) and never visits the host
+        assert not args.separate_engines, "--forecast kalman needs the batched engine"
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import forecast_lib as fl
+        forecaster = fl.DeviceForecast(abi.FORECAST_KALMAN, 1.0, 0.01, 1, batch=len(mine))
+        measured = np.ascontiguousarray(wrenches[:, 0, :])
+        rng = np.random.default_rng(rank)
 
     def tick(step):
+        if forecaster is not None:
+            t = 0.05 * step
+            m = measured + rng.normal(0, 0.1, measured.shape)
+            assert lib.mppi_b200_forecast_update(forecaster.h, el.ptr(m), t) == 0
+            assert lib.mppi_b200_set_wrench_device(engines[0].h, forecaster.table_device(t, 0.01, T)) == 0
+            assert engines[0].update(states, t, None, seed=1) == 0, engines[0].error()
+            return
         if args.separate_engines:
             for i, e in enumerate(engines):
                 rc = lib.mppi_b200_update_launch(e.h, el.ptr(states[i]), 0.05 * step, el.ptr(wrenches[i]), None, abi.NOISE_PHILOX, 1 + i)
@@ -178,6 +195,8 @@ def bench_controllers(args, rank, world, local_rank, n_gpus, dist, torch, el):
         dist.destroy_process_group()
     for e in engines:
         e.close()
+    if forecaster is not None:
+        forecaster.close()
     if rank != 0:
         return 0
     units = total * (K + 2) * T * args.steps
@@ -186,11 +205,13 @@ def bench_controllers(args, rank, world, local_rank, n_gpus, dist, torch, el):
             "ms_per_step": t_wall / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "256_controllers_franka_ridgeback_assisted_K1024xT64_fp32", "controllers": total, "controllers_per_gpu": len(mine),
                        "rollouts": K, "steps_per_rollout": T, "noise": "in-kernel Philox4x32-10", "parallelism": "controllers split over %d GPU(s), no collective; %s" % (world, "one engine per controller, overlapped streams" if args.separate_engines else "one batched engine per GPU (blockIdx.y = controller)"),
-                       "timing": "host clock around one tick (launch all controllers, wait for all); per-controller states and wrench tables come from host memory every tick"},
+                       "timing": "host clock around one tick (launch all controllers, wait for all); per-controller states and wrench tables come from host memory every tick" if forecaster is None else
+                       "host clock around one tick (measured wrenches H2D -> batched Kalman forecast update -> device wrench table -> batched MPPI update)",
+                       "forecast": "host tables" if forecaster is None else "device Kalman producer, order 1, dt 0.01, horison 1.0"},
             "clocks": sampler.result(),
-            "e2e": {"value": units / t_wall, "unit": "rollout-steps/s", "h2d_bytes_per_step": int(len(mine) * 8 * (40 + 6 * T)), "d2h_bytes_per_step": int(len(mine) * 8 * (12 * T + 5)),
+            "e2e": {"value": units / t_wall, "unit": "rollout-steps/s", "h2d_bytes_per_step": int(len(mine) * 8 * (40 + (6 * T if forecaster is None else 6))), "d2h_bytes_per_step": int(len(mine) * 8 * (12 * T + 5)),
                     "tick_latency_us": {"p50": float(np.median(ticks) * 1e6), "p99": float(np.percentile(ticks, 99) * 1e6)}},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches) + (2 * args.steps if forecaster is not None else 0),   # + k_kalman_update, k_table per tick
             "per_controller_device_update_us": {"p50": float(np.median(dev) * 1e6), "max": float(dev.max() * 1e6)}}
     print(json.dumps(line))
     return 0
@@ -205,6 +226,7 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
+    ap.add_argument("--forecast", default="table", choices=["table", "kalman"], help="cfg5: host wrench tables, or the device forecast producer fed measured wrenches")
     ap.add_argument("--separate-engines", action="store_true", help="cfg5: one engine per controller instead of one batched engine")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
