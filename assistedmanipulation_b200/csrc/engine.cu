@@ -311,9 +311,9 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     d.wrench = reinterpret_cast<const double *>(e->d_frame + sizeof(Frame));
     A(d.U, n); A(d.U_shift, n); A(d.costs, (size_t)d.k_count); A(d.weights, (size_t)d.k_count);
     A(d.kept, (size_t)d.k_count); A(d.kept_list, (size_t)std::max<long long>(d.keep_best, 1));
-    d.world = c->world_size;
+    d.world = c->world_size; d.rank = c->rank;
     A(d.cand, (size_t)2 * std::max<long long>(d.keep_best, 1)); A(d.cand_all, (size_t)2 * std::max<long long>(d.keep_best, 1) * c->world_size);
-    A(d.minmax_enc, 2); A(d.valid_count, 1); A(d.argmin, 1); A(d.minmax, 4); A(d.sums, 1 + n);
+    A(d.minmax_enc, 2); A(d.valid_count, 1); A(d.argmin, 1); A(d.minmax, 4); A(d.sums, 1 + n + (size_t)c->world_size);
     d.weight_blocks = (int)((d.k_count + 255) / 256);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -577,7 +577,7 @@ int mppi_b200_update_launch(mppi_b200_engine *e, const double *state, double tim
         }
         if ((rc = enqueue_weights(e))) return rc;
         if (e->comm) {
-            ncclResult_t r = g_nccl.AllReduce(e->d.sums, e->d.sums, 1 + (size_t)e->d.nu * e->d.T, ncclDouble, ncclSum, e->comm, e->stream);
+            ncclResult_t r = g_nccl.AllReduce(e->d.sums, e->d.sums, 1 + (size_t)e->d.nu * e->d.T + (size_t)e->d.world, ncclDouble, ncclSum, e->comm, e->stream);
             if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-reduce failed");
         }
         if ((rc = enqueue_finish(e))) return rc;
@@ -605,7 +605,7 @@ int mppi_b200_reduce_buffers(mppi_b200_engine *e, void **minmax, size_t *minmax_
     if (minmax) *minmax = e->d.minmax;
     if (minmax_count) *minmax_count = 3;
     if (sums) *sums = e->d.sums;
-    if (sums_count) *sums_count = 1 + (size_t)e->d.nu * e->d.T;
+    if (sums_count) *sums_count = 1 + (size_t)e->d.nu * e->d.T + (e->d.world > 1 ? (size_t)e->d.world : 0);
     return MPPI_B200_OK;
 }
 

@@ -398,7 +398,15 @@ __global__ void __launch_bounds__(1024) k_gradient_reduce(const __grid_constant_
         for (int b = lane; b < d.weight_blocks; b += 32) s += d.wsum_partial[b];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) d.sums[0] = s;
+        if (lane == 0) {
+            d.sums[0] = s;
+            // sharded: one slot per rank after {sum w, sum w*eps} carries this rank's best global index + 1
+            // (0 = the global minimum is not here), so the SUM exchange doubles as an all-gather of the argmin
+            if (d.world > 1) {
+                const long long a = *d.argmin;
+                for (int r = 0; r < d.world; r++) d.sums[1 + d.nu * d.T + r] = (r == d.rank && a != 0x7fffffffffffffffll) ? (double)(a + 1) : 0.0;
+            }
+        }
     }
 }
 
@@ -428,7 +436,12 @@ __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DeviceSt
     const bool dead = !(d.minmax[2] >= 2.0);  // "all nan rollouts" (mppi.cpp:368-370): the reference throws before publishing
     if (ch == 0 && threadIdx.x == 0) {
         d.result[n + 0] = d.minmax[0]; d.result[n + 1] = d.minmax[1]; d.result[n + 2] = d.minmax[2];
-        d.result[n + 3] = __longlong_as_double(*d.argmin);
+        long long best = *d.argmin;
+        if (d.world > 1) {   // lowest global index among the ranks that hold the global minimum (mppi.cpp:363-366 order)
+            best = 0x7fffffffffffffffll;
+            for (int r = 0; r < d.world; r++) { const double v = d.sums[1 + n + r]; if (v > 0.0 && (long long)v - 1 < best) best = (long long)v - 1; }
+        }
+        d.result[n + 3] = __longlong_as_double(best);
         d.result[n + 4] = d.sums[0];
     }
     if (dead) return;

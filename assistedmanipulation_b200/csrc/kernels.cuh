@@ -50,6 +50,7 @@ struct DeviceState {
     unsigned char *kept;   // k_count flags for the warm start
     long long *kept_list;  // keep_best global indices, sorted order
     int world;             // ranks sharing the rollout set
+    int rank;              // this rank (its slot in the argmin part of the sums exchange buffer)
     double *cand;          // this rank's keep_best best (cost, global index bits) pairs — all-gathered when sharded
     double *cand_all;      // world x keep_best pairs
     unsigned long long *minmax_enc;  // [2] order-preserving encodings for atomicMin / atomicMax

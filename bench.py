@@ -220,8 +220,8 @@ def bench_controllers(args, rank, world, local_rank, n_gpus, dist, torch, el):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -241,7 +241,7 @@ def main():
         if rank != 0:
             return 0
         # bounded sample per step: one full update of the same workload at N=1 size per GPU
-        times, T, R, phases = run_oracle(wl, args.steps, args.warmup, host_threads)
+        times, T, R, phases = run_oracle(wl, args.steps, min(args.warmup, 3), host_threads, budget_s=150.0)   # bounded: stops after ~150 s of host work
         value = R * T / times.mean()
         line = {"impl": "reference", "metric": "rollout-steps/s", "value": value, "unit": "rollout-steps/s", "n_gpus": n_gpus, "steps": len(times),
                 "warmup": args.warmup, "ms_per_step": times.mean() * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -200,7 +200,8 @@ int mppi_b200_update_begin(mppi_b200_engine *engine, const double *state, double
                            const void *noise, int32_t noise_source, uint64_t seed);
 int mppi_b200_update_weights(mppi_b200_engine *engine);
 int mppi_b200_update_finish(mppi_b200_engine *engine);
-/* device addresses of the two exchange buffers (FP64): minmax = {-min, max}; sums = {sum w, sum w*eps[nu*T]} */
+/* device addresses of the two exchange buffers (FP64): minmax = {-min, max}; sums = {sum w, sum w*eps[nu*T],
+ * and when sharded one slot per rank: that rank's best global rollout index + 1, or 0} — reduce all `sums_count` values */
 int mppi_b200_reduce_buffers(mppi_b200_engine *engine, void **minmax, size_t *minmax_count, void **sums,
                              size_t *sums_count);
 int mppi_b200_stream(mppi_b200_engine *engine, void **cuda_stream);

@@ -29,13 +29,16 @@ if rank == 0:
 dist.broadcast(uid, 0)
 assert e.lib.mppi_b200_comm_init(e.h, C.c_char_p(bytes(uid.cpu().tolist()))) == 0, e.error()
 x0 = abi.huddled_state()
-Us, kept = [], []
+Us, kept, best = [], [], []
 for u in range(4):
     assert e.update(x0, 0.05 * u, None, seed=5) == 0, e.error()
     Us.append(e.read(abi.READ_OPTIMAL, nu * T))
     kept.append(e.read(abi.READ_KEPT, 20, np.int64))
+    best.append(e.query(abi.QUERY_ARGMIN))
 gathered = [None] * world
 dist.all_gather_object(gathered, Us)
+bests = [None] * world
+dist.all_gather_object(bests, best)
 if rank == 0:
     for other in gathered[1:]:
         for a, b in zip(Us, other):
@@ -47,6 +50,7 @@ if rank == 0:
         Uw = whole.read(abi.READ_OPTIMAL, nu * T)
         assert np.array_equal(kept[u], whole.read(abi.READ_KEPT, 20, np.int64))   # the kept set is bit exact across shardings
         assert np.abs(Us[u] - Uw).max() <= 1e-12 * np.abs(Uw).max()
+        assert all(b[u] == whole.query(abi.QUERY_ARGMIN) for b in bests), (u, bests)   # the best rollout is global on every rank
         assert o.update(x0, 0.05 * u, None, whole.read(abi.READ_NOISE, (K + 2) * T * nu)) == 0
         Uo = o.read(abi.READ_OPTIMAL, nu * T)
         assert np.abs(Us[u] - Uo).max() <= 1e-9 * np.abs(Uo).max()

@@ -90,6 +90,8 @@ def test_two_shards_on_one_gpu(oracle, source):
         cw = whole.read(abi.READ_COSTS, K + 2)
         cs = np.concatenate([e.read(abi.READ_COSTS, 256) for e in shards])
         assert np.allclose(cs, cw, rtol=1e-12, atol=0)                   # U_shift differs by rounding only
+        # the best rollout is global: every rank reports the lowest index of the minimum over ALL shards
+        assert shards[0].query(abi.QUERY_ARGMIN) == shards[1].query(abi.QUERY_ARGMIN) == int(np.argmin(cs))
         nw = whole.read(abi.READ_NOISE, (K + 2) * T * nu).reshape(K + 2, -1)
         ns = np.concatenate([e.read(abi.READ_NOISE, 256 * T * nu).reshape(256, -1) for e in shards])
         assert np.array_equal(ns[2:], nw[2:])                            # the Philox stream does not depend on the sharding
