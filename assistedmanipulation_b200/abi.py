@@ -91,6 +91,20 @@ class ForecastConfig(C.Structure):
 
 FORECAST_LOCF, FORECAST_AVERAGE, FORECAST_KALMAN = 0, 1, 2
 
+
+class DynamicsForecastConfig(C.Structure):
+    """mppi_b200_dynamics_forecast_config (reference DynamicsForecast::Configuration, dynamics.hpp:173-188)."""
+    _fields_ = [("batch", C.c_int32), ("device", C.c_int32), ("time_step", C.c_double), ("horison", C.c_double),
+                ("apply_wrench", C.c_int32), ("reserved", C.c_int32)]
+
+
+DYNAMICS_FORECAST_RECORD = 112
+# slices of one record (include/mppi_b200.h)
+DF_JOINT_POSITION, DF_POSITION, DF_ORIENTATION = slice(0, 12), slice(12, 15), slice(15, 19)
+DF_LINEAR_VELOCITY, DF_ANGULAR_VELOCITY = slice(19, 22), slice(22, 25)
+DF_LINEAR_ACCELERATION, DF_ANGULAR_ACCELERATION = slice(25, 28), slice(28, 31)
+DF_JOINT_POWER, DF_EXTERNAL_POWER, DF_ENERGY, DF_WRENCH, DF_JACOBIAN = 31, 32, 33, slice(34, 40), slice(40, 112)
+
 EXPORTS = [
     "mppi_b200_create", "mppi_b200_destroy", "mppi_b200_last_error", "mppi_b200_update",
     "mppi_b200_update_begin", "mppi_b200_update_weights", "mppi_b200_update_finish",
@@ -102,7 +116,10 @@ EXPORTS = [
     "mppi_b200_update_launch", "mppi_b200_update_wait",
     "mppi_b200_forecast_create", "mppi_b200_forecast_destroy", "mppi_b200_forecast_last_error",
     "mppi_b200_forecast_update", "mppi_b200_forecast_update_time", "mppi_b200_forecast_table",
-    "mppi_b200_forecast_table_device", "mppi_b200_set_wrench_device",
+    "mppi_b200_forecast_table_device", "mppi_b200_set_wrench_device", "mppi_b200_forecast_batch",
+    "mppi_b200_dynamics_forecast_create", "mppi_b200_dynamics_forecast_destroy", "mppi_b200_dynamics_forecast_last_error",
+    "mppi_b200_dynamics_forecast_steps", "mppi_b200_dynamics_forecast_run", "mppi_b200_dynamics_forecast_read",
+    "mppi_b200_dynamics_forecast_device_records",
 ]
 STAGES = ("h2d", "warm_start_shift", "sample", "rollout", "weights", "weighted_sum", "finish", "d2h")
 
@@ -181,6 +198,22 @@ def load_library(path=None):
     lib.mppi_b200_forecast_table_device.restype = C.c_int
     lib.mppi_b200_set_wrench_device.argtypes = [C.c_void_p, C.c_void_p]
     lib.mppi_b200_set_wrench_device.restype = C.c_int
+    lib.mppi_b200_forecast_batch.argtypes = [C.c_void_p]
+    lib.mppi_b200_forecast_batch.restype = C.c_int
+    lib.mppi_b200_dynamics_forecast_create.argtypes = [C.POINTER(DynamicsForecastConfig), C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.mppi_b200_dynamics_forecast_create.restype = C.c_int
+    lib.mppi_b200_dynamics_forecast_destroy.argtypes = [C.c_void_p]
+    lib.mppi_b200_dynamics_forecast_destroy.restype = None
+    lib.mppi_b200_dynamics_forecast_last_error.argtypes = [C.c_void_p]
+    lib.mppi_b200_dynamics_forecast_last_error.restype = C.c_char_p
+    lib.mppi_b200_dynamics_forecast_steps.argtypes = [C.c_void_p]
+    lib.mppi_b200_dynamics_forecast_steps.restype = C.c_int
+    lib.mppi_b200_dynamics_forecast_run.argtypes = [C.c_void_p, _dp, C.c_double]
+    lib.mppi_b200_dynamics_forecast_run.restype = C.c_int
+    lib.mppi_b200_dynamics_forecast_read.argtypes = [C.c_void_p, _dp, C.c_size_t]
+    lib.mppi_b200_dynamics_forecast_read.restype = C.c_int
+    lib.mppi_b200_dynamics_forecast_device_records.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.mppi_b200_dynamics_forecast_device_records.restype = C.c_int
     return lib
 
 

@@ -402,6 +402,8 @@ int mppi_b200_forecast_table_device(mppi_b200_forecast *f, double time, double t
     return MPPI_B200_OK;
 }
 
+int mppi_b200_forecast_batch(const mppi_b200_forecast *f) { return f ? f->s.batch : 0; }
+
 int mppi_b200_forecast_table(mppi_b200_forecast *f, double time, double time_step, int32_t steps, double *table) {
     const double *dev = nullptr;
     if (!table) return MPPI_B200_ERR_INVALID;

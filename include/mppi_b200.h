@@ -301,6 +301,42 @@ int mppi_b200_forecast_table_device(mppi_b200_forecast *forecast, double time, d
  * of the `wrench` argument of mppi_b200_update; NULL restores the host argument. */
 int mppi_b200_set_wrench_device(mppi_b200_engine *engine, const double *device_table);
 
+/* forecasters in the object */
+int mppi_b200_forecast_batch(const mppi_b200_forecast *forecast);
+
+/* ---- Dynamics forecast: FrankaRidgeback::DynamicsForecast::forecast ---------------------------
+ * (src/frankaridgeback/dynamics.{hpp:122-408,cpp:58-138}) for `batch` controllers at once: the Pinocchio-backend
+ * dynamics rolled forward under zero control over ceil(horison / time_step) steps, one record per step taken
+ * BEFORE the step. Record layout (doubles): joint_position[12], end effector position[3], orientation
+ * quaternion x y z w [4], linear_velocity[3], angular_velocity[3], linear_acceleration[3],
+ * angular_acceleration[3], joint_power, external_power, energy, wrench[6], jacobian[6][12] row-major. */
+#define MPPI_B200_DYNAMICS_FORECAST_RECORD 112
+
+typedef struct mppi_b200_dynamics_forecast_config {
+    int32_t batch;
+    int32_t device;
+    double time_step;      /* DynamicsForecast::Configuration::time_step */
+    double horison;        /* DynamicsForecast::Configuration::horison */
+    int32_t apply_wrench;  /* 0 = the reference (add_end_effector_simulated_wrench is empty in the Pinocchio backend,
+                              pinocchio_dynamics.hpp:276); 1 = tau += J_ee^T w, the line left commented out at
+                              pinocchio_dynamics.cpp:240, fed with the forecast wrench */
+    int32_t reserved;
+} mppi_b200_dynamics_forecast_config;
+
+typedef struct mppi_b200_dynamics_forecast mppi_b200_dynamics_forecast;
+
+/* wrench_forecast: the end_effector_wrench_forecast (same batch; not owned; NULL = zero wrench) */
+int mppi_b200_dynamics_forecast_create(const mppi_b200_dynamics_forecast_config *config, mppi_b200_forecast *wrench_forecast,
+                                       mppi_b200_dynamics_forecast **forecast);
+void mppi_b200_dynamics_forecast_destroy(mppi_b200_dynamics_forecast *forecast);
+const char *mppi_b200_dynamics_forecast_last_error(const mppi_b200_dynamics_forecast *forecast);
+int mppi_b200_dynamics_forecast_steps(const mppi_b200_dynamics_forecast *forecast);
+/* DynamicsForecast::forecast(state, time); states: host, batch x 31 */
+int mppi_b200_dynamics_forecast_run(mppi_b200_dynamics_forecast *forecast, const double *states, double time);
+/* records: host, batch x steps x MPPI_B200_DYNAMICS_FORECAST_RECORD doubles */
+int mppi_b200_dynamics_forecast_read(mppi_b200_dynamics_forecast *forecast, double *records, size_t bytes);
+int mppi_b200_dynamics_forecast_device_records(mppi_b200_dynamics_forecast *forecast, const double **records);
+
 /* Host-side Philox4x32-10 + Box–Muller exactly as the sampling kernel evaluates it is NOT
  * provided: the engine's generated noise is read back with MPPI_B200_READ_NOISE instead. */
 

@@ -7,6 +7,7 @@
 
 #include "systems.hpp"
 #include "forecast_oracle.hpp"
+#include "dynamics_forecast_oracle.hpp"
 
 using namespace oracle;
 
@@ -237,5 +238,18 @@ void oracle_forecast_get(void *h, double time, double *out, int n) {
     const std::vector<double> v = static_cast<ForecastOracle *>(h)->forecast(time);
     for (int i = 0; i < n && i < (int)v.size(); i++) out[i] = v[(size_t)i];
 }
+
+// ---- DynamicsForecast::forecast -------------------------------------------------------
+void *oracle_dynamics_forecast_create(double time_step, double horison, void *wrench_forecast, int apply_wrench) {
+    return new DynamicsForecastOracle(time_step, horison, static_cast<ForecastOracle *>(wrench_forecast), apply_wrench != 0);
+}
+void oracle_dynamics_forecast_destroy(void *h) { delete static_cast<DynamicsForecastOracle *>(h); }
+int oracle_dynamics_forecast_steps(void *h) { return (int)static_cast<DynamicsForecastOracle *>(h)->steps; }
+void oracle_dynamics_forecast_run(void *h, const double *state, double time) { static_cast<DynamicsForecastOracle *>(h)->forecast(state, time); }
+void oracle_dynamics_forecast_read(void *h, double *out) {
+    auto *f = static_cast<DynamicsForecastOracle *>(h);
+    std::memcpy(out, f->record.data(), f->record.size() * sizeof(double));
+}
+long oracle_dynamics_forecast_parameterise(void *h, double time) { return static_cast<DynamicsForecastOracle *>(h)->parameterise(time); }
 
 }  // extern "C"
