@@ -262,13 +262,14 @@ public:
     inline std::size_t get_rollout_count() const { return m_rollout_count; }
     inline const auto &get_rolled_out_state() const { return m_rollout_state; }
 
-    inline const VectorXd &get_weights() { refresh(); return m_weights; }
-    inline const MatrixXd &get_gradient() { refresh(); return m_gradient; }
-    inline const std::vector<Rollout> &get_rollouts() { refresh_rollouts(); return m_rollouts; }
-    inline const MatrixXd &get_optimal_rollout() { refresh(); return m_optimal_control; }
-    inline const MatrixXd &trajectory() { refresh(); return m_optimal_control; }
-    inline double get_optimal_total_cost() { double c = 0; mppi_b200_read(m_engine, MPPI_B200_READ_OPTIMAL_COST, &c, sizeof c); return c; }
-    inline const Cost &get_optimal_cost() {
+    // const like the reference's (mppi.hpp:408-431) so loggers taking `const Trajectory &` work; the host copies are caches
+    inline const VectorXd &get_weights() const { refresh(); return m_weights; }
+    inline const MatrixXd &get_gradient() const { refresh(); return m_gradient; }
+    inline const std::vector<Rollout> &get_rollouts() const { refresh_rollouts(); return m_rollouts; }
+    inline const MatrixXd &get_optimal_rollout() const { refresh(); return m_optimal_control; }
+    inline const MatrixXd &trajectory() const { refresh(); return m_optimal_control; }
+    inline double get_optimal_total_cost() const { double c = 0; mppi_b200_read(m_engine, MPPI_B200_READ_OPTIMAL_COST, &c, sizeof c); return c; }
+    inline const Cost &get_optimal_cost() const {
         double bd[8];
         if (mppi_b200_read(m_engine, MPPI_B200_READ_BREAKDOWN, bd, sizeof bd) == MPPI_B200_OK) m_device_cost->set_optimal_breakdown(bd);
         return *m_cost;
@@ -330,7 +331,7 @@ private:
             for (std::size_t c = 0; c < T; c++) (*m_gaussian)(&m_reference_noise[(order[i] * T + c) * nu]);
     }
 
-    void refresh() {
+    void refresh() const {
         if (!m_stale) return;
         const std::size_t n = (std::size_t)m_control_dof * m_step_count;
         mppi_b200_read(m_engine, MPPI_B200_READ_OPTIMAL, m_optimal_control.data(), n * sizeof(double));
@@ -338,7 +339,7 @@ private:
         mppi_b200_read(m_engine, MPPI_B200_READ_WEIGHTS, m_weights.data(), (std::size_t)m_rollout_count * sizeof(double));
         m_stale = false;
     }
-    void refresh_rollouts() {
+    void refresh_rollouts() const {
         const std::size_t n = (std::size_t)m_control_dof * m_step_count;
         if (m_rollouts.empty()) m_rollouts.assign((std::size_t)m_rollout_count, Rollout(m_control_dof, m_step_count));
         std::vector<double> noise((std::size_t)m_rollout_count * n), costs((std::size_t)m_rollout_count);
@@ -362,9 +363,9 @@ private:
     double m_update_last = 0.0, m_update_duration = 0.0;
     std::size_t m_update_count = 0;
     VectorXd m_rollout_state;
-    VectorXd m_weights;
-    MatrixXd m_gradient, m_optimal_control;
-    std::vector<Rollout> m_rollouts;
+    mutable VectorXd m_weights;
+    mutable MatrixXd m_gradient, m_optimal_control;
+    mutable std::vector<Rollout> m_rollouts;
     std::vector<double> m_wrench;
     std::mutex m_optimal_control_mutex;
     const double *m_injected = nullptr;
@@ -375,7 +376,7 @@ private:
     std::int64_t m_keep_best = 0;
     double m_last_shift_time = 0.0;
     std::uint64_t m_seed = 0x5EED0000ull;
-    bool m_stale = true;
+    mutable bool m_stale = true;
 };
 
 }  // namespace mppi

@@ -198,6 +198,7 @@ public:
     double optimal_total_cost() const { return m_optimal_cost; }
     double update_duration() const { return m_update_duration; }
     std::int64_t shift_by() const { return m_shift_by; }
+    std::size_t update_count() const { return m_update_count; }   // mppi.hpp:386-388
     Cost &optimal_cost_object() { return *m_cost[0]; }
     double phase_seconds[4] = {0, 0, 0, 0};  // sample / rollout / optimise / filter
 

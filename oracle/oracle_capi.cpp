@@ -133,6 +133,7 @@ int oracle_query(void *p, int what, int64_t *v) {
         case MPPI_B200_QUERY_ROLLOUT_COUNT: *v = t.rollout_count(); return 0;
         case MPPI_B200_QUERY_LOCAL_BEGIN: *v = 0; return 0;
         case MPPI_B200_QUERY_LOCAL_COUNT: *v = t.rollout_count(); return 0;
+        case MPPI_B200_QUERY_UPDATE_COUNT: *v = (int64_t)t.update_count(); return 0;
         case MPPI_B200_QUERY_ARGMIN: *v = (int64_t)t.m_argmin; return 0;
         case MPPI_B200_QUERY_SHIFT_BY: *v = t.shift_by(); return 0;
         case MPPI_B200_QUERY_STATE_DOF: *v = t.state_dof(); return 0;

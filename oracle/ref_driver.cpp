@@ -9,6 +9,7 @@
 #include <memory>
 
 #include "controller/mppi.hpp"   // the reference's header
+#include "logging/mppi.hpp"      // the reference's CSV logger
 #include "systems.hpp"           // oracle systems
 
 namespace {
@@ -162,5 +163,14 @@ void ref_sg_run(int steps, int window, unsigned order, int updates, const double
         for (int i = 0; i < steps; i++) out[(size_t)n * steps + i] = m(0, i);
     }
 }
+
+// ---- the reference's own CSV logger over its own Trajectory (logging/mppi.cpp, csv.hpp, file.hpp), SURVEY §8f-4 ----
+void *ref_logger_create(const char *folder, unsigned control_dof, size_t rollouts) {
+    logger::MPPI::Configuration c;
+    c.folder = folder; c.state_dof = 0; c.control_dof = control_dof; c.rollouts = rollouts;
+    return logger::MPPI::create(c).release();
+}
+void ref_logger_log(void *lg, void *p) { static_cast<logger::MPPI *>(lg)->log(*static_cast<Handle *>(p)->traj); }
+void ref_logger_destroy(void *lg) { delete static_cast<logger::MPPI *>(lg); }
 
 }  // extern "C"

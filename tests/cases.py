@@ -36,6 +36,15 @@ REF_CASES = {
                                 updates=5, cadence=0.05, wrench=constant_wrench(30), smoothing=(10, 1)),
 }
 
+# small cases whose CSV logs, written by the reference's own logger over its own Trajectory, are committed under
+# tests/golden/ref_logs/ (tools/gen_log_golden.py)
+LOG_CASES = {
+    "toy_k6": dict(system=abi.SYSTEM_TOY, objective=abi.OBJECTIVE_TOY, params=abi.default_toy_objective, K=6, horison=0.05, keep=2, threads=1,
+                   x0=np.array([0.1, -0.2, 0.3, 0.0]), updates=4, cadence=0.02, wrench=None, smoothing=(2, 1)),
+    "franka_trackpoint_k4": dict(system=abi.SYSTEM_FRANKA_RIDGEBACK, objective=abi.OBJECTIVE_TRACK_POINT, params=abi.default_track_point, K=4,
+                                 horison=0.03, keep=1, threads=2, x0=abi.huddled_state(), updates=3, cadence=0.01, wrench=None, smoothing=None),
+}
+
 
 def config_for(case, **over):
     kw = dict(keep_best=case["keep"], threads=case["threads"], smoothing=case["smoothing"])

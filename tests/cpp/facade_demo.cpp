@@ -6,6 +6,7 @@
 #include <fstream>
 #include <vector>
 
+#include "mppi_b200/logging.hpp"
 #include "mppi_b200/systems.hpp"
 
 static const double kPi = 3.14159265358979323846;
@@ -24,7 +25,7 @@ int main(int argc, char **argv) {
     const bool refrng = argc > 10 && std::strcmp(argv[10], "refrng") == 0;
     c.rollouts = K; c.keep_best_rollouts = keep_best; c.time_step = 0.01; c.horison = horison; c.gradient_step = 2.0; c.cost_scale = 10.0; c.cost_discount_factor = 1.0;
     c.control_bound = true; c.threads = 1;
-    if (smoothing) c.smoothing = mppi::Configuration::Smoothing{10, 1};
+    if (smoothing) c.smoothing = mppi::Configuration::Smoothing{(unsigned)(std::getenv("MPPI_B200_DEMO_SG_WINDOW") ? std::atoi(std::getenv("MPPI_B200_DEMO_SG_WINDOW")) : 10), 1};
     std::unique_ptr<mppi::Dynamics> dyn; std::unique_ptr<mppi::Cost> cost;
     VectorXd x0;
     if (which == "toy") {
@@ -80,6 +81,14 @@ int main(int argc, char **argv) {
         if (!f) return 4;
     }
     std::ofstream out(argv[6], std::ios::binary);
+    // the reference's CSV logger (logging/mppi.cpp) over the device trajectory, as BaseTest does (test/case/base.cpp:52-63)
+    std::unique_ptr<logger::MPPI> mppi_logger;
+    if (const char *folder = std::getenv("MPPI_B200_DEMO_LOG")) {
+        logger::MPPI::Configuration lc;
+        lc.folder = folder; lc.state_dof = trajectory->get_state_dof(); lc.control_dof = trajectory->get_control_dof(); lc.rollouts = trajectory->get_rollout_count();
+        mppi_logger = logger::MPPI::create(lc);
+        if (!mppi_logger) return 5;
+    }
     for (int u = 0; u < updates; u++) {
         if (!noise.empty()) trajectory->set_injected_noise(noise.data() + (std::size_t)u * R * T * nu);
         trajectory->update(x0, cadence * u);
@@ -91,7 +100,9 @@ int main(int argc, char **argv) {
         out.write(reinterpret_cast<const char *>(&oc), 8);
         const auto &w = trajectory->get_weights();
         out.write(reinterpret_cast<const char *>(w.data()), (std::streamsize)(R * 8));
+        if (mppi_logger) { mppi_logger->log(*trajectory); mppi_logger->log(*trajectory); }   // the second call writes nothing
     }
+    mppi_logger.reset();
     if (which == "assisted" || which == "assisted_locf") {
         const auto &am = dynamic_cast<const FrankaRidgeback::AssistedManipulation &>(trajectory->get_optimal_cost());
         std::printf("breakdown %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", am.get_joint_limit_cost(), am.get_self_collision_cost(), am.get_workspace_cost(),

@@ -70,7 +70,7 @@ def test_missing_library_fails_loudly(tmp_path):
 def build_facade_demo(name="facade_demo"):
     exe = os.path.join(ol.ROOT, "tests", "cpp", name)
     src = exe + ".cpp"
-    hdrs = [os.path.join(ol.ROOT, "assistedmanipulation_b200", "cpp", "mppi_b200", f) for f in ("trajectory.hpp", "systems.hpp", "linalg.hpp", "forecast.hpp")] + [HEADER]
+    hdrs = [os.path.join(ol.ROOT, "assistedmanipulation_b200", "cpp", "mppi_b200", f) for f in ("trajectory.hpp", "systems.hpp", "linalg.hpp", "forecast.hpp", "logging.hpp")] + [HEADER]
     if not os.path.exists(exe) or any(os.path.getmtime(f) > os.path.getmtime(exe) for f in [src] + hdrs):
         subprocess.check_call(["g++", "-std=c++20", "-O2", "-Wall", "-Werror", "-DMPPI_B200_NO_EIGEN", "-I" + os.path.join(ol.ROOT, "include"),
                                "-I" + os.path.join(ol.ROOT, "assistedmanipulation_b200", "cpp"), src, "-L" + os.path.dirname(abi.library_path()), "-lmppi_b200",

@@ -82,3 +82,37 @@ def test_reference_rng_mode_reproduces_the_reference_build(golden, tmp_path, nam
         assert np.allclose(rec[u, nu * T:nu * T + nu], get_ref[u], rtol=1e-9, atol=1e-9 * scale)
         assert abs(rec[u, nu * T + nu] - oc_ref[u, 0]) <= 1e-8 * abs(oc_ref[u, 0])
         assert np.allclose(rec[u, nu * T + nu + 1:], w_ref[u], rtol=1e-8, atol=1e-14)
+
+
+LOG_ARGS = {
+    # case -> (which, K, horison, updates, keep, smoothing, cadence, x0 args, SG window)
+    "toy_k6": ("toy", 6, 0.05, 4, 2, 1, 0.02, ["0.1", "-0.2", "0.3", "0.0"], 2),
+    "franka_trackpoint_k4": ("track", 4, 0.03, 3, 1, 0, 0.01, ["100.0"], 10),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LOG_ARGS))
+def test_cpp_logger_writes_the_reference_files(tmp_path, name):
+    """SURVEY §8f-4: logger::MPPI of the facade (cpp/mppi_b200/logging.hpp) over the device trajectory in
+    reference-RNG mode against the files the reference's own logger wrote for its own Trajectory
+    (tests/golden/ref_logs): same files, same headers, same row keys; values to the 6 printed digits."""
+    from assistedmanipulation_b200 import formats
+    exe = build_facade_demo()
+    which, K, horison, updates, keep, smoothing, cadence, extra, window = LOG_ARGS[name]
+    folder = tmp_path / "logs"
+    env = dict(os.environ, MPPI_B200_DEMO_LOG=str(folder), MPPI_B200_DEMO_SG_WINDOW=str(window))
+    r = subprocess.run([exe, which, str(K), str(horison), str(updates), "-", str(tmp_path / "out.bin"), str(keep), str(smoothing), str(cadence), "refrng"] + extra,
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    golden = os.path.join(ol.ROOT, "tests", "golden", "ref_logs", name)
+    assert sorted(os.listdir(folder)) == sorted(os.listdir(golden))
+    identical = 0
+    for f in sorted(os.listdir(golden)):
+        got_text, want_text = open(folder / f).read(), open(os.path.join(golden, f)).read()
+        assert got_text.splitlines()[0] == want_text.splitlines()[0]          # header, byte for byte
+        (_, got), (_, want) = formats.read_csv(str(folder / f)), formats.read_csv(os.path.join(golden, f))
+        assert got.shape == want.shape, f
+        cols = slice(0, 2) if f == "update.csv" else slice(None)                # the third column of update.csv is a duration
+        np.testing.assert_allclose(got[:, cols], want[:, cols], rtol=2e-5, atol=1e-9, err_msg=f)
+        identical += got_text == want_text
+    assert identical >= 3, identical   # most files agree to the last printed digit
