@@ -313,7 +313,7 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     A(d.kept, (size_t)d.k_count); A(d.kept_list, (size_t)std::max<long long>(d.keep_best, 1));
     d.world = c->world_size; d.rank = c->rank;
     A(d.cand, (size_t)2 * std::max<long long>(d.keep_best, 1)); A(d.cand_all, (size_t)2 * std::max<long long>(d.keep_best, 1) * c->world_size);
-    A(d.minmax_enc, 2); A(d.valid_count, 1); A(d.argmin, 1); A(d.minmax, 4); A(d.sums, 1 + n + (size_t)c->world_size);
+    A(d.minmax_enc, 2); A(d.valid_count, 1); A(d.argmin, 1); A(d.finish_count, 1); A(d.minmax, 4); A(d.sums, 1 + n + (size_t)c->world_size);
     d.weight_blocks = (int)((d.k_count + 255) / 256);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);

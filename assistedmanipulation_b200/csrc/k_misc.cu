@@ -422,6 +422,48 @@ __device__ __forceinline__ int sg_lower_bound(const double *tt, int len, double 
     return first;
 }
 
+// The recurrent part of the Savitzky-Golay application in registers (transposed form): when res_i is known it is
+// added, with its tap, to the NR = w-1 accumulators of the applications that will read it; every step is NR
+// independent FMAs and the chain from res_i to res_{i+1} is a single FMA.
+template <int NR> __device__ __forceinline__ void sg_recurrence(const double *F, const double *sw, int T, double *u, int w, double *sU) {
+    double c[NR], acc[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++) { c[j] = sw[j]; acc[j] = j < T ? F[j] : 0.0; }
+    for (int i = 0; i < T; i++) {
+        const double res = acc[0];
+        u[w + i - 1] = res; sU[i] = res;
+        const double next = i + NR < T ? F[i + NR] : 0.0;
+#pragma unroll
+        for (int m = 1; m < NR; m++) acc[m - 1] = fma(c[NR - m], res, acc[m]);
+        acc[NR - 1] = fma(c[0], res, next);
+    }
+}
+__device__ __forceinline__ bool sg_recurrence_dispatch(int nr, const double *F, const double *sw, int T, double *u, int w, double *sU) {
+    switch (nr) {
+        case 1: sg_recurrence<1>(F, sw, T, u, w, sU); return true;
+        case 2: sg_recurrence<2>(F, sw, T, u, w, sU); return true;
+        case 3: sg_recurrence<3>(F, sw, T, u, w, sU); return true;
+        case 4: sg_recurrence<4>(F, sw, T, u, w, sU); return true;
+        case 5: sg_recurrence<5>(F, sw, T, u, w, sU); return true;
+        case 7: sg_recurrence<7>(F, sw, T, u, w, sU); return true;
+        case 9: sg_recurrence<9>(F, sw, T, u, w, sU); return true;    // the default window of 10
+        case 14: sg_recurrence<14>(F, sw, T, u, w, sU); return true;
+        case 19: sg_recurrence<19>(F, sw, T, u, w, sU); return true;
+        default: return false;
+    }
+}
+
+__device__ __forceinline__ void finish_publish_stats(const DeviceState &d, int n) {
+    d.result[n + 0] = d.minmax[0]; d.result[n + 1] = d.minmax[1]; d.result[n + 2] = d.minmax[2];
+    long long best = *d.argmin;
+    if (d.world > 1) {   // lowest global index among the ranks that hold the global minimum (mppi.cpp:363-366 order)
+        best = 0x7fffffffffffffffll;
+        for (int r = 0; r < d.world; r++) { const double v = d.sums[1 + n + r]; if (v > 0.0 && (long long)v - 1 < best) best = (long long)v - 1; }
+    }
+    d.result[n + 3] = __longlong_as_double(best);
+    d.result[n + 4] = d.sums[0];
+}
+
 __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DeviceState dg) {
     const DeviceState d = controller_view(dg, blockIdx.y);
     // One BLOCK per control channel (channels are independent, mppi.cpp:424-447): the elementwise work runs over the
@@ -434,17 +476,10 @@ __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DeviceSt
     const int n = d.nu * d.T, ch = blockIdx.x;
     const int skip = *d.skip;
     const bool dead = !(d.minmax[2] >= 2.0);  // "all nan rollouts" (mppi.cpp:368-370): the reference throws before publishing
-    if (ch == 0 && threadIdx.x == 0) {
-        d.result[n + 0] = d.minmax[0]; d.result[n + 1] = d.minmax[1]; d.result[n + 2] = d.minmax[2];
-        long long best = *d.argmin;
-        if (d.world > 1) {   // lowest global index among the ranks that hold the global minimum (mppi.cpp:363-366 order)
-            best = 0x7fffffffffffffffll;
-            for (int r = 0; r < d.world; r++) { const double v = d.sums[1 + n + r]; if (v > 0.0 && (long long)v - 1 < best) best = (long long)v - 1; }
-        }
-        d.result[n + 3] = __longlong_as_double(best);
-        d.result[n + 4] = d.sums[0];
+    if (dead) {   // nothing is published but the statistics
+        if (ch == 0 && threadIdx.x == 0) finish_publish_stats(d, n);
+        return;
     }
-    if (dead) return;
     const double total = d.sums[0];
     for (int t = threadIdx.x; t < d.T; t += blockDim.x) {
         const int e = t * d.nu + ch;
@@ -495,7 +530,36 @@ __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DeviceSt
                 tm[w + i] = __dadd_rn(t0, __dmul_rn((double)k, d.dt));
             }
             __syncwarp();
-            // apply x T (filter.cpp:163-173): the filtered value is written ONE SLOT EARLIER than the sample
+            // apply x T (filter.cpp:163-173): the filtered value is written ONE SLOT EARLIER than the sample, so
+            // application i reads what applications i-w+1 .. i-1 wrote (slots i .. i+w-2 of its 2w+1 taps) and
+            // untouched samples beyond: an order-(w-1) recurrence plus a feed-forward part.
+            // Fast path (every lookup lands on its own sample, idx_i = w + i — always, unless the window holds
+            // duplicate times): the feed-forward part F_i = sum_{j>=w-1} sw[j] u[i+j] is evaluated for all i by
+            // the lanes at once from the untouched window; lane 0 then runs the short recurrence in place.
+            bool regular = true;
+            for (int i = lane; i < d.T; i += 32) {
+                const double t = __dadd_rn(t0, __dmul_rn((double)i, d.dt));
+                if (!(tm[w + i] >= t && tm[w + i - 1] < t)) regular = false;
+            }
+            regular = __all_sync(0xffffffffu, regular) && w >= 1;
+            if (regular) {
+                double *F = sw + ntaps;   // T feed-forward sums
+                for (int i = lane; i < d.T; i += 32) {
+                    double acc = 0.0;
+                    for (int j = w - 1; j < ntaps; j++) acc = fma(sw[j], u[i + j], acc);
+                    for (int j = 0; j < w - 1 - i; j++) acc = fma(sw[j], u[i + j], acc);   // history left of the first written slot
+                    F[i] = acc;
+                }
+                __syncwarp();
+                if (lane == 0 && !sg_recurrence_dispatch(w - 1, F, sw, d.T, u, w, sU)) {
+                    for (int i = 0; i < d.T; i++) {   // any other window: the same recurrence through shared memory
+                        double acc = F[i];
+                        for (int j = (w - 1 - i > 0 ? w - 1 - i : 0); j < w - 1; j++) acc = fma(sw[j], u[i + j], acc);
+                        u[w + i - 1] = acc; sU[i] = acc;
+                    }
+                }
+                __syncwarp();
+            } else {
             const double my_w0 = lane < ntaps ? sw[lane] : 0.0;
             for (int i = 0; i < d.T; i++) {
                 const double t = __dadd_rn(t0, __dmul_rn((double)i, d.dt));
@@ -510,6 +574,7 @@ __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DeviceSt
                 __syncwarp();
                 if (lane == 0) { u[idx - 1] = res; sU[i] = res; }
                 __syncwarp();
+            }
             }
         }
         __syncthreads();
@@ -527,7 +592,21 @@ __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DeviceSt
         d.U_shift[e] = v;
         d.U[e] = v;        // publication: m_optimal_control = m_optimal_control_shifted (mppi.cpp:178-182)
         d.U_snap[e] = v;   // input of the optimal re-rollout (side stream)
-        d.result[e] = v;   // host-mapped copy, visible to the caller when the stream completes
+    }
+    // Publication to the host-mapped block: the LAST channel block to get here copies the whole sequence with
+    // 16-byte stores in address order (full PCIe write segments) instead of nu x T strided 8-byte stores.
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(d.finish_count, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        const double2 *src = reinterpret_cast<const double2 *>(d.U);
+        double2 *dst = reinterpret_cast<double2 *>(d.result);
+        for (int i = threadIdx.x; i < n / 2; i += blockDim.x) dst[i] = __ldcg(src + i);
+        if ((n & 1) && threadIdx.x == 0) d.result[n - 1] = __ldcg(d.U + n - 1);
+        if (threadIdx.x == 0) { finish_publish_stats(d, n); *d.finish_count = 0; }
     }
 }
 
@@ -643,7 +722,7 @@ cudaError_t launch_gradient(const DeviceState &d, int precision, cudaStream_t s,
 }
 
 cudaError_t launch_finish(const DeviceState &d, cudaStream_t s) {
-    const size_t smem = sizeof(double) * ((size_t)d.T + 2 * (size_t)d.sg_len + 2 * (size_t)d.sg_window + 1);
+    const size_t smem = sizeof(double) * (2 * (size_t)d.T + 2 * (size_t)d.sg_len + 2 * (size_t)d.sg_window + 1);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

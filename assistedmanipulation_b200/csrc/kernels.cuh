@@ -56,6 +56,7 @@ struct DeviceState {
     unsigned long long *minmax_enc;  // [2] order-preserving encodings for atomicMin / atomicMax
     int *valid_count;      // number of non-NaN local rollouts
     long long *argmin;     // global index of the best rollout
+    int *finish_count;     // channel blocks of k_finish that are done (the last one publishes)
     double *minmax;        // exchange buffer {-min, max, valid(<=2)}
     double *sums;          // exchange buffer {sum w, sum w*eps [nu*T]}
     double *wsum_partial;  // per block of the weights kernel
@@ -101,7 +102,7 @@ __device__ __forceinline__ DeviceState controller_view(const DeviceState &g, int
     if (g.injected) d.injected = static_cast<const unsigned char *>(g.injected) + (size_t)c * K * n * (g.injected_is_double ? 8 : g.elem_bytes);
     d.costs = g.costs + c * K; d.weights = g.weights + c * K; d.kept = g.kept + c * K;
     d.kept_list = g.kept_list + c * keep;
-    d.minmax_enc = g.minmax_enc + 2 * c; d.valid_count = g.valid_count + c; d.argmin = g.argmin + c;
+    d.minmax_enc = g.minmax_enc + 2 * c; d.valid_count = g.valid_count + c; d.argmin = g.argmin + c; d.finish_count = g.finish_count + c;
     d.minmax = g.minmax + 4 * c; d.sums = g.sums + c * (1 + n);
     d.wsum_partial = g.wsum_partial + (size_t)c * g.weight_blocks; d.grad_partial = g.grad_partial + (size_t)c * g.grad_blocks * n;
     d.skip = g.skip + c;
