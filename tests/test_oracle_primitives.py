@@ -133,3 +133,42 @@ def test_op_count_per_rollout_step(oracle):
     cnt = (C.c_uint64 * 6)()
     n = oracle.oracle_count_step_flops(abi.OBJECTIVE_TRACK_POINT, C.cast(C.byref(tp), C.c_void_p), cnt)
     assert 15000 < n < 30000 and sum(cnt[:5]) == n
+
+
+# ---- cross-check against a derivation that shares no formulation with the oracle (tests/independent_dynamics.py) ----
+
+def test_mass_matrix_against_textbook_jacobian_form(oracle):
+    import independent_dynamics as ind
+    rng = np.random.default_rng(5)
+    for _ in range(6):
+        q = rng.uniform(-1.5, 1.5, 12)
+        M = np.zeros(144)
+        oracle.oracle_robot_crba(ol.ptr(q), ol.ptr(M))
+        Mi, _ = ind.mass_matrix_and_potential(q)
+        assert np.abs(M.reshape(12, 12) - Mi).max() <= 1e-11 * np.abs(Mi).max()
+        assert np.allclose(fk(oracle, q)[0], ind.end_effector_position(q), atol=1e-13)
+
+
+def test_nonlinear_effects_against_the_lagrangian(oracle):
+    """RNEA's Coriolis/centrifugal + gravity vector equals Mdot v - 1/2 d(v^T M v)/dq + dU/dq of the textbook M, U."""
+    import independent_dynamics as ind
+    rng = np.random.default_rng(6)
+    for _ in range(4):
+        q, v = rng.uniform(-1.5, 1.5, 12), rng.uniform(-2, 2, 12)
+        nle = np.zeros(12)
+        oracle.oracle_robot_nle(ol.ptr(q), ol.ptr(v), ol.ptr(nle))
+        want = ind.nonlinear_effects(q, v)
+        assert np.abs(nle - want).max() <= 2e-7 * max(1.0, np.abs(want).max()), (nle, want)
+
+
+def test_forward_dynamics_against_the_lagrangian(oracle):
+    """ABA(q, v, tau) = M^-1 (tau - C v - g) with M, C, g from the independent derivation."""
+    import independent_dynamics as ind
+    rng = np.random.default_rng(7)
+    for _ in range(3):
+        q, v, tau = rng.uniform(-1.5, 1.5, 12), rng.uniform(-1, 1, 12), rng.uniform(-10, 10, 12)
+        a = np.zeros(12)
+        oracle.oracle_robot_aba(ol.ptr(q), ol.ptr(v), ol.ptr(tau), ol.ptr(a))
+        M, _ = ind.mass_matrix_and_potential(q)
+        want = np.linalg.solve(M, tau - ind.nonlinear_effects(q, v))
+        assert np.abs(a - want).max() <= 1e-6 * max(1.0, np.abs(want).max()), (a, want)
