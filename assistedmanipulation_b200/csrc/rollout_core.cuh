@@ -17,15 +17,22 @@ template <class R> struct QuadP { R c0, c1, c2; };
 
 // cost.hpp:25-31
 template <class R> MPPI_HD R quadratic(const QuadP<R> &c, R v) { return c.c0 + c.c1 * fabs_(v) + c.c2 * v * v; }
-// cost.hpp:57-62
+// cost.hpp:57-62 and :88-93. Same value in every case as the reference's two-branch form; written as a select so a warp
+// whose rollouts sit on both sides of a bound does not run both paths one after the other, and with the division
+// skipped for a zero scale (a uniform test: the parameters are constants) — 0 / x is 0 for every x the branch admits.
 template <class R> MPPI_HD R right_barrier(const BarrierP<R> &b, R v) {
-    if (v >= b.bound) { const R d = v - b.bound; return b.maxc + b.scale * (d * d); }
-    return std_min(b.scale / (b.bound - v), b.maxc);
+    const R d = v - b.bound;
+    const R outside = b.maxc + b.scale * (d * d);
+    if (b.scale == R(0)) return (v >= b.bound) ? outside : ((v != v) ? v : std_min(R(0), b.maxc));
+    const R inside = std_min(b.scale / (b.bound - v), b.maxc);
+    return (v >= b.bound) ? outside : inside;
 }
-// cost.hpp:88-93
 template <class R> MPPI_HD R left_barrier(const BarrierP<R> &b, R v) {
-    if (v <= b.bound) { const R d = b.bound - v; return b.maxc + b.scale * (d * d); }
-    return std_min(b.scale / (v - b.bound), b.maxc);
+    const R d = b.bound - v;
+    const R outside = b.maxc + b.scale * (d * d);
+    if (b.scale == R(0)) return (v <= b.bound) ? outside : ((v != v) ? v : std_min(R(0), b.maxc));
+    const R inside = std_min(b.scale / (v - b.bound), b.maxc);
+    return (v <= b.bound) ? outside : inside;
 }
 
 // ---- objective parameter blocks in kernel arithmetic -----------------------------------------
