@@ -6,6 +6,7 @@
 // After the horizon the block folds its costs into the running min / max (warp shuffles, then one
 // order-preserving atomicMin / atomicMax per block) so no separate reduction pass is needed.
 #pragma once
+#include <cstdlib>
 #include "kernels.cuh"
 
 namespace mppi_b200 {
@@ -23,8 +24,14 @@ __device__ __forceinline__ double decode_ordered(unsigned long long e) {
     return __longlong_as_double((long long)b);
 }
 
-template <class R, int VAR, bool FAITHFUL, class ParamsT>
-__global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ DeviceState d, const __grid_constant__ ParamsT P, int optimal_only) {
+// Two builds of the lean reach-to-pose variant, chosen by the launcher (measured on B200, FP64, update time):
+//   BIG = false  one loop body for the seven arm joints, 168-register cap       K = 4096: 368 us   16384: 562   131072: 2260
+//   BIG = true   arm joints unrolled, per-joint results in registers (255)      K = 4096: 398 us   16384: 461   131072: 2075
+// (FP32: 297 / 330 / 1572 against 386 / 417 / 1577; the crossover sits near K = 12 k in FP64 and 24 k in FP32.)
+// Few rollouts = one warp per SM, which lives on a small instruction footprint; many = fewer instructions win even at
+// two blocks per SM.
+template <class R, int VAR, bool FAITHFUL, class ParamsT, bool BIG = false>
+__global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG) ? 3 : 1) k_rollout(const __grid_constant__ DeviceState d, const __grid_constant__ ParamsT P, int optimal_only) {
     // blockIdx.y = controller of a batched engine. Only the handful of buffers this kernel touches are offset
     // by hand (a full controller_view copy of the state costs ~40 registers here, i.e. a resident warp per SM).
     const size_t c = blockIdx.y;
@@ -54,7 +61,7 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ DeviceS
             RolloutInputs<R> in;
             in.x0 = sx; in.U = sU; in.W = has_w ? sW : nullptr; in.T = d.T; in.dt = (R)d.dt; in.discount = d.discount;
             double bd[7] = {0, 0, 0, 0, 0, 0, 0};
-            cost = rollout_franka<R, VAR, FAITHFUL>(MPPI_DEVICE_MODEL, MPPI_DEVICE_FAST_MODEL, P, in, eps, optimal_only ? bd : nullptr);
+            cost = rollout_franka<R, VAR, FAITHFUL, ParamsT, BIG>(MPPI_DEVICE_MODEL, MPPI_DEVICE_FAST_MODEL, P, in, eps, optimal_only ? bd : nullptr);
             if (optimal_only) {
                 for (int i = 0; i < 7; i++) d.breakdown[8 * c + i] = bd[i];
                 d.breakdown[8 * c + 7] = cost;
@@ -90,7 +97,11 @@ cudaError_t launch_rollout_t(const DeviceState &d, const void *params, bool opti
     long long grid = optimal_only ? 1 : (d.k_count + block - 1) / block;
     if (optimal_only) block = 32;
     size_t smem = sizeof(R) * ((size_t)d.nu * d.T + 6 * (size_t)d.T + 32);
-    auto kern = k_rollout<R, VAR, FAITHFUL, ParamsT>;
+    auto kern = k_rollout<R, VAR, FAITHFUL, ParamsT, false>;
+    if constexpr (VAR == VAR_TP_LEAN && !FAITHFUL) {
+        static const long long big_from = std::getenv("MPPI_B200_BIG_FROM") ? std::atoll(std::getenv("MPPI_B200_BIG_FROM")) : (sizeof(R) == 8 ? 12288 : 24576);   // measured crossovers
+        if (!optimal_only && d.k_count * (long long)d.batch >= big_from) kern = k_rollout<R, VAR, FAITHFUL, ParamsT, true>;
+    }
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -19,6 +19,9 @@ template <class R> inline ToyP<R> convert(const mppi_b200_toy_objective &p) {
 template <class R> inline TrackPointP<R> convert(const mppi_b200_track_point &p) {
     TrackPointP<R> o;
     for (int i = 0; i < 3; i++) o.point[i] = (R)p.point[i];
+    static const double lo[10] = {-2.0, -2.0, -6.28, -2.8973, -1.7628, -2.8973, -3.0718, -2.8973, -0.0175, -2.8973};   // track_point.cpp:48-65
+    static const double hi[10] = {2.0, 2.0, 6.28, 2.8973, 1.7628, 2.8973, 0.0698, 2.8973, 3.7525, 2.8973};
+    for (int i = 0; i < 10; i++) { o.lim_lo[i] = (R)lo[i]; o.lim_hi[i] = (R)hi[i]; }
     o.joint_limits = p.enable_joint_limits; o.self_collision = p.enable_self_collision_avoidance; o.reach = p.enable_reach_limits;
     o.link_mode = p.link_position_mode;
     o.collision_limit = cvt<R>(p.self_collision_limit);

@@ -40,6 +40,7 @@ template <class R> struct ToyP { R target[2]; R qp, qv, qu; };
 
 template <class R> struct TrackPointP {
     R point[3];
+    R lim_lo[10], lim_hi[10];   // track_point.cpp:48-65 (hard-coded there); here in the parameter block so they are constant-bank operands
     int joint_limits, self_collision, reach, link_mode;
     BarrierP<R> collision_limit;
     R radii[20];  // sum of the two sphere radii per checked pair
@@ -110,21 +111,22 @@ template <class R, int FLAGS> MPPI_HD void robot_kinematics(const RobotModel<R> 
 }
 
 // objective/track_point.cpp:10-79,120-174
-template <class R> MPPI_HD R track_point_cost(const TrackPointP<R> &P, const R *q, const Kinematics<R> &K) {
+// LEAN: the engine picked the variant without self-collision and reach terms, so they are compiled out
+template <class R, bool LEAN = false> MPPI_HD R track_point_cost(const TrackPointP<R> &P, const R *q, const Kinematics<R> &K) {
     const Vec3<R> e = K.ee_pos - v3<R>(P.point[0], P.point[1], P.point[2]);
-    const R distance = sqrt_(dot(e, e));
-    R cost = R(100) * (distance * distance);
+    // 100 * |e|^2: the reference squares the norm it took the root of (track_point.cpp:38-41); the root is skipped here
+    // (one rounding less, 1e-16 relative)
+    R cost = R(100) * dot(e, e);
     if (P.joint_limits) {
-        const R lo[10] = {R(-2.0), R(-2.0), R(-6.28), R(-2.8973), R(-1.7628), R(-2.8973), R(-3.0718), R(-2.8973), R(-0.0175), R(-2.8973)};
-        const R hi[10] = {R(2.0), R(2.0), R(6.28), R(2.8973), R(1.7628), R(2.8973), R(0.0698), R(2.8973), R(3.7525), R(2.8973)};
         R c = R(0);
 #pragma unroll
         for (int i = 0; i < 10; i++) {
-            if (q[i] < lo[i]) { const R d = lo[i] - q[i]; c += R(1000) + R(100000) * (d * d); }
-            if (q[i] > hi[i]) { const R d = q[i] - hi[i]; c += R(1000) + R(100000) * (d * d); }
+            if (q[i] < P.lim_lo[i]) { const R d = P.lim_lo[i] - q[i]; c += R(1000) + R(100000) * (d * d); }
+            if (q[i] > P.lim_hi[i]) { const R d = q[i] - P.lim_hi[i]; c += R(1000) + R(100000) * (d * d); }
         }
         cost += c;
     }
+    if constexpr (LEAN) return cost;
     if (P.self_collision) cost += self_collision_cost<R, true>(P.collision_limit, P.radii, P.link_mode, K);
     if (P.reach) {
         R sy, cy;
@@ -242,7 +244,8 @@ template <class R> struct RolloutInputs {
 
 // VAR selects objective + which kinematics are alive; FAITHFUL selects the dynamics evaluation.
 // eps: this rollout's noise, [t][d]. Returns the rollout cost (NaN = failed rollout, mppi.cpp:331-334).
-template <class R, int VAR, bool FAITHFUL, class ParamsT>
+// BIG: the build for rollout sets that fill the machine (see k_rollout.cuh)
+template <class R, int VAR, bool FAITHFUL, class ParamsT, bool BIG = false>
 MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, const ParamsT &P, const RolloutInputs<R> &in, const R *eps, double *bd) {
     constexpr int KF = VariantTraits<VAR>::kin;
     constexpr bool POWER = VariantTraits<VAR>::power;
@@ -254,8 +257,7 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
     Kinematics<R> K;
     R cs[NJ], sn[NJ];
     if constexpr (LEAN) {
-#pragma unroll
-        for (int i = 2; i < 10; i++) sincos_(q[i], &sn[i], &cs[i]);
+        joint_sincos<R>(F, q, cs, sn);
         K.ee_pos = ee_position_fast<R>(F, q, cs, sn);
     } else {
         robot_kinematics<R, KF>(M, q, qd, K);
@@ -269,7 +271,8 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
         for (int d = 0; d < NJ; d++) u[d] = in.U[step * NJ + d] + e_next[d];
         if (step + 1 < in.T) load_eps(eps + (step + 1) * NJ, e_next);  // next step's noise is in flight during this step
         R c;
-        if constexpr (VAR == VAR_TP_LEAN || VAR == VAR_TP_FULL) c = track_point_cost<R>(P, q, K);
+        if constexpr (VAR == VAR_TP_LEAN) c = track_point_cost<R, true>(P, q, K);
+        else if constexpr (VAR == VAR_TP_FULL) c = track_point_cost<R>(P, q, K);
         else c = assisted_cost<R>(P, q, qd, energy, K, in.W ? in.W + step * 6 : nullptr, bd);
         const double sc = discount_pow(in.discount, step) * (double)c;
         if (sc != sc) return sc;  // NaN
@@ -288,16 +291,14 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
             robot_calculate<R, true, POWER, KF>(M, q, qd, tau, qdd, nle, K);
         } else {
             // FUSED: qdd = M(q)^-1 tau through the structure-exploiting solver; joint sines / cosines are shared
-            if (!(LEAN && step == 0)) {
-#pragma unroll
-                for (int i = 2; i < 10; i++) sincos_(q[i], &sn[i], &cs[i]);
-            }
+            if (!(LEAN && step == 0)) joint_sincos<R>(F, q, cs, sn);
             qd[0] = cs[2] * u[0] - sn[2] * u[1];
             qd[1] = sn[2] * u[0] + cs[2] * u[1];
             qd[2] = u[2];
+            // (carrying the end effector point inside the inertia loop was tried: +4 registers, spills, 4 % slower)
             if constexpr (LEAN) K.ee_pos = ee_position_fast<R>(F, q, cs, sn);
             else robot_calculate<R, false, POWER, KF, false>(M, q, qd, tau, qdd, nle, K);
-            aba_fused_fast<R>(F, q, cs, sn, tau, qdd);
+            aba_fused_fast<R, BIG ? 7 : kArmUnroll>(F, q, cs, sn, tau, qdd);
         }
 #pragma unroll
         for (int i = 0; i < NJ; i++) qd[i] += qdd[i] * in.dt;
