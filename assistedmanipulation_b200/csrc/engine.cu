@@ -406,7 +406,6 @@ int enqueue_begin(mppi_b200_engine *e, const void *noise, int32_t noise_source) 
             CUDA_TRY(e, launch_merge_kept(d, e->stream)); launches++;
         }
     }
-    CUDA_TRY(e, launch_prepare(d, prec, e->stream)); launches++;
     STAGE(e, 2);
     CUDA_TRY(e, launch_sample(d, prec, e->stream, &launches));
     STAGE(e, 3);

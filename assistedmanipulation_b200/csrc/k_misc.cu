@@ -53,21 +53,19 @@ __device__ __forceinline__ void box_muller(unsigned a, unsigned b, float *z0, fl
 
 // ---- prepare: time shift of the optimal control, rollout 1 = -U_prev, reset of the reductions -------
 // mppi.cpp:194-206 (shift), :269 (rollout[1].noise = -m_optimal_control, the UNSHIFTED optimum).
-template <class R> __global__ void k_prepare(const __grid_constant__ DeviceState dg) {
-    const DeviceState d = controller_view(dg, blockIdx.y);
+// Runs as the extra last block of k_sample: nothing here is read by the sampling blocks (the two static rollouts
+// are produced by the sampling blocks themselves), so one launch and one dependency level less per update.
+__device__ __forceinline__ void prepare_block(const DeviceState &d) {
     const int n = d.nu * d.T;
     const long long shift = d.frame->shift_by;
     for (int i = threadIdx.x; i < d.frame_doubles; i += blockDim.x) d.frame_snap[i] = reinterpret_cast<const double *>(d.frame)[i];
-    for (int e = threadIdx.x; e < n; e += blockDim.x) {
-        if (shift > 0) {
+    if (shift > 0) {
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
             const int t = e / d.nu, dd = e - t * d.nu;
             const long long shifted = d.T - shift;  // columns that survive
             const int src_t = (t < shifted) ? (int)(t + shift) : d.T - 1;
             d.U_shift[e] = d.U[src_t * d.nu + dd];
         }
-        // global rollout 1 lives on the engine whose range contains it
-        if (d.k_begin <= 1 && 1 < d.k_begin + d.k_count) static_cast<R *>(d.noise)[(size_t)(1 - d.k_begin) * n + e] = (R)(-d.U[e]);
-        if (d.k_begin == 0) static_cast<R *>(d.noise)[e] = R(0);  // rollout 0: zero noise, always
     }
     if (threadIdx.x == 0) {
         d.minmax_enc[0] = 0xffffffffffffffffull;
@@ -205,6 +203,7 @@ template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *tile = reinterpret_cast<R *>(smem_raw);
     __shared__ double sL[MAX_NU * MAX_NU];
+    if (blockIdx.x == gridDim.x - 1) { prepare_block(d); return; }
     if (!d.L_is_diagonal) { for (int i = threadIdx.x; i < d.nu * d.nu; i += blockDim.x) sL[i] = d.L[i]; __syncthreads(); }
     const long long col0 = (long long)blockIdx.x * blockDim.x;
     const long long col = col0 + threadIdx.x;   // local column index
@@ -216,7 +215,13 @@ template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sa
         const int t = (int)(col - kl * d.T);
         const long long kg = kl + d.k_begin;
         R v[NU];
-        if (kg < 2 || d.kept[kl]) {   // static rollouts (k_prepare) and kept rollouts (k_shift_kept) keep their values
+        if (kg == 0) {                 // rollout 0: zero noise, always (mppi.cpp:222)
+#pragma unroll
+            for (int i = 0; i < nu; i++) v[i] = R(0);
+        } else if (kg == 1) {          // rollout 1 = -U_prev, the UNSHIFTED optimum (mppi.cpp:269)
+#pragma unroll
+            for (int i = 0; i < nu; i++) v[i] = (R)(-d.U[t * nu + i]);
+        } else if (d.kept[kl]) {       // kept rollouts (k_shift_kept) keep their values
 #pragma unroll
             for (int i = 0; i < nu; i++) v[i] = noise[(size_t)col * nu + i];
         } else {
@@ -657,11 +662,6 @@ cudaError_t measure_fma_peak(int precision, double *tflops) {
 }
 
 // ---- launchers -----------------------------------------------------------------------------------------
-cudaError_t launch_prepare(const DeviceState &d, int precision, cudaStream_t s) {
-    if (precision == 0) k_prepare<double><<<dim3(1, d.batch), 256, 0, s>>>(d); else k_prepare<float><<<dim3(1, d.batch), 256, 0, s>>>(d);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_select_kept(const DeviceState &d, cudaStream_t s) {
     k_select_kept<<<dim3(1, d.batch), 1024, 0, s>>>(d);
     return cudaGetLastError();
@@ -684,7 +684,7 @@ template <class R, class RI, int NU> static cudaError_t sample_tt(const DeviceSt
     const long long ncols = d.k_count * d.T;
     const unsigned grid = (unsigned)((ncols + 255) / 256);
     const size_t tile = sizeof(R) * 256 * (size_t)NU;
-    k_sample<R, RI, NU><<<dim3(grid, d.batch), 256, tile, s>>>(d);
+    k_sample<R, RI, NU><<<dim3(grid + 1, d.batch), 256, tile, s>>>(d);   // + the prepare block
     ++*launches;
     return cudaGetLastError();
 }

@@ -42,11 +42,13 @@ __global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG)
     R *sU = reinterpret_cast<R *>(smem_raw);        // nu*T
     R *sW = sU + d.nu * d.T;                         // 6*T
     R *sx = sW + 6 * d.T;                            // 32
+    double *sDisc = reinterpret_cast<double *>(sx + 32);   // T discount factors std::pow(gamma, step) (mppi.cpp:326)
     const double *Usrc = d.U_shift + c * n;
     for (int i = threadIdx.x; i < d.nu * d.T; i += blockDim.x) sU[i] = (R)Usrc[i];
     const int has_w = frame->has_wrench;
     for (int i = threadIdx.x; i < 6 * d.T; i += blockDim.x) sW[i] = has_w ? (R)wrench[i] : R(0);
     for (int i = threadIdx.x; i < 32; i += blockDim.x) sx[i] = (R)frame->x0[i];
+    for (int i = threadIdx.x; i < d.T; i += blockDim.x) sDisc[i] = discount_pow(d.discount, i);
     __syncthreads();
 
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG)
             cost = rollout_toy<R>(P, sx, sU, eps, d.T, (R)d.dt, d.discount);
         } else {
             RolloutInputs<R> in;
-            in.x0 = sx; in.U = sU; in.W = has_w ? sW : nullptr; in.T = d.T; in.dt = (R)d.dt; in.discount = d.discount;
+            in.x0 = sx; in.U = sU; in.W = has_w ? sW : nullptr; in.T = d.T; in.dt = (R)d.dt; in.discount = d.discount; in.discount_table = sDisc;
             double bd[7] = {0, 0, 0, 0, 0, 0, 0};
             cost = rollout_franka<R, VAR, FAITHFUL, ParamsT, BIG>(MPPI_DEVICE_MODEL, MPPI_DEVICE_FAST_MODEL, P, in, eps, optimal_only ? bd : nullptr);
             if (optimal_only) {
@@ -96,7 +98,7 @@ cudaError_t launch_rollout_t(const DeviceState &d, const void *params, bool opti
     int block = d.k_count <= 148 * 64 ? 32 : (d.k_count <= 148 * 256 ? 64 : 128);
     long long grid = optimal_only ? 1 : (d.k_count + block - 1) / block;
     if (optimal_only) block = 32;
-    size_t smem = sizeof(R) * ((size_t)d.nu * d.T + 6 * (size_t)d.T + 32);
+    size_t smem = sizeof(R) * ((size_t)d.nu * d.T + 6 * (size_t)d.T + 32) + sizeof(double) * (size_t)d.T;
     auto kern = k_rollout<R, VAR, FAITHFUL, ParamsT, false>;
     if constexpr (VAR == VAR_TP_LEAN && !FAITHFUL) {
         static const long long big_from = std::getenv("MPPI_B200_BIG_FROM") ? std::atoll(std::getenv("MPPI_B200_BIG_FROM")) : (sizeof(R) == 8 ? 12288 : 24576);   // measured crossovers

@@ -116,7 +116,6 @@ __device__ __forceinline__ DeviceState controller_view(const DeviceState &g, int
 
 cudaError_t upload_robot_model();  // once per device
 
-cudaError_t launch_prepare(const DeviceState &d, int precision, cudaStream_t s);
 cudaError_t launch_select_kept(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_merge_kept(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_sample(const DeviceState &d, int precision, cudaStream_t s, int *launches);

@@ -240,6 +240,7 @@ template <class R> struct RolloutInputs {
     int T;
     R dt;
     double discount;
+    const double *discount_table = nullptr;   // pow(discount, step) per step, staged by the kernel (keeps pow() out of the step loop)
 };
 
 // VAR selects objective + which kinematics are alive; FAITHFUL selects the dynamics evaluation.
@@ -274,7 +275,7 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
         if constexpr (VAR == VAR_TP_LEAN) c = track_point_cost<R, true>(P, q, K);
         else if constexpr (VAR == VAR_TP_FULL) c = track_point_cost<R>(P, q, K);
         else c = assisted_cost<R>(P, q, qd, energy, K, in.W ? in.W + step * 6 : nullptr, bd);
-        const double sc = discount_pow(in.discount, step) * (double)c;
+        const double sc = (in.discount_table ? in.discount_table[step] : discount_pow(in.discount, step)) * (double)c;
         if (sc != sc) return sc;  // NaN
         total += sc;
         if (step + 1 == in.T) break;  // the state after the last step is never costed (mppi.cpp:316-341)
