@@ -34,6 +34,12 @@ from assistedmanipulation_b200 import abi  # noqa: E402
 # Algorithmic work per rollout-step: Featherstone operation counts at n = 12 one-dof
 # joints — ABA 4641 + RNEA 1880 + second-order FK / frames / WORLD jacobian ~2300 + cost + Euler + tank.
 FLOPS_PER_STEP = {"cfg2": 9000.0, "cfg3": 9500.0, "toy": 25.0, "cfg4_f32": 9000.0, "cfg4_f64": 9000.0}
+# What the rollout kernel EXECUTES per rollout-step (2*DFMA + DMUL + DADD per thread from the ncu source page of
+# profiles/r1_cfg2_rollout.ncu-rep): the structure-exploiting solver needs far fewer operations than the reference's
+# generic algorithm counted above, so the algorithmic fraction can pass 1 where the pipe is full.
+EXECUTED_FLOPS_PER_STEP = {"cfg2": 3764.0, "cfg4_f64": 3764.0}
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_rollout launch, same capture (the noise rows, read once)
+ROLLOUT_DRAM_BYTES = {"cfg2": 25.23e6}
 
 
 def workload(name, n_gpus):
@@ -371,9 +377,11 @@ def main():
         "device_update_us": {"p50": float(np.median(dev_s) * 1e6), "p99": float(np.percentile(dev_s, 99) * 1e6)},
         "stages_us": {n: float(s * 1e6) for n, s in zip(abi.STAGES, stage)},
         "roofline": {"kernel": "k_rollout", "bound": "fp64_pipe" if wl["precision"] == abi.FP64 else "fp32_pipe", "achieved": achieved_tflops, "peak": fma_peak.value,
-                     "unit": "TFLOP/s", "frac": achieved_tflops / fma_peak.value, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved_tflops / fma_peak.value, "traffic": ROLLOUT_DRAM_BYTES.get(args.workload),
                      "peak_source": "FMA-chain microbenchmark run in this process (mppi_b200_measure_fma_peak); MEASURED_PEAKS.json has no vector FP peak",
-                     "algorithmic_flops_per_rollout_step": FLOPS_PER_STEP.get(args.workload, 9000.0)},
+                     "algorithmic_flops_per_rollout_step": FLOPS_PER_STEP.get(args.workload, 9000.0),
+                     "executed_flops_per_rollout_step": EXECUTED_FLOPS_PER_STEP.get(args.workload),
+                     "executed_frac": (EXECUTED_FLOPS_PER_STEP[args.workload] * k_local * T / rollout_s / 1e12 / fma_peak.value) if args.workload in EXECUTED_FLOPS_PER_STEP else None},
         "roofline_hbm": {
             "sample": {"bound": "hbm", "achieved": noise_bytes / float(stage[abi.STAGES.index("sample")]) / 1e9, "peak": hbm_peak, "unit": "GB/s"},
             "weighted_sum": {"bound": "hbm", "achieved": noise_bytes / float(stage[abi.STAGES.index("weighted_sum")]) / 1e9, "peak": hbm_peak, "unit": "GB/s"},
