@@ -116,12 +116,13 @@ template <class R> struct Scratch {
     Art<R> Ia9;        // joint 9 collects two children
 };
 
-template <class R, int I> MPPI_HD void joint_transform(const RobotModel<R> &M, R q, Xf<R> &X) {
+// cs / sn: the joint's cosine / sine when the caller already has them (FUSED mode shares one set per step), else null
+template <class R, int I> MPPI_HD void joint_transform(const RobotModel<R> &M, R q, Xf<R> &X, const R *cs = nullptr, const R *sn = nullptr) {
     constexpr int T = Joint<I>::type;
     const R *P = M.place_R[I];
     if (T == JT_RZ) {
         R s, c;
-        sincos_(q, &s, &c);
+        if (cs) { s = sn[I]; c = cs[I]; } else sincos_(q, &s, &c);
 #pragma unroll
         for (int r = 0; r < 3; r++) {
             X.R_.m[3 * r + 0] = P[3 * r + 0] * c + P[3 * r + 1] * s;
@@ -139,10 +140,10 @@ template <class R, int I> MPPI_HD void joint_transform(const RobotModel<R> &M, R
 
 // ---- pass 1: transforms, velocities, RNEA forces ----------------------------------------------
 template <class R, int I, bool VEL, bool NLE, bool BIAS>
-MPPI_HD void pass1(const RobotModel<R> &M, const R *q, const R *qd, Scratch<R> &S, Mot<R> *agf) {
+MPPI_HD void pass1(const RobotModel<R> &M, const R *q, const R *qd, Scratch<R> &S, Mot<R> *agf, const R *cs = nullptr, const R *sn = nullptr) {
     constexpr int P = Joint<I>::parent, T = Joint<I>::type;
     const R sg = M.sign[I];
-    joint_transform<R, I>(M, q[I] * sg, S.li[I]);
+    joint_transform<R, I>(M, q[I] * sg, S.li[I], cs, sn);
     if (VEL) {
         const R w = qd[I] * sg;
         Mot<R> vj = joint_motion<R, T>(w);
@@ -163,7 +164,7 @@ MPPI_HD void pass1(const RobotModel<R> &M, const R *q, const R *qd, Scratch<R> &
             if (BIAS) S.pA[I] = vxh;
         }
     }
-    if (I + 1 < NJ) pass1<R, (I + 1 < NJ ? I + 1 : I), VEL, NLE, BIAS>(M, q, qd, S, agf);
+    if (I + 1 < NJ) pass1<R, (I + 1 < NJ ? I + 1 : I), VEL, NLE, BIAS>(M, q, qd, S, agf, cs, sn);
 }
 
 // ---- RNEA backward: nle_i = S^T f_i ; f_parent += X f_i ----------------------------------------
@@ -335,12 +336,12 @@ MPPI_HD void world_chain(const RobotModel<R> &M, const Scratch<R> &S, Xf<R> &oM,
 //   FUSED  : a = M^-1 u
 //   NLE    : also produce nle(q, qd) (needed for tau^T v of the energy tank, or in FAITHFUL mode)
 template <class R, bool FAITHFUL, bool NLE, int FLAGS, bool DO_ABA = true>
-MPPI_HD void robot_calculate(const RobotModel<R> &M, const R *q, const R *qd, const R *u, R *qdd, R *nle, Kinematics<R> &K) {
+MPPI_HD void robot_calculate(const RobotModel<R> &M, const R *q, const R *qd, const R *u, R *qdd, R *nle, Kinematics<R> &K, const R *cs = nullptr, const R *sn = nullptr) {
     Scratch<R> S;
     Mot<R> agf[NJ];
     constexpr bool NEED_NLE = NLE || FAITHFUL;
     constexpr bool VEL = NEED_NLE || (FLAGS & KIN_VEL);
-    pass1<R, 0, VEL, NEED_NLE, FAITHFUL>(M, q, qd, S, agf);
+    pass1<R, 0, VEL, NEED_NLE, FAITHFUL>(M, q, qd, S, agf, cs, sn);
     {
         Xf<R> oM;
         R Jl[21];

@@ -298,7 +298,7 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
             qd[2] = u[2];
             // (carrying the end effector point inside the inertia loop was tried: +4 registers, spills, 4 % slower)
             if constexpr (LEAN) K.ee_pos = ee_position_fast<R>(F, q, cs, sn);
-            else robot_calculate<R, false, POWER, KF, false>(M, q, qd, tau, qdd, nle, K);
+            else robot_calculate<R, false, POWER, KF, false>(M, q, qd, tau, qdd, nle, K, cs, sn);   // the joint sines / cosines are shared
             aba_fused_fast<R, BIG ? 7 : kArmUnroll>(F, q, cs, sn, tau, qdd);
         }
 #pragma unroll
