@@ -120,6 +120,7 @@ EXPORTS = [
     "mppi_b200_dynamics_forecast_create", "mppi_b200_dynamics_forecast_destroy", "mppi_b200_dynamics_forecast_last_error",
     "mppi_b200_dynamics_forecast_steps", "mppi_b200_dynamics_forecast_run", "mppi_b200_dynamics_forecast_read",
     "mppi_b200_dynamics_forecast_device_records",
+    "mppi_b200_p2p_handle", "mppi_b200_p2p_init",
 ]
 STAGES = ("h2d", "warm_start_shift", "sample", "rollout", "weights", "weighted_sum", "finish", "d2h")
 
@@ -214,10 +215,39 @@ def load_library(path=None):
     lib.mppi_b200_dynamics_forecast_read.restype = C.c_int
     lib.mppi_b200_dynamics_forecast_device_records.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     lib.mppi_b200_dynamics_forecast_device_records.restype = C.c_int
+    lib.mppi_b200_p2p_handle.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mppi_b200_p2p_handle.restype = C.c_int
+    lib.mppi_b200_p2p_init.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mppi_b200_p2p_init.restype = C.c_int
     return lib
 
 
 # ---- reference defaults (host data only) -----------------------------------------------------
+
+def connect_ranks(lib, engine_handle, dist, torch, exchange="p2p"):
+    """Attach the in-library exchange of a sharded engine (one process per GPU). `p2p`: every rank's mailbox handle is
+    all-gathered through torch.distributed and opened by its peers; `nccl`: rank 0's NCCL id is broadcast."""
+    rank = dist.get_rank()
+    if exchange == "p2p":
+        buf = (C.c_ubyte * 64)()
+        rc = lib.mppi_b200_p2p_handle(engine_handle, buf)
+        if rc != 0:
+            return rc
+        mine = torch.tensor(list(buf), dtype=torch.uint8, device="cuda")
+        every = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(dist.get_world_size())]
+        dist.all_gather(every, mine)
+        raw = bytes(torch.cat(every).cpu().tolist())
+        return lib.mppi_b200_p2p_init(engine_handle, C.c_char_p(raw))
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf = (C.c_ubyte * 128)()
+        rc = lib.mppi_b200_comm_unique_id(buf)
+        if rc != 0:
+            return rc
+        uid.copy_(torch.tensor(list(buf), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    return lib.mppi_b200_comm_init(engine_handle, C.c_char_p(bytes(uid.cpu().tolist())))
+
 
 def huddled_state(energy=100.0):
     """make_state(Preset::HUDDLED), reference src/frankaridgeback/state.cpp:15-19."""

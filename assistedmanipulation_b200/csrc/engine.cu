@@ -142,6 +142,13 @@ struct mppi_b200_engine {
     bool has_default = false;
     std::vector<long long> argmin;       // per controller
     ncclComm_t comm = nullptr;
+    // peer-memory exchange (kernels.cuh: PeerExchange): replaces the NCCL calls once mppi_b200_p2p_init has run
+    bool p2p = false;
+    PeerExchange px{};
+    double *mailbox = nullptr;
+    int *h_p2p_error = nullptr;          // host-mapped
+    std::vector<void *> peer_mappings;
+    unsigned long long attempts = 0;
     std::string error;
     float last_ms = 0.f;
     bool profiling = false;
@@ -184,6 +191,9 @@ void mppi_b200_destroy(mppi_b200_engine *e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->side) cudaStreamSynchronize(e->side);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    for (void *p : e->peer_mappings) cudaIpcCloseMemHandle(p);
+    if (e->mailbox) cudaFree(e->mailbox);
+    if (e->h_p2p_error) cudaFreeHost(e->h_p2p_error);
     for (void *p : e->allocs) cudaFree(p);
     if (e->h_frame) cudaFreeHost(e->h_frame);
     if (e->h_U) cudaFreeHost(e->h_U);
@@ -366,9 +376,11 @@ int host_prepare(mppi_b200_engine *e, const double *state, double time, const do
         std::memcpy(f->x0, state + (size_t)c * d.nx, sizeof(double) * d.nx);
         f->time = time; f->sg_prev_trim = 0.0; f->shift_by = shift_by; f->seed = seed + (uint64_t)c;
         f->update_index = (unsigned long long)e->update_count;
+        f->attempt = e->attempts;
         f->has_wrench = wrench != nullptr || e->wrench_device != nullptr; f->noise_source = noise_source;
         if (wrench && !e->wrench_device) std::memcpy(base + sizeof(Frame), wrench + (size_t)c * 6 * d.T, sizeof(double) * 6 * d.T);
     }
+    e->attempts++;
     // double-buffered snapshot for the side-stream re-rollout
     const int slot = (int)(e->update_count & 1);
     d.frame_snap = e->d_frame_snap[slot]; d.U_snap = e->d_U_snap[slot];
@@ -399,10 +411,14 @@ int enqueue_begin(mppi_b200_engine *e, const void *noise, int32_t noise_source) 
         CUDA_TRY(e, launch_select_kept(d, e->stream)); launches++;
         if (d.world > 1) {
             // warm start over a sharded set: all-gather every rank's best candidates, merge identically everywhere
-            if (!e->comm) return fail(e, MPPI_B200_ERR_UNSUPPORTED, "keep_best_rollouts > 0 on a sharded rollout set needs the in-library NCCL exchange (mppi_b200_comm_init)");
+            if (!e->comm && !e->p2p) return fail(e, MPPI_B200_ERR_UNSUPPORTED, "keep_best_rollouts > 0 on a sharded rollout set needs an in-library exchange (mppi_b200_p2p_init or mppi_b200_comm_init)");
             const long long keep = std::min<long long>(d.keep_best, d.K_total - 2);
-            ncclResult_t r = g_nccl.AllGather(d.cand, d.cand_all, (size_t)2 * keep, ncclDouble, e->comm, e->stream);
-            if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-gather failed");
+            if (e->p2p) {
+                CUDA_TRY(e, launch_exchange(d, e->px, EX_CAND, e->stream)); launches++;
+            } else {
+                ncclResult_t r = g_nccl.AllGather(d.cand, d.cand_all, (size_t)2 * keep, ncclDouble, e->comm, e->stream);
+                if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-gather failed");
+            }
             CUDA_TRY(e, launch_merge_kept(d, e->stream)); launches++;
         }
     }
@@ -430,6 +446,12 @@ int enqueue_finish(mppi_b200_engine *e) {
     CUDA_TRY(e, launch_finish(e->d, e->stream));   // writes U and the update's scalars straight into host-mapped memory
     e->launches += 1;
     STAGE(e, 7);
+    return MPPI_B200_OK;
+}
+
+int enqueue_exchange(mppi_b200_engine *e, int kind) {
+    CUDA_TRY(e, launch_exchange(e->d, e->px, kind, e->stream));
+    e->launches += 1;
     return MPPI_B200_OK;
 }
 
@@ -466,6 +488,7 @@ int host_complete(mppi_b200_engine *e) {
         for (int i = 0; i < MPPI_B200_STAGES; i++) { float ms = 0.f; cudaEventElapsedTime(&ms, e->ev_stage[i], e->ev_stage[i + 1]); e->stage_s[i] = ms * 1e-3; }
     }
     e->in_update = false;
+    if (e->p2p && *e->h_p2p_error) { *e->h_p2p_error = 0; return fail(e, MPPI_B200_ERR_NCCL, "peer exchange timed out: a rank of the sharded rollout set did not arrive"); }
     bool all_nan = false, smoothed = false;
     for (int c = 0; c < e->batch; c++) {
         const double *res = e->h_result + (size_t)c * (n + 8);
@@ -552,7 +575,9 @@ int mppi_b200_update_launch(mppi_b200_engine *e, const double *state, double tim
         const long long before = e->launches;
         CUDA_TRY(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
         rc = enqueue_begin(e, nullptr, MPPI_B200_NOISE_PHILOX);
+        if (!rc && e->p2p) rc = enqueue_exchange(e, EX_MINMAX);
         if (!rc) rc = enqueue_weights(e);
+        if (!rc && e->p2p) rc = enqueue_exchange(e, EX_SUMS);
         if (!rc) rc = enqueue_finish(e);
         cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
         e->graph_launches = (int)(e->launches - before);
@@ -570,12 +595,14 @@ int mppi_b200_update_launch(mppi_b200_engine *e, const double *state, double tim
         e->launches += e->graph_launches;
     } else {
         if ((rc = enqueue_begin(e, noise, noise_source))) return rc;
-        if (e->comm) {
+        if (e->p2p) { if ((rc = enqueue_exchange(e, EX_MINMAX))) return rc; }
+        else if (e->comm) {
             ncclResult_t r = g_nccl.AllReduce(e->d.minmax, e->d.minmax, 3, ncclDouble, ncclMax, e->comm, e->stream);
             if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-reduce failed");
         }
         if ((rc = enqueue_weights(e))) return rc;
-        if (e->comm) {
+        if (e->p2p) { if ((rc = enqueue_exchange(e, EX_SUMS))) return rc; }
+        else if (e->comm) {
             ncclResult_t r = g_nccl.AllReduce(e->d.sums, e->d.sums, 1 + (size_t)e->d.nu * e->d.T + (size_t)e->d.world, ncclDouble, ncclSum, e->comm, e->stream);
             if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-reduce failed");
         }
@@ -642,6 +669,66 @@ int mppi_b200_comm_init(mppi_b200_engine *e, const void *id128) {
     std::memcpy(&id, id128, 128);
     ncclResult_t r = g_nccl.CommInitRank(&e->comm, e->cfg.world_size, id, e->cfg.rank);
     if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "ncclCommInitRank failed");
+    return MPPI_B200_OK;
+}
+
+// ---- peer-memory exchange set-up ------------------------------------------------------------------------------
+static int p2p_allocate(mppi_b200_engine *e) {
+    if (e->mailbox) return MPPI_B200_OK;
+    const DeviceState &d = e->d;
+    if (d.world < 2 || d.world > MPPI_MAX_WORLD) return fail(e, MPPI_B200_ERR_UNSUPPORTED, "peer exchange: world size 2.." + std::to_string(MPPI_MAX_WORLD));
+    PeerExchange &px = e->px;
+    px.world = d.world; px.rank = d.rank;
+    const long long keep = std::max<long long>(1, std::min<long long>(d.keep_best, d.K_total - 2));
+    px.count[EX_MINMAX] = 3; px.count[EX_SUMS] = 1 + d.nu * d.T + d.world; px.count[EX_CAND] = (int)(2 * keep);
+    long long at = 0;
+    for (int parity = 0; parity < 2; parity++)
+        for (int k = 0; k < EX_KINDS; k++) { px.offset[parity][k] = at; at += (long long)d.world * ((px.count[k] + 1) & ~1); }
+    px.flags_offset = at;
+    at += 2ll * EX_KINDS * d.world;
+    CUDA_TRY(e, cudaMalloc(&e->mailbox, (size_t)at * sizeof(double)));
+    CUDA_TRY(e, cudaMemset(e->mailbox, 0, (size_t)at * sizeof(double)));
+    CUDA_TRY(e, cudaHostAlloc(&e->h_p2p_error, sizeof(int), cudaHostAllocMapped));
+    *e->h_p2p_error = 0;
+    CUDA_TRY(e, cudaHostGetDevicePointer((void **)&px.error, e->h_p2p_error, 0));
+    px.copies_done = dev_alloc<int>(e, 1);
+    if (!px.copies_done) return fail(e, MPPI_B200_ERR_CUDA, "device allocation failed");
+    px.timeout_cycles = 4000000000ll;   // ~2 s
+    for (int q = 0; q < MPPI_MAX_WORLD; q++) px.mail[q] = nullptr;
+    px.mail[d.rank] = e->mailbox;
+    return MPPI_B200_OK;
+}
+
+int mppi_b200_p2p_handle(mppi_b200_engine *e, void *handle64) {
+    if (!e || !handle64) return MPPI_B200_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    const int rc = p2p_allocate(e);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(e, cudaIpcGetMemHandle(&h, e->mailbox));
+    std::memcpy(handle64, &h, 64);
+    return MPPI_B200_OK;
+}
+
+int mppi_b200_p2p_init(mppi_b200_engine *e, const void *handles) {
+    if (!e || !handles) return MPPI_B200_ERR_INVALID;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    const int rc = p2p_allocate(e);
+    if (rc) return rc;
+    if (e->comm) return fail(e, MPPI_B200_ERR_INVALID, "this engine already exchanges through NCCL");
+    for (int q = 0; q < e->d.world; q++) {
+        if (q == e->d.rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const unsigned char *>(handles) + 64 * (size_t)q, 64);
+        void *ptr = nullptr;
+        CUDA_TRY(e, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        e->peer_mappings.push_back(ptr);
+        e->px.mail[q] = static_cast<double *>(ptr);
+    }
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    for (cudaGraphExec_t &g : e->graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    e->p2p = true;
     return MPPI_B200_OK;
 }
 

@@ -701,6 +701,69 @@ cudaError_t launch_rollout(const DeviceState &d, int precision, int variant, boo
     return precision == 0 ? launch_rollout_f64(d, variant, faithful, params, optimal_only, s) : launch_rollout_f32(d, variant, faithful, params, optimal_only, s);
 }
 
+// ---- peer-memory exchange (kernels.cuh: PeerExchange) ---------------------------------------------------------
+// grid = world blocks. Block p != rank: this rank's payload -> slot [rank] of peer p's mailbox, fence, flag.
+// Block rank: wait for every peer's flag in the local mailbox, combine the slots in rank order into the exchange buffer
+// (MAX for {-min, max, valid}, SUM for {sum w, sum w*eps, argmin slots}; the warm-start candidates are concatenated).
+__global__ void __launch_bounds__(256) k_exchange(const __grid_constant__ DeviceState d, const __grid_constant__ PeerExchange px, int kind) {
+    const int count = px.count[kind];
+    const unsigned long long update = d.frame->attempt;
+    const int parity = (int)(update & 1ull);
+    const unsigned long long seq = update * 4ull + (unsigned long long)kind + 1ull;   // never 0, unique per (update, kind)
+    double *payload = kind == EX_MINMAX ? d.minmax : (kind == EX_SUMS ? d.sums : d.cand);
+    const long long slot0 = px.offset[parity][kind];
+    const long long flag0 = px.flags_offset + ((long long)parity * EX_KINDS + kind) * px.world;
+    const int p = blockIdx.x;
+    if (p != px.rank) {
+        double *dst = px.mail[p] + slot0 + (long long)px.rank * count;
+        for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = payload[i];
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(px.mail[p] + flag0) + px.rank;
+            *flag = seq;
+            atomicAdd(px.copies_done, 1);   // the payload has been read: the combining block may overwrite it
+        }
+        return;
+    }
+    const double *mine = px.mail[px.rank] + slot0;
+    if (threadIdx.x < px.world && threadIdx.x != px.rank) {
+        const volatile unsigned long long *flag = reinterpret_cast<const volatile unsigned long long *>(px.mail[px.rank] + flag0) + threadIdx.x;
+        const long long t0 = clock64();
+        while (*flag != seq) {
+            if (clock64() - t0 > px.timeout_cycles) { *px.error = 1; break; }   // never hang the device on a missing peer
+            __nanosleep(100);
+        }
+    }
+    if (threadIdx.x == 0) {   // the (co-resident) copy blocks of this launch are done with the payload
+        const long long t0 = clock64();
+        while (atomicAdd(px.copies_done, 0) != px.world - 1) { if (clock64() - t0 > px.timeout_cycles) { *px.error = 1; break; } }
+        *px.copies_done = 0;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (kind == EX_CAND) {
+        for (int i = threadIdx.x; i < count * px.world; i += blockDim.x) {
+            const int q = i / count, e = i - q * count;
+            d.cand_all[i] = (q == px.rank) ? payload[e] : __ldcg(mine + (long long)q * count + e);
+        }
+        return;
+    }
+    for (int e = threadIdx.x; e < count; e += blockDim.x) {
+        double acc = (kind == EX_MINMAX) ? -CUDART_INF : 0.0;
+        for (int q = 0; q < px.world; q++) {
+            const double v = (q == px.rank) ? payload[e] : __ldcg(mine + (long long)q * count + e);
+            acc = (kind == EX_MINMAX) ? fmax(acc, v) : acc + v;
+        }
+        payload[e] = acc;
+    }
+}
+
+cudaError_t launch_exchange(const DeviceState &d, const PeerExchange &px, int kind, cudaStream_t s) {
+    k_exchange<<<px.world, 256, 0, s>>>(d, px, kind);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_minmax_publish(const DeviceState &d, cudaStream_t s) {
     k_minmax_publish<<<1, 32, 0, s>>>(d);
     return cudaGetLastError();

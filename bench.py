@@ -233,6 +233,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--forecast", default="table", choices=["table", "kalman"], help="cfg5: host wrench tables, or the device forecast producer fed measured wrenches")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: the library's own kernels over NVLink peer memory, or NCCL all-reduces")
     ap.add_argument("--separate-engines", action="store_true", help="cfg5: one engine per controller instead of one batched engine")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -273,14 +274,7 @@ def main():
                              keep_best=0, device=local_rank, rank=rank, world_size=world)
     e = el.Engine(holder, wl["params"])
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            buf = (C.c_ubyte * 128)()
-            assert e.lib.mppi_b200_comm_unique_id(buf) == 0
-            uid.copy_(torch.tensor(list(buf), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        raw = bytes(uid.cpu().tolist())
-        assert e.lib.mppi_b200_comm_init(e.h, C.c_char_p(raw)) == 0, e.error()
+        assert abi.connect_ranks(e.lib, e.h, dist, torch, args.exchange) == 0, e.error()
     T, R = e.query(abi.QUERY_STEP_COUNT), e.query(abi.QUERY_ROLLOUT_COUNT)
     nu = e.query(abi.QUERY_CONTROL_DOF)
     flush = None if args.no_l2_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
@@ -367,7 +361,7 @@ def main():
         "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": wl.get("scaling", "weak"), "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
         "config": {"workload": wl["name"], "rollouts": wl["K"], "static_rollouts": 2, "steps_per_rollout": T, "time_step": 0.01, "update_cadence_s": 0.05,
                    "noise": "in-kernel Philox4x32-10", "dynamics_mode": "fused", "keep_best_rollouts": 0,
-                   "parallelism": "rollouts sharded over %d GPU(s); NCCL all-reduce of [-min,max] and [sum w, sum w*eps]" % world,
+                   "parallelism": "rollouts sharded over %d GPU(s); %s of [-min,max] and [sum w, sum w*eps]" % (world, "no exchange" if world == 1 else ("exchange kernels over NVLink peer memory (IPC mailboxes)" if args.exchange == "p2p" else "NCCL all-reduce")),
                    "l2": "not flushed" if flush is None else "flushed between timed iterations (256 MiB write)",
                    "timing": "value: CUDA events on the engine stream around each update (inputs resident); e2e: host clock around the C-ABI call"},
         "clocks": sampler.result(),

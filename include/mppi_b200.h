@@ -212,6 +212,15 @@ int mppi_b200_synchronize(mppi_b200_engine *engine);
 int mppi_b200_comm_unique_id(void *id128);
 int mppi_b200_comm_init(mppi_b200_engine *engine, const void *id128);
 
+/* In-library exchange over NVLink peer memory, one process per GPU (preferred to NCCL for this path: the payloads are
+ * 24 B and ~6 KB, the cost is latency). Every rank exports its mailbox (a cudaIpcMemHandle_t, 64 bytes); the caller
+ * gathers the handles of all ranks in rank order with whatever transport it has and hands them to every engine. After
+ * that mppi_b200_update performs the min/max, weighted-sum and warm-start exchanges with its own kernels (stores into
+ * the peers' mailboxes, flags, rank-ordered combine), all inside the update's CUDA graph. A rank that does not arrive
+ * within ~2 s makes the update return MPPI_B200_ERR_NCCL instead of hanging the device. */
+int mppi_b200_p2p_handle(mppi_b200_engine *engine, void *handle64);
+int mppi_b200_p2p_init(mppi_b200_engine *engine, const void *handles /* world_size x 64 bytes, rank order */);
+
 /* mppi::Trajectory::get, mppi.cpp:481-512 (host side, linear interpolation / default control). */
 int mppi_b200_get(mppi_b200_engine *engine, double *control, double time);
 

@@ -21,13 +21,8 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 K, T, nu = 2046, 32, 12
 tp = abi.default_track_point()
 e = el.Engine(abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_TRACK_POINT, K, 0.32, dynamics_mode=abi.DYNAMICS_FUSED, device=local, rank=rank, world_size=world, keep_best=20), tp)
-uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-if rank == 0:
-    buf = (C.c_ubyte * 128)()
-    assert e.lib.mppi_b200_comm_unique_id(buf) == 0
-    uid.copy_(torch.tensor(list(buf), dtype=torch.uint8))
-dist.broadcast(uid, 0)
-assert e.lib.mppi_b200_comm_init(e.h, C.c_char_p(bytes(uid.cpu().tolist()))) == 0, e.error()
+exchange = os.environ.get("MPPI_B200_TEST_EXCHANGE", "nccl")   # "nccl" or "p2p" (NVLink peer-memory mailboxes)
+assert abi.connect_ranks(e.lib, e.h, dist, torch, exchange) == 0, e.error()
 x0 = abi.huddled_state()
 Us, kept, best = [], [], []
 for u in range(4):
@@ -54,6 +49,6 @@ if rank == 0:
         assert o.update(x0, 0.05 * u, None, whole.read(abi.READ_NOISE, (K + 2) * T * nu)) == 0
         Uo = o.read(abi.READ_OPTIMAL, nu * T)
         assert np.abs(Us[u] - Uo).max() <= 1e-9 * np.abs(Uo).max()
-    print("sharded ok", world, "ranks")
+    print("sharded ok", world, "ranks", exchange)
 e.close()
 dist.destroy_process_group()

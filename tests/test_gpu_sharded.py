@@ -114,12 +114,16 @@ def test_sharded_keep_best_needs_the_library_exchange():
     e.close()
 
 
-def test_nccl_two_gpus():
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+def test_two_gpus_in_library_exchange(exchange):
+    """One process per GPU; the library exchanges min/max, weighted sums and warm-start candidates itself — through NCCL
+    or through its own kernels over NVLink peer memory (IPC-mapped mailboxes). Rank 0 compares with one GPU and the oracle."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     worker = os.path.join(ol.ROOT, "tests", "sharded_worker.py")
+    env = dict(os.environ, MPPI_B200_TEST_EXCHANGE=exchange)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                          "--master-port", "29611", worker], capture_output=True, text=True, timeout=600)
+                          "--master-port", "29611" if exchange == "nccl" else "29612", worker], capture_output=True, text=True, timeout=150, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "sharded ok" in out.stdout
+    assert "sharded ok 2 ranks " + exchange in out.stdout
