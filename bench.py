@@ -273,8 +273,20 @@ def main():
     holder = abi.make_config(wl["system"], wl["objective"], wl["K"], wl["horison"], precision=wl["precision"], dynamics_mode=abi.DYNAMICS_FUSED,
                              keep_best=0, device=local_rank, rank=rank, world_size=world)
     e = el.Engine(holder, wl["params"])
+    exchange = args.exchange
     if world > 1:
-        assert abi.connect_ranks(e.lib, e.h, dist, torch, args.exchange) == 0, e.error()
+        rc = abi.connect_ranks(e.lib, e.h, dist, torch, exchange)
+        ok = torch.tensor([1 if rc == 0 else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok[0]) == 0 and exchange == "p2p":
+            # peer mappings not available on this box (no IPC / no P2P): every rank falls back to NCCL together
+            sys.stderr.write("bench: peer-memory exchange unavailable (%s); using NCCL\n" % e.error())
+            e.close()
+            e = el.Engine(holder, wl["params"])
+            exchange = "nccl"
+            assert abi.connect_ranks(e.lib, e.h, dist, torch, exchange) == 0, e.error()
+        else:
+            assert int(ok[0]) == 1, e.error()
     T, R = e.query(abi.QUERY_STEP_COUNT), e.query(abi.QUERY_ROLLOUT_COUNT)
     nu = e.query(abi.QUERY_CONTROL_DOF)
     flush = None if args.no_l2_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
@@ -361,7 +373,7 @@ def main():
         "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": wl.get("scaling", "weak"), "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
         "config": {"workload": wl["name"], "rollouts": wl["K"], "static_rollouts": 2, "steps_per_rollout": T, "time_step": 0.01, "update_cadence_s": 0.05,
                    "noise": "in-kernel Philox4x32-10", "dynamics_mode": "fused", "keep_best_rollouts": 0,
-                   "parallelism": "rollouts sharded over %d GPU(s); %s of [-min,max] and [sum w, sum w*eps]" % (world, "no exchange" if world == 1 else ("exchange kernels over NVLink peer memory (IPC mailboxes)" if args.exchange == "p2p" else "NCCL all-reduce")),
+                   "parallelism": "rollouts sharded over %d GPU(s); %s of [-min,max] and [sum w, sum w*eps]" % (world, "no exchange" if world == 1 else ("exchange kernels over NVLink peer memory (IPC mailboxes)" if exchange == "p2p" else "NCCL all-reduce")),
                    "l2": "not flushed" if flush is None else "flushed between timed iterations (256 MiB write)",
                    "timing": "value: CUDA events on the engine stream around each update (inputs resident); e2e: host clock around the C-ABI call"},
         "clocks": sampler.result(),
