@@ -231,11 +231,11 @@ def connect_ranks(lib, engine_handle, dist, torch, exchange="p2p"):
     if exchange == "p2p":
         buf = (C.c_ubyte * 64)()
         rc = lib.mppi_b200_p2p_handle(engine_handle, buf)
-        if rc != 0:
-            return rc
-        mine = torch.tensor(list(buf), dtype=torch.uint8, device="cuda")
+        mine = torch.tensor(list(buf), dtype=torch.uint8, device="cuda")   # every rank takes part in the gather, also one that failed
         every = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(dist.get_world_size())]
         dist.all_gather(every, mine)
+        if rc != 0:
+            return rc
         raw = bytes(torch.cat(every).cpu().tolist())
         return lib.mppi_b200_p2p_init(engine_handle, C.c_char_p(raw))
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
