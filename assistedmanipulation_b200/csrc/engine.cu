@@ -112,9 +112,15 @@ struct mppi_b200_engine {
     int variant = VAR_TOY;
     bool faithful = false;
     std::vector<unsigned char> params;  // objective block in kernel arithmetic
-    cudaStream_t stream = nullptr, side = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_main_done = nullptr, ev_side_done[2] = {nullptr, nullptr};
-    bool side_pending[2] = {false, false};
+    // SLOTS snapshot slots, each with its own side stream: the optimal re-rollout of an update is one thread per
+    // controller for T steps (milliseconds for the assisted-manipulation objective), so several of them must be in
+    // flight for the side work to keep up with short updates (32 controllers per GPU: 1.25 ms per update)
+    static constexpr int SLOTS = 4;
+    cudaStream_t stream = nullptr, side[SLOTS] = {};
+    cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_main_done = nullptr, ev_side_done[SLOTS] = {};
+    bool side_pending[SLOTS] = {};
+    double *d_opt[SLOTS] = {};          // per slot: optimal cost [batch] | breakdown [8 x batch]
+    double *h_opt = nullptr;            // pinned, SLOTS x 9 x batch
     // host mirrors (pinned)
     unsigned char *h_frame = nullptr;  // Frame + wrench
     double *h_U = nullptr;             // nu*T (stable copy of the published sequence for get())
@@ -124,9 +130,9 @@ struct mppi_b200_engine {
     // device allocations
     std::vector<void *> allocs;
     unsigned char *d_frame = nullptr;
-    double *d_frame_snap[2] = {nullptr, nullptr};
-    double *d_U_snap[2] = {nullptr, nullptr};
-    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    double *d_frame_snap[SLOTS] = {};
+    double *d_U_snap[SLOTS] = {};
+    cudaGraphExec_t graph[SLOTS] = {};
     int graph_launches = 0;
     bool use_graphs = true;
     const double *wrench_device = nullptr;   // forecast table left on the device by the forecast producer (batch x T x 6)
@@ -189,7 +195,7 @@ void mppi_b200_destroy(mppi_b200_engine *e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    if (e->side) cudaStreamSynchronize(e->side);
+    for (cudaStream_t s : e->side) if (s) cudaStreamSynchronize(s);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (void *p : e->peer_mappings) cudaIpcCloseMemHandle(p);
     if (e->mailbox) cudaFree(e->mailbox);
@@ -199,11 +205,13 @@ void mppi_b200_destroy(mppi_b200_engine *e) {
     if (e->h_U) cudaFreeHost(e->h_U);
     if (e->h_result) cudaFreeHost(e->h_result);
     if (e->h_stats) cudaFreeHost(e->h_stats);
-    for (cudaEvent_t ev : {e->ev_start, e->ev_end, e->ev_main_done, e->ev_side_done[0], e->ev_side_done[1]}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {e->ev_start, e->ev_end, e->ev_main_done}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->ev_side_done) if (ev) cudaEventDestroy(ev);
+    if (e->h_opt) cudaFreeHost(e->h_opt);
     for (cudaGraphExec_t g : e->graph) if (g) cudaGraphExecDestroy(g);
     for (cudaEvent_t ev : e->ev_stage) if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
-    if (e->side) cudaStreamDestroy(e->side);
+    for (cudaStream_t s : e->side) if (s) cudaStreamDestroy(s);
     delete e;
 }
 
@@ -292,12 +300,15 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     e->frame_bytes = sizeof(Frame) + sizeof(double) * 6 * T;   // per controller
 
     CREATE_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    CREATE_TRY(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+    for (cudaStream_t &s : e->side) CREATE_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (cudaEvent_t *ev : {&e->ev_start, &e->ev_end}) CREATE_TRY(cudaEventCreate(ev));
-    for (cudaEvent_t *ev : {&e->ev_main_done, &e->ev_side_done[0], &e->ev_side_done[1]}) CREATE_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&e->ev_main_done, cudaEventDisableTiming));
+    for (cudaEvent_t &ev : e->ev_side_done) CREATE_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CREATE_TRY(cudaMallocHost(&e->h_frame, e->frame_bytes * B));
     CREATE_TRY(cudaMallocHost(&e->h_U, n * B * sizeof(double)));
     CREATE_TRY(cudaMallocHost(&e->h_stats, 16 * B * sizeof(double)));
+    CREATE_TRY(cudaMallocHost(&e->h_opt, mppi_b200_engine::SLOTS * 9 * B * sizeof(double)));
+    std::memset(e->h_opt, 0, mppi_b200_engine::SLOTS * 9 * B * sizeof(double));
     CREATE_TRY(cudaHostAlloc(&e->h_result, (n + 8) * B * sizeof(double), cudaHostAllocMapped));
     std::memset(e->h_result, 0, (n + 8) * B * sizeof(double));
     CREATE_TRY(cudaHostGetDevicePointer((void **)&d.result, e->h_result, 0));
@@ -310,9 +321,10 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     auto A = [&](auto *&ptr, size_t count) { using P = std::remove_reference_t<decltype(*ptr)>; ptr = dev_alloc<P>(e, count * B); ok = ok && ptr; };
     auto A1 = [&](auto *&ptr, size_t count) { using P = std::remove_reference_t<decltype(*ptr)>; ptr = dev_alloc<P>(e, count); ok = ok && ptr; };
     e->d_frame = dev_alloc<unsigned char>(e, e->frame_bytes * B); ok = ok && e->d_frame;
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < mppi_b200_engine::SLOTS; i++) {
         e->d_frame_snap[i] = dev_alloc<double>(e, e->frame_bytes / 8 * B); ok = ok && e->d_frame_snap[i];
         e->d_U_snap[i] = dev_alloc<double>(e, n * B); ok = ok && e->d_U_snap[i];
+        e->d_opt[i] = dev_alloc<double>(e, 9 * B); ok = ok && e->d_opt[i];
     }
     d.frame_doubles = (int)(e->frame_bytes / 8);
     d.frame_snap = e->d_frame_snap[0]; d.U_snap = e->d_U_snap[0];
@@ -381,8 +393,8 @@ int host_prepare(mppi_b200_engine *e, const double *state, double time, const do
         if (wrench && !e->wrench_device) std::memcpy(base + sizeof(Frame), wrench + (size_t)c * 6 * d.T, sizeof(double) * 6 * d.T);
     }
     e->attempts++;
-    // double-buffered snapshot for the side-stream re-rollout
-    const int slot = (int)(e->update_count & 1);
+    // snapshot slot for the side-stream re-rollout
+    const int slot = (int)(e->update_count % mppi_b200_engine::SLOTS);
     d.frame_snap = e->d_frame_snap[slot]; d.U_snap = e->d_U_snap[slot];
     return MPPI_B200_OK;
 }
@@ -460,20 +472,20 @@ int enqueue_exchange(mppi_b200_engine *e, int kind) {
 // side stream over the snapshot k_prepare / k_finish left in this update's slot.
 int launch_optimal(mppi_b200_engine *e) {
     DeviceState &d = e->d;
-    const int slot = (int)(e->update_count & 1);
+    const int slot = (int)(e->update_count % mppi_b200_engine::SLOTS);
+    cudaStream_t side = e->side[slot];
     CUDA_TRY(e, cudaEventRecord(e->ev_main_done, e->stream));
-    CUDA_TRY(e, cudaStreamWaitEvent(e->side, e->ev_main_done, 0));
+    CUDA_TRY(e, cudaStreamWaitEvent(side, e->ev_main_done, 0));
     DeviceState o = d;
     o.frame = reinterpret_cast<const Frame *>(e->d_frame_snap[slot]);
     o.wrench = e->d_frame_snap[slot] + sizeof(Frame) / sizeof(double);
     o.U_shift = e->d_U_snap[slot];
     o.noise = e->d_zero_row;
-    CUDA_TRY(e, launch_rollout(o, e->cfg.precision, e->variant, e->faithful, e->params.data(), true, e->side));
+    o.optimal_cost = e->d_opt[slot]; o.breakdown = e->d_opt[slot] + e->batch;   // [batch] | [8 x batch], per slot: slots overlap
+    CUDA_TRY(e, launch_rollout(o, e->cfg.precision, e->variant, e->faithful, e->params.data(), true, side));
     e->launches += 1;
-    // h_stats: [5 x batch] update scalars | [batch] optimal cost | [8 x batch] breakdown
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 5 * e->batch, d.optimal_cost, e->batch * sizeof(double), cudaMemcpyDeviceToHost, e->side));
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_stats + 6 * e->batch, d.breakdown, 8 * e->batch * sizeof(double), cudaMemcpyDeviceToHost, e->side));
-    CUDA_TRY(e, cudaEventRecord(e->ev_side_done[slot], e->side));
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_opt + (size_t)slot * 9 * e->batch, e->d_opt[slot], 9 * e->batch * sizeof(double), cudaMemcpyDeviceToHost, side));
+    CUDA_TRY(e, cudaEventRecord(e->ev_side_done[slot], side));
     e->side_pending[slot] = true;
     return MPPI_B200_OK;
 }
@@ -509,9 +521,9 @@ int host_complete(mppi_b200_engine *e) {
     return MPPI_B200_OK;
 }
 
-// the previous user of this update's snapshot slot (two updates ago) must have finished
+// the previous user of this update's snapshot slot (SLOTS updates ago) must have finished
 int wait_slot(mppi_b200_engine *e) {
-    const int slot = (int)(e->update_count & 1);
+    const int slot = (int)(e->update_count % mppi_b200_engine::SLOTS);
     if (e->side_pending[slot]) CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_side_done[slot], 0));
     return MPPI_B200_OK;
 }
@@ -569,7 +581,7 @@ int mppi_b200_update_launch(mppi_b200_engine *e, const double *state, double tim
     const bool graph_ok = e->use_graphs && noise_source == MPPI_B200_NOISE_PHILOX && !e->comm && !e->profiling;
     int rc = host_prepare(e, state, time, wrench, noise, noise_source, seed);
     if (rc) return rc;
-    const int slot = (int)(e->update_count & 1);
+    const int slot = (int)(e->update_count % mppi_b200_engine::SLOTS);
     if (graph_ok && !e->graph[slot]) {
         cudaGraph_t g = nullptr;
         const long long before = e->launches;
@@ -645,7 +657,7 @@ int mppi_b200_synchronize(mppi_b200_engine *e) {
     if (!e) return MPPI_B200_ERR_INVALID;
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-    CUDA_TRY(e, cudaStreamSynchronize(e->side));
+    for (cudaStream_t s : e->side) CUDA_TRY(e, cudaStreamSynchronize(s));
     return MPPI_B200_OK;
 }
 
@@ -787,8 +799,9 @@ int mppi_b200_read(mppi_b200_engine *e, int32_t what, void *dst, size_t bytes) {
             for (size_t c = 0; c < B; c++) { static_cast<double *>(dst)[2 * c] = -e->h_stats[5 * c]; static_cast<double *>(dst)[2 * c + 1] = e->h_stats[5 * c + 1]; }
             return MPPI_B200_OK;
         }
-        case MPPI_B200_READ_OPTIMAL_COST: if (!need(B * 8)) break; std::memcpy(dst, e->h_stats + 5 * B, bytes); return MPPI_B200_OK;
-        case MPPI_B200_READ_BREAKDOWN: if (!need(B * 64)) break; std::memcpy(dst, e->h_stats + 6 * B, bytes); return MPPI_B200_OK;
+        // the re-rollout of the LAST update: its slot's pinned copy (every stream was synchronised above)
+        case MPPI_B200_READ_OPTIMAL_COST: if (!need(B * 8)) break; std::memcpy(dst, e->h_opt + ((e->update_count + mppi_b200_engine::SLOTS - 1) % mppi_b200_engine::SLOTS) * 9 * B, bytes); return MPPI_B200_OK;
+        case MPPI_B200_READ_BREAKDOWN: if (!need(B * 64)) break; std::memcpy(dst, e->h_opt + ((e->update_count + mppi_b200_engine::SLOTS - 1) % mppi_b200_engine::SLOTS) * 9 * B + B, bytes); return MPPI_B200_OK;
         case MPPI_B200_READ_KEPT: {
             const size_t k = bytes / 8;
             if (bytes % 8 || k > B * (size_t)std::max<long long>(d.keep_best, 1)) break;
