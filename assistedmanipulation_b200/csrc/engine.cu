@@ -536,6 +536,13 @@ int mppi_b200_set_wrench_device(mppi_b200_engine *e, const double *device_table)
     if (device_table != e->wrench_device) {
         // the copy's source address is part of the captured update: capture again on the next launch
         CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+        if (device_table) {   // a table on another GPU would turn the per-update copy into a staged peer copy
+            cudaPointerAttributes attr{};
+            if (cudaPointerGetAttributes(&attr, device_table) != cudaSuccess || attr.type != cudaMemoryTypeDevice || attr.device != e->cfg.device) {
+                cudaGetLastError();
+                return fail(e, MPPI_B200_ERR_INVALID, "the wrench table must be device memory of the engine's GPU (create the forecast producer with the same device)");
+            }
+        }
         CUDA_TRY(e, cudaStreamSynchronize(e->stream));
         for (cudaGraphExec_t &g : e->graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
         e->wrench_device = device_table;

@@ -64,27 +64,35 @@ def workload(name, n_gpus):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md). One sampler per job (rank 0)
+    covering the first `gpus` devices in a single query every 0.2 s (nvidia-smi takes driver-wide locks; eight ranks polling
+    it every 50 ms is load the measurement does not need)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
+    def __init__(self, gpus=1, enabled=True):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.gpus, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.enabled = max(int(gpus), 1), [], set(), False, None, enabled
 
     def run(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag:
+        while self.enabled and not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:6]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
+                ids = ",".join(str(i) for i in range(self.gpus))
+                lines = subprocess.run(["nvidia-smi", "-i", ids, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                       capture_output=True, text=True, timeout=5).stdout.strip().splitlines()
+                clocks = []
+                for line in lines:
+                    out = line.split(",")
+                    clocks.append(float(out[0]))
+                    self.max_mhz = float(out[1])
+                    for n, v in zip(names, out[2:6]):
+                        if v.strip().lower().startswith("active"):
+                            self.reasons.add(n)
+                if clocks:
+                    self.samples.append(min(clocks))   # the slowest device of the job
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.2)
 
     def result(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
@@ -149,7 +157,7 @@ def bench_controllers(args, rank, world, local_rank, n_gpus, dist, torch, el):
         assert not args.separate_engines, "--forecast kalman needs the batched engine"
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import forecast_lib as fl
-        forecaster = fl.DeviceForecast(abi.FORECAST_KALMAN, 1.0, 0.01, 1, batch=len(mine))
+        forecaster = fl.DeviceForecast(abi.FORECAST_KALMAN, 1.0, 0.01, 1, batch=len(mine), device=local_rank)   # on the engine's GPU
         measured = np.ascontiguousarray(wrenches[:, 0, :])
         rng = np.random.default_rng(rank)
 
@@ -180,7 +188,7 @@ def bench_controllers(args, rank, world, local_rank, n_gpus, dist, torch, el):
     for _ in range(args.warmup):
         tick(step); step += 1
     launches0 = sum(e.query(abi.QUERY_KERNEL_LAUNCHES) for e in engines)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(n_gpus, enabled=(rank == 0))
     sampler.start()
     barrier()
     ticks = []
@@ -307,7 +315,7 @@ def main():
         assert e.update(x0, 0.05 * step, wrench, seed=1) == 0, e.error()
         step += 1
     launches0 = e.query(abi.QUERY_KERNEL_LAUNCHES)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(n_gpus, enabled=(rank == 0))
     sampler.start()
     barrier()
     dev_s, wall_s = [], []

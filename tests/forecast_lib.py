@@ -88,9 +88,9 @@ def ref_available():
 class DeviceForecast:
     """The CUDA producer through the C ABI; `batch` forecasters, tables read back to the host."""
 
-    def __init__(self, typ, hw, dt, order, batch=1, initial=None):
+    def __init__(self, typ, hw, dt, order, batch=1, initial=None, device=0):
         self.lib = abi.load_library()
-        cfg = abi.ForecastConfig(type=typ, batch=batch, device=0, order=order, time_step=dt,
+        cfg = abi.ForecastConfig(type=typ, batch=batch, device=device, order=order, time_step=dt,
                                  horison=hw, window=hw)
         self.batch = batch
         h = C.c_void_p()
