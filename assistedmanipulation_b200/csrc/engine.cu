@@ -469,7 +469,7 @@ int enqueue_exchange(mppi_b200_engine *e, int kind) {
 
 // Optimal re-rollout (Trajectory::filter, mppi.cpp:450-479) off the critical path: with no mppi::Filter
 // attached (actor.cpp:100) it only produces the optimal cost and its per-term breakdown, so it runs on a
-// side stream over the snapshot k_prepare / k_finish left in this update's slot.
+// side stream over the snapshot the prepare block of k_sample / k_finish left in this update's slot.
 int launch_optimal(mppi_b200_engine *e) {
     DeviceState &d = e->d;
     const int slot = (int)(e->update_count % mppi_b200_engine::SLOTS);

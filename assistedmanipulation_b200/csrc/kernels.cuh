@@ -79,8 +79,8 @@ struct DeviceState {
     int bound;
     double cmin[MAX_NU], cmax[MAX_NU];
     // optimal re-rollout outputs
-    // snapshot of this update's inputs for the optimal re-rollout on the side stream (double buffered)
-    double *frame_snap;    // copy of the frame block, written by k_prepare
+    // snapshot of this update's inputs for the optimal re-rollout on a side stream (one of the engine's slots)
+    double *frame_snap;    // copy of the frame block, written by the prepare block of k_sample
     int frame_doubles;
     double *U_snap;        // copy of the updated m_optimal_control_shifted, written by k_finish
     double *result;        // host-mapped: U [nu*T], {-min, max, valid} [3], argmin [1], sum w [1] — written by k_finish
