@@ -49,3 +49,66 @@ def all_reduce(dist, array, op):
     t = torch.from_numpy(np.ascontiguousarray(array, dtype=np.float64).copy())
     dist.all_reduce(t, op=op)
     return t.numpy()
+
+
+# ---- host model of the peer-memory exchange (csrc/k_misc.cu: k_exchange) ---------------------------------------
+# The device protocol, one step at a time, so that its buffer-reuse argument can be checked under ANY interleaving of the
+# ranks (tests/test_sharded_gloo.py): per (parity, kind) every rank's mailbox holds one slot and one flag per rank; a
+# rank stores its payload into its slot of every peer's mailbox and then raises the flag with the sequence number of
+# the exchange; it combines its own mailbox's slots in rank order once every flag carries that number.
+
+EX_MINMAX, EX_SUMS, EX_CAND = 0, 1, 2
+
+
+class MailboxModel:
+    """All ranks' mailboxes plus one program counter per rank. `step(rank)` performs that rank's next atomic action:
+    one store into one peer (payload, then flag) or — when every flag has arrived — the combine. A rank never blocks
+    inside `step`; `step` returns False while the rank is waiting."""
+
+    def __init__(self, world, counts, parities=2):
+        self.world, self.counts, self.parities = world, counts, parities   # parities=1 models a single-buffered (broken) mailbox
+        self.slots = [[[[None] * world for _ in counts] for _ in range(2)] for _ in range(world)]   # [owner][parity][kind][src]
+        self.flags = [[[[0] * world for _ in counts] for _ in range(2)] for _ in range(world)]
+        self.pc = [0] * world            # peers already served in the current exchange
+        self.exchange = [0] * world      # exchanges completed per rank (attempt*len(kinds) + position)
+        self.results = [[] for _ in range(world)]
+        self.payload_of = None           # callable (rank, attempt, kind) -> np.ndarray
+
+    def kinds(self):
+        return list(range(len(self.counts)))
+
+    def step(self, rank):
+        kinds = self.kinds()
+        attempt, kind = divmod(self.exchange[rank], len(kinds))
+        parity, seq = attempt % self.parities, attempt * 4 + kind + 1
+        payload = self.payload_of(rank, attempt, kind)
+        peers = [p for p in range(self.world) if p != rank]
+        if self.pc[rank] < len(peers):
+            p = peers[self.pc[rank]]
+            # the slot must not still be needed by its owner: the owner has combined every earlier exchange that used it
+            pending = self.flags[p][parity][kind][rank]
+            assert pending == 0 or self._consumed(p, pending), "rank %d overwrites a slot of rank %d that was not read yet" % (rank, p)
+            self.slots[p][parity][kind][rank] = (seq, payload.copy())
+            self.flags[p][parity][kind][rank] = seq
+            self.pc[rank] += 1
+            return True
+        if any(self.flags[rank][parity][kind][q] != seq for q in peers):
+            return False                 # spinning on a flag
+        parts = []
+        for q in range(self.world):
+            if q == rank:
+                parts.append(payload)
+            else:
+                got_seq, data = self.slots[rank][parity][kind][q]
+                assert got_seq == seq, "rank %d read a payload of exchange %d while combining %d" % (rank, got_seq, seq)
+                parts.append(data)
+        parts = np.stack(parts)
+        out = parts.max(axis=0) if kind == EX_MINMAX else (parts.reshape(-1) if kind == EX_CAND else np.add.reduce(parts, axis=0))
+        self.results[rank].append((attempt, kind, out))
+        self.exchange[rank] += 1
+        self.pc[rank] = 0
+        return True
+
+    def _consumed(self, owner, seq):
+        attempt, kind = (seq - 1) // 4, (seq - 1) % 4
+        return self.exchange[owner] > attempt * len(self.counts) + kind

@@ -72,3 +72,63 @@ def test_shard_ranges_are_contiguous_and_ordered():
             assert edges[0][0] == 0 and edges[-1][1] == total
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
             assert max(e - b for b, e in edges) - min(e - b for b, e in edges) <= 1
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_mailbox_protocol_under_adversarial_interleaving(world):
+    sys.path.insert(0, ROOT)
+    from assistedmanipulation_b200 import sharding
+    """Host model of the device's peer-memory exchange (sharding.MailboxModel mirrors k_exchange step by step): under
+    random schedules — including one rank racing as far ahead as the protocol lets it — no slot is overwritten before
+    its owner combined it, every combine sees the payloads of its own exchange, and all ranks compute the same bits."""
+    rng = np.random.default_rng(world)
+    counts = [3, 9 + world, 6]
+    updates = 12
+
+    def payload(rank, attempt, kind):
+        r = np.random.default_rng(1000 * attempt + 10 * kind + rank)
+        return r.normal(size=counts[kind])
+
+    for trial in range(30):
+        m = sharding.MailboxModel(world, counts)
+        m.payload_of = payload
+        total = updates * len(counts)
+        bias = rng.integers(0, world)          # one rank is scheduled far more often than the others
+        guard = 0
+        while min(m.exchange) < total:
+            guard += 1
+            assert guard < 200000, "deadlock in the model"
+            runnable = [r for r in range(world) if m.exchange[r] < total]
+            r = bias if (bias in runnable and rng.uniform() < 0.7) else runnable[rng.integers(0, len(runnable))]
+            m.step(r)
+        # a rank can never be two exchanges of the same (parity, kind) ahead of a peer: that is what makes two buffers enough
+        for r in range(1, world):
+            assert len(m.results[r]) == len(m.results[0]) == total
+            for (a0, k0, v0), (a1, k1, v1) in zip(m.results[0], m.results[r]):
+                assert (a0, k0) == (a1, k1) and np.array_equal(v0, v1)
+        # and the combines are the reductions they stand for
+        for attempt, kind, out in m.results[0]:
+            parts = np.stack([payload(q, attempt, kind) for q in range(world)])
+            want = parts.max(axis=0) if kind == sharding.EX_MINMAX else (parts.reshape(-1) if kind == sharding.EX_CAND else np.add.reduce(parts, axis=0))
+            assert np.array_equal(out, want)
+
+
+def test_mailbox_model_catches_a_single_buffered_mailbox():
+    """The same model with ONE buffer per kind must trip its overwrite check: the double buffering is what the device relies on."""
+    sys.path.insert(0, ROOT)
+    from assistedmanipulation_b200 import sharding
+    rng = np.random.default_rng(0)
+    counts = [3]
+    tripped = False
+    for trial in range(50):
+        m = sharding.MailboxModel(2, counts, parities=1)
+        m.payload_of = lambda rank, attempt, kind: np.full(3, 10.0 * attempt + rank)
+        try:
+            for _ in range(400):
+                r = 0 if rng.uniform() < 0.8 else 1     # rank 0 races ahead
+                if m.exchange[r] < 8:
+                    m.step(r)
+        except AssertionError:
+            tripped = True
+            break
+    assert tripped
