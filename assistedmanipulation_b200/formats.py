@@ -274,3 +274,83 @@ def assisted_manipulation_from_json(j, base=None):
         if k in j:
             setattr(p, k, float(j[k]))
     return p
+
+
+_TP_FLAGS = ("enable_joint_limits", "enable_self_collision_avoidance", "enable_power_limit", "enable_reach_limits")
+
+
+def track_point_to_json(p):
+    """TrackPoint::Configuration in the field order of track_point.hpp:50-56."""
+    j = {"point": matrix_to_json(list(p.point))}
+    for k in _TP_FLAGS:
+        j[k] = bool(getattr(p, k))
+    j["lower_joint_limit"] = [_barrier_to_json(b, True) for b in p.lower_joint_limit]
+    j["upper_joint_limit"] = [_barrier_to_json(b, False) for b in p.upper_joint_limit]
+    j["self_collision_limit"] = _barrier_to_json(p.self_collision_limit, True)
+    j["self_collision_radii"] = [float(r) for r in p.self_collision_radii]
+    j["maximum_reach_limit"] = _barrier_to_json(p.maximum_reach_limit, False)
+    return j
+
+
+def track_point_from_json(j, base=None):
+    p = base if base is not None else abi.default_track_point()
+    if "point" in j:
+        for i, v in enumerate(vector_from_json(j["point"])):
+            p.point[i] = float(v)
+    for k in _TP_FLAGS:
+        if k in j:
+            setattr(p, k, int(bool(j[k])))
+    for k in ("lower_joint_limit", "upper_joint_limit"):
+        if k in j:
+            assert len(j[k]) == 12, k
+            for i, b in enumerate(j[k]):
+                _barrier_from_json(b, getattr(p, k)[i])
+    for k in ("self_collision_limit", "maximum_reach_limit"):
+        if k in j:
+            _barrier_from_json(j[k], getattr(p, k))
+    if "self_collision_radii" in j:
+        assert len(j["self_collision_radii"]) == 8
+        for i, r in enumerate(j["self_collision_radii"]):
+            p.self_collision_radii[i] = float(r)
+    return p
+
+
+def forecast_configuration_to_json(cfg, initial=None, observation=None):
+    """Forecast::Configuration (forecast.hpp:391-416): `type` is a plain enum (an integer in the JSON), the three
+    optional sub-configurations are `{}` when absent (controller/json.hpp:15-34)."""
+    j = {"type": int(cfg.type), "locf": {}, "average": {}, "kalman": {}}
+    if cfg.type == abi.FORECAST_LOCF:
+        j["locf"] = {"observation": matrix_to_json(np.zeros(6) if observation is None else observation), "horison": cfg.horison}
+    elif cfg.type == abi.FORECAST_AVERAGE:
+        j["average"] = {"states": 6, "window": cfg.window}
+    else:
+        j["kalman"] = {"observed_states": 6, "time_step": cfg.time_step, "horison": cfg.horison, "order": int(cfg.order),
+                       "variance": matrix_to_json(np.zeros(6)), "initial_state": matrix_to_json(np.zeros(6) if initial is None else initial)}
+    return j
+
+
+def forecast_configuration_from_json(j, batch=1, device=0):
+    """-> (abi.ForecastConfig, initial 6-vector or None) for mppi_b200_forecast_create."""
+    typ = int(j["type"])
+    cfg = abi.ForecastConfig(type=typ, batch=batch, device=device, order=0, time_step=0.0, horison=0.0, window=0.0)
+    initial = None
+    if typ == abi.FORECAST_LOCF:
+        sub = j.get("locf") or None
+        assert sub, "locf forecast selected with no configuration provided"        # forecast.cpp:10-13
+        cfg.horison = float(sub["horison"])
+        initial = vector_from_json(sub["observation"])
+    elif typ == abi.FORECAST_AVERAGE:
+        sub = j.get("average") or None
+        assert sub, "average forecast selected with no configuration provided"
+        assert int(sub["states"]) == 6, "the device producer forecasts the 6-component wrench"
+        cfg.window = float(sub["window"])
+    elif typ == abi.FORECAST_KALMAN:
+        sub = j.get("kalman") or None
+        assert sub, "kalman forecast selected with no configuration provided"
+        assert int(sub["observed_states"]) == 6, "the device producer forecasts the 6-component wrench"
+        cfg.time_step, cfg.horison, cfg.order = float(sub["time_step"]), float(sub["horison"]), int(sub["order"])
+        init = vector_from_json(sub.get("initial_state") or [])
+        initial = init if init.size else None
+    else:
+        raise ValueError("unknown forecast type %d" % typ)
+    return cfg, initial

@@ -101,3 +101,28 @@ def test_assisted_manipulation_json_round_trip():
     assert q.enable_energy_limit == 0 and q.energy_limit_above.bound == 25.0 and q.energy_limit_above.scale == p.energy_limit_above.scale
     assert q.trajectory_velocity_dropoff == 3.0
     assert formats.assisted_manipulation_to_json(formats.assisted_manipulation_from_json(j)) == j
+
+
+def test_track_point_json_round_trip():
+    p = abi.default_track_point()
+    j = formats.track_point_to_json(p)
+    assert list(j) == ["point", "enable_joint_limits", "enable_self_collision_avoidance", "enable_power_limit", "enable_reach_limits",
+                       "lower_joint_limit", "upper_joint_limit", "self_collision_limit", "self_collision_radii", "maximum_reach_limit"]   # track_point.hpp:50-56
+    assert j["point"] == [[1.0], [1.0], [1.0]] and len(j["self_collision_radii"]) == 8
+    q = formats.track_point_from_json(formats.merge_patch(json.loads(json.dumps(j)), {"point": [[0.5], [0.0], [1.2]], "enable_reach_limits": True}))
+    assert list(q.point) == [0.5, 0.0, 1.2] and q.enable_reach_limits == 1 and q.enable_joint_limits == p.enable_joint_limits
+    assert formats.track_point_to_json(formats.track_point_from_json(j)) == j
+
+
+def test_forecast_configuration_json():
+    cfg = abi.ForecastConfig(type=abi.FORECAST_KALMAN, batch=1, device=0, order=1, time_step=0.01, horison=1.0, window=0.0)
+    j = formats.forecast_configuration_to_json(cfg)
+    assert list(j) == ["type", "locf", "average", "kalman"] and j["type"] == 2 and j["locf"] == {} and j["average"] == {}   # forecast.hpp:413-416
+    assert set(j["kalman"]) == {"observed_states", "time_step", "horison", "order", "variance", "initial_state"}
+    back, initial = formats.forecast_configuration_from_json(json.loads(json.dumps(j)), batch=4, device=1)
+    assert (back.type, back.order, back.time_step, back.horison, back.batch, back.device) == (2, 1, 0.01, 1.0, 4, 1) and np.array_equal(initial, np.zeros(6))
+    locf = formats.forecast_configuration_to_json(abi.ForecastConfig(type=abi.FORECAST_LOCF, batch=1, device=0, order=0, time_step=0, horison=0.4, window=0), observation=[1, 2, 3, 0, 0, 0])
+    back, initial = formats.forecast_configuration_from_json(locf)
+    assert back.horison == 0.4 and list(initial) == [1, 2, 3, 0, 0, 0]
+    with pytest.raises(AssertionError, match="no configuration provided"):
+        formats.forecast_configuration_from_json({"type": 1, "locf": {}, "average": {}, "kalman": {}})
