@@ -30,8 +30,11 @@ __device__ __forceinline__ double decode_ordered(unsigned long long e) {
 // (FP32: 297 / 330 / 1572 against 386 / 417 / 1577; the crossover sits near K = 12 k in FP64 and 24 k in FP32.)
 // Few rollouts = one warp per SM, which lives on a small instruction footprint; many = fewer instructions win even at
 // two blocks per SM.
+#ifndef MPPI_LEAN_MIN_BLOCKS
+#define MPPI_LEAN_MIN_BLOCKS 1
+#endif
 template <class R, int VAR, bool FAITHFUL, class ParamsT, bool BIG = false>
-__global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG) ? 3 : 1) k_rollout(const __grid_constant__ DeviceState d, const __grid_constant__ ParamsT P, int optimal_only) {
+__global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG) ? MPPI_LEAN_MIN_BLOCKS : 1) k_rollout(const __grid_constant__ DeviceState d, const __grid_constant__ ParamsT P, int optimal_only) {
     // blockIdx.y = controller of a batched engine. Only the handful of buffers this kernel touches are offset
     // by hand (a full controller_view copy of the state costs ~40 registers here, i.e. a resident warp per SM).
     const size_t c = blockIdx.y;

@@ -118,11 +118,20 @@ template <class R, bool LEAN = false> MPPI_HD R track_point_cost(const TrackPoin
     // (one rounding less, 1e-16 relative)
     R cost = R(100) * dot(e, e);
     if (P.joint_limits) {
+        // track_point.cpp:48-65: 1000 + 1e5 * excess^2 for every joint outside [lo, hi]. With the default noise most
+        // rollouts are outside some limit for most of the horizon (63 % of the rollout-steps of BASELINE config 2), so
+        // there is no fast path to branch to; the term is written for a low FP64 instruction count instead: at most one
+        // side is violated, so ONE penalty is formed per joint, of the negative one of (q - lo, hi - q) — its square is
+        // the square of the reference's (lo - q) or (q - hi) — and both selections read the sign bit on the integer
+        // pipe (an FP64 comparison occupies the FP64 pipe and delivers its predicate ~13 cycles later). Same values and
+        // order of additions for every finite state; a NaN joint makes the end effector term NaN either way.
         R c = R(0);
 #pragma unroll
         for (int i = 0; i < 10; i++) {
-            if (q[i] < P.lim_lo[i]) { const R d = P.lim_lo[i] - q[i]; c += R(1000) + R(100000) * (d * d); }
-            if (q[i] > P.lim_hi[i]) { const R d = q[i] - P.lim_hi[i]; c += R(1000) + R(100000) * (d * d); }
+            const R below = q[i] - P.lim_lo[i], above = P.lim_hi[i] - q[i];
+            const R m = (sign_word(below) & 0x80000000u) ? below : above;
+            const R penalty = R(1000) + R(100000) * (m * m);
+            c += (sign_word(m) & 0x80000000u) ? penalty : R(0);
         }
         cost += c;
     }
@@ -296,10 +305,10 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
             qd[0] = cs[2] * u[0] - sn[2] * u[1];
             qd[1] = sn[2] * u[0] + cs[2] * u[1];
             qd[2] = u[2];
-            // (carrying the end effector point inside the inertia loop was tried: +4 registers, spills, 4 % slower)
-            if constexpr (LEAN) K.ee_pos = ee_position_fast<R>(F, q, cs, sn);
-            else robot_calculate<R, false, POWER, KF, false>(M, q, qd, tau, qdd, nle, K, cs, sn);   // the joint sines / cosines are shared
-            aba_fused_fast<R, BIG ? 7 : kArmUnroll>(F, q, cs, sn, tau, qdd);
+            // (carrying the end effector point inside the INERTIA loop was tried: +4 registers, spills, 4 % slower)
+            // (LEAN: the end effector point rides the solver's forward loop as a second, independent dependency chain)
+            if constexpr (!LEAN) robot_calculate<R, false, POWER, KF, false>(M, q, qd, tau, qdd, nle, K, cs, sn);   // the joint sines / cosines are shared
+            aba_fused_fast<R, BIG ? 7 : kArmUnroll, LEAN>(F, q, cs, sn, tau, qdd, &K.ee_pos);
         }
 #pragma unroll
         for (int i = 0; i < NJ; i++) qd[i] += qdd[i] * in.dt;

@@ -5,6 +5,7 @@
 // the device.
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define MPPI_HD __host__ __device__ __forceinline__
@@ -121,6 +122,25 @@ MPPI_HD void sincos_(float a, float *s, float *c) {
     sincosf(a, s, c);
 #else
     *s = sinf(a); *c = cosf(a);
+#endif
+}
+// fused multiply-add, spelled out where the operation order matters for the instruction count: the compiler contracts
+// a * b + c on the device but may not re-associate  x - (a * b - c * d)  into two dependent FMAs
+MPPI_HD double fma_(double a, double b, double c) { return fma(a, b, c); }
+MPPI_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+// the word that carries the sign bit (bit 31)
+MPPI_HD unsigned int sign_word(double a) {
+#if defined(__CUDA_ARCH__)
+    return (unsigned int)__double2hiint(a);
+#else
+    unsigned long long b; memcpy(&b, &a, sizeof b); return (unsigned int)(b >> 32);
+#endif
+}
+MPPI_HD unsigned int sign_word(float a) {
+#if defined(__CUDA_ARCH__)
+    return (unsigned int)__float_as_int(a);
+#else
+    unsigned int b; memcpy(&b, &a, sizeof b); return b;
 #endif
 }
 MPPI_HD double sqrt_(double a) { return sqrt(a); }

@@ -23,7 +23,7 @@ def hc():
     so = os.path.join(HC_DIR, "libhost_check.so")
     src = os.path.join(HC_DIR, "host_check.cpp")
     csrc = os.path.join(ol.ROOT, "assistedmanipulation_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("robot.cuh", "rollout_core.cuh", "spatial.cuh", "model_init.h", "params_convert.h", "robot_model.h")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("robot.cuh", "robot_fast.cuh", "rollout_core.cuh", "spatial.cuh", "model_init.h", "params_convert.h", "robot_model.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-x", "c++", "-fPIC", "-shared", "-I" + csrc, "-o", so, src])
     lib = C.CDLL(so)
