@@ -143,6 +143,21 @@ MPPI_HD unsigned int sign_word(float a) {
     unsigned int b; memcpy(&b, &a, sizeof b); return b;
 #endif
 }
+// low 32 bits of a double; v with the bits of `mask` (bit 31 = sign) flipped in its high word
+MPPI_HD int low_word(double a) {
+#if defined(__CUDA_ARCH__)
+    return __double2loint(a);
+#else
+    unsigned long long b; memcpy(&b, &a, sizeof b); return (int)(unsigned int)(b & 0xffffffffull);
+#endif
+}
+MPPI_HD double xor_high(double a, unsigned int mask) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(a) ^ (int)mask, __double2loint(a));
+#else
+    unsigned long long b; memcpy(&b, &a, sizeof b); b ^= (unsigned long long)mask << 32; memcpy(&a, &b, sizeof b); return a;
+#endif
+}
 MPPI_HD double sqrt_(double a) { return sqrt(a); }
 MPPI_HD float sqrt_(float a) { return sqrtf(a); }
 MPPI_HD double acos_(double a) { return acos(a); }

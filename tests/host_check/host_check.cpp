@@ -58,6 +58,11 @@ void host_fast_aba(int f32, const double *q, const double *u, double *qdd, doubl
         ee[0] = p.x; ee[1] = p.y; ee[2] = p.z;
     }
 }
+// the device's FP64 sine / cosine (polynomial core of robot_fast.cuh) evaluated on the host
+void host_sincos_poly(int n, const double *a, double *s, double *c) {
+    static const FastModel<double> F = make_fast_model<double>();
+    for (int i = 0; i < n; i++) sincos_poly(F.trig, a[i], &s[i], &c[i]);
+}
 int host_fast_structure_matches() { std::string w; return fast_structure_matches(&w) ? 1 : 0; }
 int host_topology_matches() { std::string w; return topology_matches(&w) ? 1 : 0; }
 }

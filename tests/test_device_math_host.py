@@ -32,6 +32,23 @@ def hc():
     return lib
 
 
+def test_device_sincos_matches_libm(hc):
+    """robot_fast.cuh sincos_poly (magic-constant reduction, sign bits flipped on the integer side) against libm: every
+    quadrant, both signs, exact zero, the neighbourhood of multiples of pi/2 and arguments up to the 2^31 range limit."""
+    rng = np.random.default_rng(3)
+    a = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-1e4, 1e4, 50000), rng.uniform(-2.0e9, 2.0e9, 50000),
+                        np.arange(-64, 65) * (np.pi / 2), np.arange(-64, 65) * (np.pi / 2) + 1e-9, np.arange(-64, 65) * (np.pi / 4),
+                        [0.0, -0.0, 1e-300, -1e-300, 5e-324, 0.7853981633974483, -0.7853981633974483]])
+    s, c = np.zeros_like(a), np.zeros_like(a)
+    hc.host_sincos_poly.argtypes = [C.c_int, _dp, _dp, _dp]
+    hc.host_sincos_poly(a.size, ol.ptr(a), ol.ptr(s), ol.ptr(c))
+    assert np.abs(s - np.sin(a)).max() <= 2.3e-16 and np.abs(c - np.cos(a)).max() <= 2.3e-16     # one ulp of a value near 1
+    small = np.abs(np.sin(a)) < 0.5
+    assert (np.abs(s - np.sin(a))[small] <= 2.0 * np.spacing(np.abs(np.sin(a))[small]) + 1e-25).all()   # relative accuracy near the zeros
+    assert (s[a == 0.0] == 0.0).all() and (c[a == 0.0] == 1.0).all()
+    assert np.abs(s * s + c * c - 1.0).max() <= 5e-16
+
+
 def test_topology_matches_generated_model(hc):
     assert hc.host_topology_matches() == 1
 

@@ -98,11 +98,11 @@ FP64_OPS = ("DFMA", "DMUL", "DADD", "DSETP", "DMNMX")
 
 
 def is_fp64(it):
-    return opcode(it["text"]).split(".")[0] in FP64_OPS
+    return not it.get("skipped") and opcode(it["text"]).split(".")[0] in FP64_OPS
 
 
 def cost(it):
-    return max(1, it["stall"])
+    return 0 if it.get("skipped") else max(1, it["stall"])
 
 
 def summarize(ins, lo, hi):
@@ -121,10 +121,15 @@ def main():
     ap.add_argument("--trip", type=int, default=7)
     ap.add_argument("--fp64-issue", type=int, default=2, help="cycles one FP64 warp instruction occupies the pipe")
     ap.add_argument("--dump", action="store_true", help="print every instruction of the step loop with its stall field")
+    ap.add_argument("--skip", default="", help="comma-separated file:line whose instructions are left out (slow paths behind forward branches)")
     ap.add_argument("--lines", type=int, default=0, help="print the N source lines with the most stall cycles per step (needs -lineinfo)")
     a = ap.parse_args()
     name, lines = disassemble(a.path, a.pattern)
     ins, labels = parse(lines)
+    skip = set(tuple([w.split(":")[0], int(w.split(":")[1])]) for w in a.skip.split(",") if w)
+    for it in ins:
+        if it["where"] in skip:
+            it["stall"], it["skipped"] = 0, True
     lp = loops(ins, labels)
     print("kernel %s: %d instructions, %d loops" % (name, len(ins), len(lp)))
     if not lp:
@@ -154,7 +159,7 @@ def main():
     for k in range(outer[0], outer[1] + 1):
         depth = sum(1 for r in inner if r[0] <= k <= r[1])
         w = a.trip ** depth
-        total_n += w
+        total_n += 0 if ins[k].get("skipped") else w
         e = by_line.setdefault(ins[k]["where"], [0.0, 0.0])
         e[0] += w * cost(ins[k]); e[1] += w
         if is_fp64(ins[k]):
