@@ -125,15 +125,15 @@ template <class R, bool LEAN = false> MPPI_HD R track_point_cost(const TrackPoin
         // the square of the reference's (lo - q) or (q - hi) — and both selections read the sign bit on the integer
         // pipe (an FP64 comparison occupies the FP64 pipe and delivers its predicate ~13 cycles later). Same values and
         // order of additions for every finite state; a NaN joint makes the end effector term NaN either way.
-        R c = R(0);
+        R c[2] = {R(0), R(0)};   // two partial sums: half the dependent additions (the sum differs from the sequential one by rounding only)
 #pragma unroll
         for (int i = 0; i < 10; i++) {
             const R below = q[i] - P.lim_lo[i], above = P.lim_hi[i] - q[i];
             const R m = (sign_word(below) & 0x80000000u) ? below : above;
             const R penalty = R(1000) + R(100000) * (m * m);
-            c += (sign_word(m) & 0x80000000u) ? penalty : R(0);
+            c[i & 1] += (sign_word(m) & 0x80000000u) ? penalty : R(0);
         }
-        cost += c;
+        cost += c[0] + c[1];
     }
     if constexpr (LEAN) return cost;
     if (P.self_collision) cost += self_collision_cost<R, true>(P.collision_limit, P.radii, P.link_mode, K);
@@ -285,7 +285,9 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
         else if constexpr (VAR == VAR_TP_FULL) c = track_point_cost<R>(P, q, K);
         else c = assisted_cost<R>(P, q, qd, energy, K, in.W ? in.W + step * 6 : nullptr, bd);
         const double sc = (in.discount_table ? in.discount_table[step] : discount_pow(in.discount, step)) * (double)c;
-        if (sc != sc) return sc;  // NaN
+        // A NaN stage cost ends the reference's rollout with a NaN total (mppi.cpp:331-334). NaN is absorbing in the sum,
+        // so the total is the same without leaving the loop — and without a data-dependent branch at the head of every
+        // step, behind which the scheduler cannot move the (independent) dynamics of the same step.
         total += sc;
         if (step + 1 == in.T) break;  // the state after the last step is never costed (mppi.cpp:316-341)
         // PinocchioDynamics::step, pinocchio_dynamics.cpp:226-260
