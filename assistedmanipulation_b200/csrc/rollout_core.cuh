@@ -17,21 +17,41 @@ template <class R> struct QuadP { R c0, c1, c2; };
 
 // cost.hpp:25-31
 template <class R> MPPI_HD R quadratic(const QuadP<R> &c, R v) { return c.c0 + c.c1 * fabs_(v) + c.c2 * v * v; }
-// cost.hpp:57-62 and :88-93. Same value in every case as the reference's two-branch form; written as a select so a warp
-// whose rollouts sit on both sides of a bound does not run both paths one after the other, and with the division
-// skipped for a zero scale (a uniform test: the parameters are constants) — 0 / x is 0 for every x the branch admits.
+// cost.hpp:57-62 and :88-93. Same value in every case as the reference's two-branch form, written as selects: a warp
+// whose rollouts sit on both sides of a bound does not run both paths one after the other, and — what matters more with
+// ~50 barrier terms per step — there is no control flow at all, so the terms are one basic block that the scheduler
+// overlaps (as branches each term was its own chain of compare, branch, reciprocal, compare, branch: ~100 cycles, 46 % of
+// the assisted-manipulation kernel's issue time in the static model).
+//   FP32 (the fast mode): scale / x as scale * rcp(x), one MUFU and one multiply (2 ulp; the compiler's approximate
+//   division adds four range-scaling multiplies and two comparisons). x is kept at or above the smallest normal number,
+//   so the reciprocal is finite and a ZERO scale needs no special case: 0 * rcp(x) is the reference's 0 / x = 0 for
+//   every x > 0, and NaN for a NaN state (the comparison-select keeps NaN, unlike fmaxf).
+//   FP64: IEEE division, skipped by a uniform branch when the scale is zero (the parameters are constants) — 0 / x is 0.
+MPPI_HD float barrier_div(float scale, float x) {
+    const float xs = (x < 1.17549435e-38f) ? 1.17549435e-38f : x;
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(xs));
+    return scale * r;
+#else
+    return scale / xs;
+#endif
+}
+MPPI_HD double barrier_div(double scale, double x) { return scale / x; }
+template <class R> MPPI_HD R barrier_inside(const BarrierP<R> &b, R v, R x) {   // x: distance to the bound, positive inside
+    if (sizeof(R) == 8 && b.scale == R(0)) return (v != v) ? v : std_min(R(0), b.maxc);
+    return std_min(barrier_div(b.scale, x), b.maxc);
+}
 template <class R> MPPI_HD R right_barrier(const BarrierP<R> &b, R v) {
     const R d = v - b.bound;
     const R outside = b.maxc + b.scale * (d * d);
-    if (b.scale == R(0)) return (v >= b.bound) ? outside : ((v != v) ? v : std_min(R(0), b.maxc));
-    const R inside = std_min(b.scale / (b.bound - v), b.maxc);
+    const R inside = barrier_inside(b, v, b.bound - v);
     return (v >= b.bound) ? outside : inside;
 }
 template <class R> MPPI_HD R left_barrier(const BarrierP<R> &b, R v) {
     const R d = b.bound - v;
     const R outside = b.maxc + b.scale * (d * d);
-    if (b.scale == R(0)) return (v <= b.bound) ? outside : ((v != v) ? v : std_min(R(0), b.maxc));
-    const R inside = std_min(b.scale / (v - b.bound), b.maxc);
+    const R inside = barrier_inside(b, v, v - b.bound);
     return (v <= b.bound) ? outside : inside;
 }
 
@@ -112,7 +132,8 @@ template <class R, int FLAGS> MPPI_HD void robot_kinematics(const RobotModel<R> 
 
 // objective/track_point.cpp:10-79,120-174
 // LEAN: the engine picked the variant without self-collision and reach terms, so they are compiled out
-template <class R, bool LEAN = false> MPPI_HD R track_point_cost(const TrackPointP<R> &P, const R *q, const Kinematics<R> &K) {
+// yaw: cos / sin of q[2] when the caller already has them (FUSED mode shares the step's joint sines / cosines), else null
+template <class R, bool LEAN = false> MPPI_HD R track_point_cost(const TrackPointP<R> &P, const R *q, const Kinematics<R> &K, const R *yaw = nullptr) {
     const Vec3<R> e = K.ee_pos - v3<R>(P.point[0], P.point[1], P.point[2]);
     // 100 * |e|^2: the reference squares the norm it took the root of (track_point.cpp:38-41); the root is skipped here
     // (one rounding less, 1e-16 relative)
@@ -139,7 +160,7 @@ template <class R, bool LEAN = false> MPPI_HD R track_point_cost(const TrackPoin
     if (P.self_collision) cost += self_collision_cost<R, true>(P.collision_limit, P.radii, P.link_mode, K);
     if (P.reach) {
         R sy, cy;
-        sincos_(q[2], &sy, &cy);
+        if (yaw) { cy = yaw[0]; sy = yaw[1]; } else sincos_(q[2], &sy, &cy);
         const Vec3<R> robot = K.mount_pos + v3<R>(cy * R(0.3), sy * R(0.3), R(0.15));
         const Vec3<R> d = K.ee_pos - robot;
         cost += right_barrier(P.reach_limit, sqrt_(dot(d, d)));
@@ -149,7 +170,7 @@ template <class R, bool LEAN = false> MPPI_HD R track_point_cost(const TrackPoin
 
 // objective/assisted_manipulation.cpp:37-319; bd (7 doubles) accumulates the per-term totals the
 // reference's logger reads after Trajectory::filter() (logging/assisted_manipulation.cpp:58-103).
-template <class R> MPPI_HD R assisted_cost(const AssistedP<R> &P, const R *q, const R *qd, R energy, const Kinematics<R> &K, const R *wrench, double *bd) {
+template <class R> MPPI_HD R assisted_cost(const AssistedP<R> &P, const R *q, const R *qd, R energy, const Kinematics<R> &K, const R *wrench, double *bd, const R *yaw = nullptr) {
     R cost = R(0);
     if (P.joint_limit) {
         R c = R(0);
@@ -166,7 +187,7 @@ template <class R> MPPI_HD R assisted_cost(const AssistedP<R> &P, const R *q, co
     if (P.workspace) {
         R c = R(0);
         R sy, cy;
-        sincos_(q[2], &sy, &cy);
+        if (yaw) { cy = yaw[0]; sy = yaw[1]; } else sincos_(q[2], &sy, &cy);
         const Vec3<R> fwd = v3<R>(cy, sy, R(0));
         const Vec3<R> robot = K.mount_pos + v3<R>(cy * R(0.1), sy * R(0.1), R(0.15));
         const Vec3<R> d = K.ee_pos - robot;
@@ -266,8 +287,10 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
     R energy = in.x0[30];
     Kinematics<R> K;
     R cs[NJ], sn[NJ];
+    // FUSED: one set of joint sines / cosines per state, evaluated when the state is formed (here and after every
+    // integration) and read by the objective's yaw terms, the kinematics and the solver of the next step
+    if constexpr (!FAITHFUL) joint_sincos<R>(F, q, cs, sn);
     if constexpr (LEAN) {
-        joint_sincos<R>(F, q, cs, sn);
         K.ee_pos = ee_position_fast<R>(F, q, cs, sn);
     } else {
         robot_kinematics<R, KF>(M, q, qd, K);
@@ -281,9 +304,11 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
         for (int d = 0; d < NJ; d++) u[d] = in.U[step * NJ + d] + e_next[d];
         if (step + 1 < in.T) load_eps(eps + (step + 1) * NJ, e_next);  // next step's noise is in flight during this step
         R c;
+        R yaw[2] = {cs[2], sn[2]};
+        const R *yawp = FAITHFUL ? nullptr : yaw;
         if constexpr (VAR == VAR_TP_LEAN) c = track_point_cost<R, true>(P, q, K);
-        else if constexpr (VAR == VAR_TP_FULL) c = track_point_cost<R>(P, q, K);
-        else c = assisted_cost<R>(P, q, qd, energy, K, in.W ? in.W + step * 6 : nullptr, bd);
+        else if constexpr (VAR == VAR_TP_FULL) c = track_point_cost<R>(P, q, K, yawp);
+        else c = assisted_cost<R>(P, q, qd, energy, K, in.W ? in.W + step * 6 : nullptr, bd, yawp);
         const double sc = (in.discount_table ? in.discount_table[step] : discount_pow(in.discount, step)) * (double)c;
         // A NaN stage cost ends the reference's rollout with a NaN total (mppi.cpp:331-334). NaN is absorbing in the sum,
         // so the total is the same without leaving the loop — and without a data-dependent branch at the head of every
@@ -303,7 +328,9 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
             robot_calculate<R, true, POWER, KF>(M, q, qd, tau, qdd, nle, K);
         } else {
             // FUSED: qdd = M(q)^-1 tau through the structure-exploiting solver; joint sines / cosines are shared
-            if (!(LEAN && step == 0)) joint_sincos<R>(F, q, cs, sn);
+            // (the lean kernel evaluates them here, at the head of the solver: its objective has no yaw term, and this
+            // placement gives the better schedule of the inertia loop)
+            if constexpr (LEAN) { if (step != 0) joint_sincos<R>(F, q, cs, sn); }
             qd[0] = cs[2] * u[0] - sn[2] * u[1];
             qd[1] = sn[2] * u[0] + cs[2] * u[1];
             qd[2] = u[2];
@@ -322,6 +349,7 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
             for (int i = 0; i < NJ; i++) p += (tau[i] + nle[i]) * qd[i];
             energy = std_max(R(0), energy + p * in.dt);  // energy.hpp:19-22
         }
+        if constexpr (!FAITHFUL && !LEAN) joint_sincos<R>(F, q, cs, sn);
     }
     return total;
 }

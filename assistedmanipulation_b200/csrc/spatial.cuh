@@ -143,6 +143,20 @@ MPPI_HD unsigned int sign_word(float a) {
     unsigned int b; memcpy(&b, &a, sizeof b); return b;
 #endif
 }
+MPPI_HD int float_bits(float a) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(a);
+#else
+    int b; memcpy(&b, &a, sizeof b); return b;
+#endif
+}
+MPPI_HD float xor_high(float a, unsigned int mask) {
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(__float_as_int(a) ^ (int)mask);
+#else
+    unsigned int b; memcpy(&b, &a, sizeof b); b ^= mask; memcpy(&a, &b, sizeof b); return a;
+#endif
+}
 // low 32 bits of a double; v with the bits of `mask` (bit 31 = sign) flipped in its high word
 MPPI_HD int low_word(double a) {
 #if defined(__CUDA_ARCH__)

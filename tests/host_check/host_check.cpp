@@ -63,6 +63,9 @@ void host_sincos_poly(int n, const double *a, double *s, double *c) {
     static const FastModel<double> F = make_fast_model<double>();
     for (int i = 0; i < n; i++) sincos_poly(F.trig, a[i], &s[i], &c[i]);
 }
+void host_sincos_poly_f32(int n, const float *a, float *s, float *c) {
+    for (int i = 0; i < n; i++) sincos_poly((const float *)nullptr, a[i], &s[i], &c[i]);
+}
 int host_fast_structure_matches() { std::string w; return fast_structure_matches(&w) ? 1 : 0; }
 int host_topology_matches() { std::string w; return topology_matches(&w) ? 1 : 0; }
 }

@@ -49,6 +49,21 @@ def test_device_sincos_matches_libm(hc):
     assert np.abs(s * s + c * c - 1.0).max() <= 5e-16
 
 
+def test_device_sincos_f32_matches_libm(hc):
+    rng = np.random.default_rng(4)
+    a = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-3000, 3000, 50000), rng.uniform(-1e5, 1e5, 50000), np.arange(-64, 65) * (np.pi / 4), [0.0, -0.0]]).astype(np.float32)
+    s, c = np.zeros_like(a), np.zeros_like(a)
+    fp = C.POINTER(C.c_float)
+    hc.host_sincos_poly_f32.argtypes = [C.c_int, fp, fp, fp]
+    hc.host_sincos_poly_f32(a.size, a.ctypes.data_as(fp), s.ctypes.data_as(fp), c.ctypes.data_as(fp))
+    assert np.abs(s - np.sin(a.astype(np.float64))).max() <= 1.2e-7 and np.abs(c - np.cos(a.astype(np.float64))).max() <= 1.2e-7
+    assert (s[a == 0.0] == 0.0).all() and (c[a == 0.0] == 1.0).all()
+    bad = np.array([np.inf, -np.inf, np.nan], np.float32)
+    s3, c3 = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    hc.host_sincos_poly_f32(3, bad.ctypes.data_as(fp), s3.ctypes.data_as(fp), c3.ctypes.data_as(fp))
+    assert np.isnan(s3).all() and np.isnan(c3).all()
+
+
 def test_topology_matches_generated_model(hc):
     assert hc.host_topology_matches() == 1
 
