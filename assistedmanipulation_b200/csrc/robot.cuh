@@ -138,16 +138,55 @@ template <class R, int I> MPPI_HD void joint_transform(const RobotModel<R> &M, R
     }
 }
 
+// ---- PLANE: the transforms of joints 0..9 by their structure ---------------------------------------------------------
+// FUSED mode has the step's joint sines / cosines at hand and (checked by fast_structure_matches at engine creation)
+// joints 0, 1 translate along x / y without rotating, joint 2 is Rz(q) in place, and every arm joint is Rx(alpha) Rz(q)
+// behind a fixed translation: motions and forces cross a joint by two plane rotations (8 operations per vector) and one
+// cross product instead of two 3x3 products (30), and no transform matrix is formed. The fingers keep the generic path.
+template <class R, int I> MPPI_HD Vec3<R> joint_offset(const RobotModel<R> &M, const R *q) {
+    if (I == 0) return v3<R>(q[0] * M.sign[0], R(0), R(0));
+    if (I == 1) return v3<R>(R(0), q[1] * M.sign[1], R(0));
+    return v3<R>(M.place_p[I][0], M.place_p[I][1], M.place_p[I][2]);
+}
+template <class R, int I> MPPI_HD Vec3<R> rot_to_joint(const RobotModel<R> &M, const R *cs, const R *sn, const Vec3<R> &v) {   // E^T v
+    if (I < 2) return v;
+    if (I == 2) return rotz_t(cs[2], sn[2], v);
+    return rotz_t(cs[I], sn[I], rotx_t(M.place_R[I][4], M.place_R[I][7], v));
+}
+template <class R, int I> MPPI_HD Vec3<R> rot_to_parent(const RobotModel<R> &M, const R *cs, const R *sn, const Vec3<R> &v) {   // E v
+    if (I < 2) return v;
+    if (I == 2) return rotz(cs[2], sn[2], v);
+    return rotx(M.place_R[I][4], M.place_R[I][7], rotz(cs[I], sn[I], v));
+}
+template <class R, int I> MPPI_HD Mot<R> act_inv_joint(const RobotModel<R> &M, const R *q, const R *cs, const R *sn, const Mot<R> &m) {
+    Mot<R> o;
+    o.v = rot_to_joint<R, I>(M, cs, sn, (I == 2) ? m.v : cross_sub(joint_offset<R, I>(M, q), m.w, m.v));
+    o.w = rot_to_joint<R, I>(M, cs, sn, m.w);
+    return o;
+}
+template <class R, int I> MPPI_HD Frc<R> act_joint(const RobotModel<R> &M, const R *q, const R *cs, const R *sn, const Frc<R> &f) {
+    Frc<R> o;
+    o.f = rot_to_parent<R, I>(M, cs, sn, f.f);
+    const Vec3<R> n = rot_to_parent<R, I>(M, cs, sn, f.n);
+    o.n = (I == 2) ? n : cross_add(joint_offset<R, I>(M, q), o.f, n);
+    return o;
+}
+
 // ---- pass 1: transforms, velocities, RNEA forces ----------------------------------------------
-template <class R, int I, bool VEL, bool NLE, bool BIAS>
+template <class R, int I, bool VEL, bool NLE, bool BIAS, bool PLANE = false>
 MPPI_HD void pass1(const RobotModel<R> &M, const R *q, const R *qd, Scratch<R> &S, Mot<R> *agf, const R *cs = nullptr, const R *sn = nullptr) {
     constexpr int P = Joint<I>::parent, T = Joint<I>::type;
+    constexpr bool PL = PLANE && I <= 9;   // this joint's transform by its structure (no matrix formed)
     const R sg = M.sign[I];
-    joint_transform<R, I>(M, q[I] * sg, S.li[I], cs, sn);
+    if (!PL) joint_transform<R, I>(M, q[I] * sg, S.li[I], cs, sn);
     if (VEL) {
         const R w = qd[I] * sg;
         Mot<R> vj = joint_motion<R, T>(w);
-        if (P >= 0) { Mot<R> vp = act_inv(S.li[I], S.v[P < 0 ? 0 : P]); S.v[I].v = vp.v + vj.v; S.v[I].w = vp.w + vj.w; }
+        if (P >= 0) {
+            Mot<R> vp;
+            if (PL) vp = act_inv_joint<R, I>(M, q, cs, sn, S.v[P < 0 ? 0 : P]); else vp = act_inv(S.li[I], S.v[P < 0 ? 0 : P]);
+            S.v[I].v = vp.v + vj.v; S.v[I].w = vp.w + vj.w;
+        }
         else S.v[I] = vj;
         if (NLE || BIAS) {
             S.c[I] = cross_joint<R, T>(S.v[I], w);
@@ -155,7 +194,8 @@ MPPI_HD void pass1(const RobotModel<R> &M, const R *q, const R *qd, Scratch<R> &
             Frc<R> vxh = fcross(S.v[I], h);
             if (NLE) {
                 Mot<R> ap;
-                if (P >= 0) ap = act_inv(S.li[I], agf[P < 0 ? 0 : P]);
+                if (P >= 0) { if (PL) ap = act_inv_joint<R, I>(M, q, cs, sn, agf[P < 0 ? 0 : P]); else ap = act_inv(S.li[I], agf[P < 0 ? 0 : P]); }
+                else if (PL) { ap.v = v3<R>(R(0), R(0), M.gravity); ap.w = v3<R>(R(0), R(0), R(0)); }   // the root joint does not rotate
                 else { ap.v = tmul(S.li[I].R_, v3<R>(R(0), R(0), M.gravity)); ap.w = v3<R>(R(0), R(0), R(0)); }
                 agf[I].v = ap.v + S.c[I].v; agf[I].w = ap.w + S.c[I].w;
                 Frc<R> ya = body_mul(M, I, agf[I]);
@@ -164,19 +204,20 @@ MPPI_HD void pass1(const RobotModel<R> &M, const R *q, const R *qd, Scratch<R> &
             if (BIAS) S.pA[I] = vxh;
         }
     }
-    if (I + 1 < NJ) pass1<R, (I + 1 < NJ ? I + 1 : I), VEL, NLE, BIAS>(M, q, qd, S, agf, cs, sn);
+    if (I + 1 < NJ) pass1<R, (I + 1 < NJ ? I + 1 : I), VEL, NLE, BIAS, PLANE>(M, q, qd, S, agf, cs, sn);
 }
 
 // ---- RNEA backward: nle_i = S^T f_i ; f_parent += X f_i ----------------------------------------
-template <class R, int I> MPPI_HD void rnea_back(const RobotModel<R> &M, Scratch<R> &S, R *nle) {
+template <class R, int I, bool PLANE = false> MPPI_HD void rnea_back(const RobotModel<R> &M, Scratch<R> &S, R *nle, const R *q = nullptr, const R *cs = nullptr, const R *sn = nullptr) {
     constexpr int P = Joint<I>::parent, T = Joint<I>::type;
     nle[I] = joint_dot<R, T>(S.f[I]) * M.sign[I];
     if (P >= 0) {
-        Frc<R> fp = act(S.li[I], S.f[I]);
+        Frc<R> fp;
+        if (PLANE && I <= 9) fp = act_joint<R, I>(M, q, cs, sn, S.f[I]); else fp = act(S.li[I], S.f[I]);
         S.f[P < 0 ? 0 : P].f = S.f[P < 0 ? 0 : P].f + fp.f;
         S.f[P < 0 ? 0 : P].n = S.f[P < 0 ? 0 : P].n + fp.n;
     }
-    if (I > 0) rnea_back<R, (I > 0 ? I - 1 : 0)>(M, S, nle);
+    if (I > 0) rnea_back<R, (I > 0 ? I - 1 : 0), PLANE>(M, S, nle, q, cs, sn);
 }
 
 // A P^ and P^ A helpers, P^ = [p]x
@@ -307,10 +348,30 @@ MPPI_HD void aba_fwd(const RobotModel<R> &M, Scratch<R> &S, Mot<R> *a, R *qdd) {
 }
 
 // ---- world kinematics for the objective ----------------------------------------------------------
-template <class R, int I, int FLAGS>
-MPPI_HD void world_chain(const RobotModel<R> &M, const Scratch<R> &S, Xf<R> &oM, Kinematics<R> &K, R *Jl /* 3 x 7 */) {
+template <class R, int I, int FLAGS, bool PLANE = false>
+MPPI_HD void world_chain(const RobotModel<R> &M, const Scratch<R> &S, Xf<R> &oM, Kinematics<R> &K, R *Jl /* 3 x 7 */, const R *q = nullptr, const R *cs = nullptr, const R *sn = nullptr) {
     // oM enters as oMi[I-1], leaves as oMi[I]
-    if (I == 0) oM = S.li[0];
+    if (PLANE) {
+        if (I == 0) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) oM.R_.m[k] = (k % 4 == 0) ? R(1) : R(0);
+            oM.p = joint_offset<R, 0>(M, q);
+        } else if (I == 1) {
+            oM.p.y = q[1] * M.sign[1];
+        } else if (I == 2) {   // Rz(q2) itself: the frame above does not rotate
+            oM.R_.m[0] = cs[2]; oM.R_.m[1] = -sn[2]; oM.R_.m[3] = sn[2]; oM.R_.m[4] = cs[2];
+        } else {
+            oM.p = mul(oM.R_, joint_offset<R, I>(M, q)) + oM.p;
+            // R <- R Rx(alpha) Rz(theta): two column rotations (24 operations; the 3x3 product is 45)
+            const R ca = M.place_R[I][4], sa = M.place_R[I][7], c = cs[I], s = sn[I];
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const R a = oM.R_(r, 0), b = oM.R_(r, 1), d = oM.R_(r, 2);
+                const R b1 = ca * b + sa * d, d1 = ca * d - sa * b;
+                oM.R_(r, 0) = c * a + s * b1; oM.R_(r, 1) = c * b1 - s * a; oM.R_(r, 2) = d1;
+            }
+        }
+    } else if (I == 0) oM = S.li[0];
     else {
         Xf<R> n;
         n.R_ = matmul(oM.R_, S.li[I].R_);
@@ -328,24 +389,27 @@ MPPI_HD void world_chain(const RobotModel<R> &M, const Scratch<R> &S, Xf<R> &oM,
         K.ee_pos = mul(oM.R_, v3<R>(M.ee_p[0], M.ee_p[1], M.ee_p[2])) + oM.p;
         if (FLAGS & KIN_VEL) K.ee_lin_vel = mul(oM.R_, S.v[9].v) + cross(oM.p, mul(oM.R_, S.v[9].w));
     }
-    if (I < 9) world_chain<R, (I < 9 ? I + 1 : I), FLAGS>(M, S, oM, K, Jl);
+    if (I < 9) world_chain<R, (I < 9 ? I + 1 : I), FLAGS, PLANE>(M, S, oM, K, Jl, q, cs, sn);
 }
 
 // One PinocchioDynamics::calculate(): accelerations + the kinematics the objective will read.
 //   u      : generalised forces commanded by the control, tau = [0,0,0,u3..u9,0,0] (pinocchio_dynamics.cpp:238-239)
 //   FUSED  : a = M^-1 u
 //   NLE    : also produce nle(q, qd) (needed for tau^T v of the energy tank, or in FAITHFUL mode)
-template <class R, bool FAITHFUL, bool NLE, int FLAGS, bool DO_ABA = true>
+//   PLANE  : cs / sn hold the joint sines / cosines and joints 0..9 are crossed by their structure (see act_inv_joint);
+//            only with DO_ABA = false (the generic solver reads the transform matrices PLANE does not form)
+template <class R, bool FAITHFUL, bool NLE, int FLAGS, bool DO_ABA = true, bool PLANE = false>
 MPPI_HD void robot_calculate(const RobotModel<R> &M, const R *q, const R *qd, const R *u, R *qdd, R *nle, Kinematics<R> &K, const R *cs = nullptr, const R *sn = nullptr) {
+    static_assert(!(PLANE && DO_ABA), "PLANE forms no transform matrices for the generic solver");
     Scratch<R> S;
     Mot<R> agf[NJ];
     constexpr bool NEED_NLE = NLE || FAITHFUL;
     constexpr bool VEL = NEED_NLE || (FLAGS & KIN_VEL);
-    pass1<R, 0, VEL, NEED_NLE, FAITHFUL>(M, q, qd, S, agf, cs, sn);
+    pass1<R, 0, VEL, NEED_NLE, FAITHFUL, PLANE>(M, q, qd, S, agf, cs, sn);
     {
         Xf<R> oM;
         R Jl[21];
-        world_chain<R, 0, FLAGS>(M, S, oM, K, Jl);
+        world_chain<R, 0, FLAGS, PLANE>(M, S, oM, K, Jl, q, cs, sn);
         if (FLAGS & KIN_MANIP) {
             R g[6];  // J J^T, symmetric: 00 01 02 11 12 22
             int n = 0;
@@ -363,7 +427,7 @@ MPPI_HD void robot_calculate(const RobotModel<R> &M, const R *q, const R *qd, co
         }
     }
     R tau[NJ];
-    if (NEED_NLE) rnea_back<R, NJ - 1>(M, S, nle);
+    if (NEED_NLE) rnea_back<R, NJ - 1, PLANE>(M, S, nle, q, cs, sn);
     if (!DO_ABA) return;  // the caller runs the structure-exploiting solver of robot_fast.cuh instead
 #pragma unroll
     for (int i = 0; i < NJ; i++) tau[i] = FAITHFUL ? (u[i] + nle[i]) : u[i];

@@ -336,7 +336,7 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
             qd[2] = u[2];
             // (carrying the end effector point inside the INERTIA loop was tried: +4 registers, spills, 4 % slower)
             // (LEAN: the end effector point rides the solver's forward loop as a second, independent dependency chain)
-            if constexpr (!LEAN) robot_calculate<R, false, POWER, KF, false>(M, q, qd, tau, qdd, nle, K, cs, sn);   // the joint sines / cosines are shared
+            if constexpr (!LEAN) robot_calculate<R, false, POWER, KF, false, true>(M, q, qd, tau, qdd, nle, K, cs, sn);   // the joint sines / cosines are shared
             aba_fused_fast<R, BIG ? 7 : kArmUnroll, LEAN>(F, q, cs, sn, tau, qdd, &K.ee_pos);
         }
 #pragma unroll

@@ -189,4 +189,20 @@ template <class R> MPPI_HD R std_min(R a, R b) { return (b < a) ? b : a; }
 template <class R> MPPI_HD R std_max(R a, R b) { return (a < b) ? b : a; }
 template <class R> MPPI_HD R std_clamp(R v, R lo, R hi) { return (v < lo) ? lo : ((hi < v) ? hi : v); }
 
+// a x b + c, each component one chain of two fused multiply-adds (the expression form is multiply, FMA, add)
+template <class R> MPPI_HD Vec3<R> cross_add(const Vec3<R> &a, const Vec3<R> &b, const Vec3<R> &c) {
+    return v3<R>(fma_(a.y, b.z, fma_(-a.z, b.y, c.x)), fma_(a.z, b.x, fma_(-a.x, b.z, c.y)), fma_(a.x, b.y, fma_(-a.y, b.x, c.z)));
+}
+// c - a x b
+template <class R> MPPI_HD Vec3<R> cross_sub(const Vec3<R> &a, const Vec3<R> &b, const Vec3<R> &c) {
+    return v3<R>(fma_(a.z, b.y, fma_(-a.y, b.z, c.x)), fma_(a.x, b.z, fma_(-a.z, b.x, c.y)), fma_(a.y, b.x, fma_(-a.x, b.y, c.z)));
+}
+
+// ---- plane rotations ------------------------------------------------------------------------------
+template <class R> MPPI_HD Vec3<R> rotz(R c, R s, const Vec3<R> &v) { return v3<R>(c * v.x - s * v.y, s * v.x + c * v.y, v.z); }
+template <class R> MPPI_HD Vec3<R> rotz_t(R c, R s, const Vec3<R> &v) { return v3<R>(c * v.x + s * v.y, c * v.y - s * v.x, v.z); }
+template <class R> MPPI_HD Vec3<R> rotx(R c, R s, const Vec3<R> &v) { return v3<R>(v.x, c * v.y - s * v.z, s * v.y + c * v.z); }
+template <class R> MPPI_HD Vec3<R> rotx_t(R c, R s, const Vec3<R> &v) { return v3<R>(v.x, c * v.y + s * v.z, c * v.z - s * v.y); }
+
+
 }  // namespace mppi_b200

@@ -27,7 +27,33 @@ static void calc(const double *q, const double *qd, const double *u, double *qdd
     for (int l = 0; l < 8; l++) { *k++ = K.link_com[l].x; *k++ = K.link_com[l].y; *k++ = K.link_com[l].z; }
 }
 
+// what the FUSED rollout step runs: kinematics / RNEA crossing joints 0..9 by their structure (PLANE) with shared joint
+// sines / cosines, then the structure-exploiting solver (EE variant of the lean kernel checked through `ee3`)
+template <class R>
+static void calc_plane(const double *q, const double *qd, const double *u, double *qdd, double *nle, double *kin, double *ee3) {
+    static const RobotModel<R> M = make_robot_model<R>();
+    static const FastModel<R> F = make_fast_model<R>();
+    R q_[12], qd_[12], u_[12], qdd_[12], nle_[12], cs[12], sn[12];
+    for (int i = 0; i < 12; i++) { q_[i] = (R)q[i]; qd_[i] = (R)qd[i]; u_[i] = (R)u[i]; nle_[i] = 0; }
+    joint_sincos<R>(F, q_, cs, sn);
+    Kinematics<R> K;
+    robot_calculate<R, false, true, KIN_MOUNT | KIN_VEL | KIN_MANIP | KIN_LINKS, false, true>(M, q_, qd_, u_, qdd_, nle_, K, cs, sn);
+    Vec3<R> ee;
+    aba_fused_fast<R, 1, true>(F, q_, cs, sn, u_, qdd_, &ee);
+    for (int i = 0; i < 12; i++) { qdd[i] = qdd_[i]; nle[i] = nle_[i]; }
+    double *k = kin;
+    *k++ = K.ee_pos.x; *k++ = K.ee_pos.y; *k++ = K.ee_pos.z;
+    *k++ = K.mount_pos.x; *k++ = K.mount_pos.y; *k++ = K.mount_pos.z;
+    *k++ = K.ee_lin_vel.x; *k++ = K.ee_lin_vel.y; *k++ = K.ee_lin_vel.z;
+    *k++ = K.manip_det;
+    for (int l = 0; l < 8; l++) { *k++ = K.link_com[l].x; *k++ = K.link_com[l].y; *k++ = K.link_com[l].z; }
+    ee3[0] = ee.x; ee3[1] = ee.y; ee3[2] = ee.z;
+}
+
 extern "C" {
+void host_robot_calculate_plane(int f32, const double *q, const double *qd, const double *u, double *qdd, double *nle, double *kin34, double *ee3) {
+    if (f32) calc_plane<float>(q, qd, u, qdd, nle, kin34, ee3); else calc_plane<double>(q, qd, u, qdd, nle, kin34, ee3);
+}
 // mode: bit0 = FAITHFUL, bit1 = NLE requested, bit2 = float
 void host_robot_calculate(int mode, const double *q, const double *qd, const double *u, double *qdd, double *nle, double *kin34) {
     switch (mode) {

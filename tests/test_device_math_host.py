@@ -114,6 +114,36 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("f32,tol", [(0, 1e-12), (1, 5e-5)])
+def test_fused_step_by_joint_structure_matches_oracle(oracle, hc, f32, tol):
+    """What the FUSED rollout step executes — kinematics / RNEA crossing joints 0..9 by their structure (PLANE, robot.cuh)
+    on the shared polynomial sines / cosines, and the solver that also carries the end effector point — against the
+    oracle's generic recursion: accelerations, nonlinear effects, every kinematic quantity the objectives read."""
+    rng = np.random.default_rng(7)
+    hc.host_robot_calculate_plane.argtypes = [C.c_int] + [_dp] * 7
+    for _ in range(8):
+        q, v, u = rng.uniform(-1.5, 1.5, 12), rng.uniform(-1, 1, 12), np.zeros(12)
+        q[10:] = rng.uniform(0.0, 0.04, 2)
+        u[3:10] = rng.uniform(-10, 10, 7)
+        nle, a = np.zeros(12), np.zeros(12)
+        oracle.oracle_robot_nle(ol.ptr(q), ol.ptr(v), ol.ptr(nle))
+        tau = u + nle
+        oracle.oracle_robot_aba(ol.ptr(q), ol.ptr(v), ol.ptr(tau), ol.ptr(a))
+        pos, lin, ang, J = np.zeros(3), np.zeros(3), np.zeros(3), np.zeros(72)
+        oracle.oracle_robot_kinematics(ol.ptr(q), ol.ptr(v), ol.ptr(pos), ol.ptr(lin), ol.ptr(ang), ol.ptr(J))
+        Ja = J.reshape(6, 12)[:3, 3:10]
+        ee, mt, lc = np.zeros(3), np.zeros(3), np.zeros(39)
+        oracle.oracle_robot_fk(ol.ptr(q), ol.ptr(ee), ol.ptr(mt), ol.ptr(lc))
+        qdd, n2, kin, ee3 = np.zeros(12), np.zeros(12), np.zeros(34), np.zeros(3)
+        hc.host_robot_calculate_plane(f32, ol.ptr(q), ol.ptr(v), ol.ptr(u), ol.ptr(qdd), ol.ptr(n2), ol.ptr(kin), ol.ptr(ee3))
+        assert np.abs(qdd - a).max() <= tol * np.abs(a).max()
+        assert np.abs(n2 - nle).max() <= tol * max(np.abs(nle).max(), 1.0)
+        assert np.abs(kin[:3] - pos).max() <= tol and np.abs(ee3 - pos).max() <= tol and np.abs(kin[3:6] - mt).max() <= tol
+        assert np.abs(kin[6:9] - lin).max() <= tol * 10
+        assert abs(kin[9] - np.linalg.det(Ja @ Ja.T)) <= max(tol, 1e-10) * 10 * abs(np.linalg.det(Ja @ Ja.T)) + tol * 1e-3
+        assert np.abs(kin[10:].reshape(8, 3) - lc.reshape(13, 3)[3:11]).max() <= tol
+
+
 def _track_point_full():
     tp = abi.default_track_point()
     tp.enable_self_collision_avoidance, tp.enable_reach_limits, tp.link_position_mode = 1, 1, abi.LINKS_BODY_COM
