@@ -142,6 +142,7 @@ def main():
     total_c = total_n = 0.0
     fp64 = 0.0
     by_line = {}
+    mix = {}
     # issue-time walk: an instruction issues `stall` cycles after its predecessor, and an FP64 instruction not before
     # the FP64 pipe of the sub-partition is free again (one warp instruction per 2 cycles, tools/microbench/dfma_issue.cu);
     # the second condition is enforced by the hardware, not by the stall field (back-to-back DADDs carry a stall of 1)
@@ -164,6 +165,9 @@ def main():
         e[0] += w * cost(ins[k]); e[1] += w
         if is_fp64(ins[k]):
             fp64 += w
+        if not ins[k].get("skipped"):
+            o = opcode(ins[k]["text"]).split(".")[0]
+            mix[o] = mix.get(o, 0) + w
     total_c = seg_c[outer] + sum(a.trip * seg_c[r] for r in inner)
     s = summarize(ins, *outer)
     print("step loop [%#x..%#x]: %d static instructions, %d static stall cycles, %d with scoreboard waits" % (ins[outer[0]]["addr"], ins[outer[1]]["addr"], s["n"], s["cycles"], s["waits"]))
@@ -173,6 +177,9 @@ def main():
             ins[r[0]]["addr"], ins[r[1]]["addr"], t["n"], t["cycles"], seg_c[r], t["ops"].get("DFMA", 0), t["ops"].get("DMUL", 0), t["ops"].get("DADD", 0),
             t["ops"].get("LDL", 0), t["ops"].get("STL", 0)))
     print("per step with %d trips per inner loop: %.0f instructions (%.0f FP64), %.0f cycles (stall fields + FP64 pipe occupancy); FP64 issue floor %.0f" % (a.trip, total_n, fp64, total_c, a.fp64_issue * fp64))
+    fl = {k: mix.get(k, 0) for k in ("DFMA", "DMUL", "DADD", "FFMA", "FMUL", "FADD", "MUFU")}
+    print("arithmetic per step: " + ", ".join("%s %d" % kv for kv in fl.items() if kv[1]) + "; flops %d (FP64) %d (FP32)" % (
+        2 * fl["DFMA"] + fl["DMUL"] + fl["DADD"], 2 * fl["FFMA"] + fl["FMUL"] + fl["FADD"]))
     for (f, ln), (c, n) in sorted(by_line.items(), key=lambda kv: -kv[1][0])[:a.lines]:
         print("  %6.0f cycles %5.0f instructions  %s:%d" % (c, n, f, ln))
     if a.dump:
