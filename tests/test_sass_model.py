@@ -1,0 +1,39 @@
+"""tools/sass_cycles.py — the static issue-cycle model of DESIGN.md section 5 — run on the objects build() leaves in
+csrc/build (nvcc cross-compiles here; no GPU involved). Pins the numbers the documentation quotes to a band, so a
+change that silently loses the kernel's schedule (the inertia loop's is fragile) fails a CPU test."""
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OBJ = os.path.join(ROOT, "assistedmanipulation_b200", "csrc", "build")
+
+
+def _model(obj, pattern, *extra):
+    path = os.path.join(OBJ, obj)
+    if not os.path.exists(path) or not shutil.which("nvdisasm") or not shutil.which("cuobjdump"):
+        pytest.skip("needs the built objects and the CUDA binary utilities")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_cycles.py"), path, pattern, *extra], check=True, capture_output=True, text=True).stdout
+    m = re.search(r"per step with 7 trips per inner loop: (\d+) instructions \((\d+) FP64\), (\d+) cycles .*floor (\d+)", out)
+    assert m, out
+    return tuple(int(v) for v in m.groups()), out
+
+
+def test_config2_kernel_stays_near_its_fp64_issue_floor():
+    (instr, fp64, cycles, floor), out = _model("k_rollout_f64.o", "Li1ELb0ENS_11TrackPointPIdEELb0EEE")
+    assert floor == 2 * fp64
+    assert 2000 <= fp64 <= 2300, out          # 2585 before the round's second half
+    assert instr <= 3100 and cycles <= 5600, out   # 3668 instructions / 7597 cycles before; 5250 with the guarded slow path counted
+    assert cycles <= 1.30 * floor, out
+    assert "1 loops" not in out and "inner loop" in out     # the inertia pass is a loop body in this build
+
+
+def test_unrolled_and_assisted_kernels_keep_their_instruction_counts():
+    (instr, fp64, _, _), out = _model("k_rollout_f64.o", "Li1ELb0ENS_11TrackPointPIdEELb1EEE")
+    assert instr <= 2650 and fp64 <= 2100, out     # 3120 / 2515 before
+    (instr, _, cycles, _), out = _model("k_rollout_f32.o", "IfLi4ELb0ENS_9AssistedPIfEELb0EEE", "--fp64-issue", "1")
+    assert instr <= 6200 and cycles <= 8500, out   # 8832 / 18154 before
