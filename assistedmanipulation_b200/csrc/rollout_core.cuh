@@ -145,14 +145,15 @@ template <class R, bool LEAN = false> MPPI_HD R track_point_cost(const TrackPoin
         // side is violated, so ONE penalty is formed per joint, of the negative one of (q - lo, hi - q) — its square is
         // the square of the reference's (lo - q) or (q - hi) — and both selections read the sign bit on the integer
         // pipe (an FP64 comparison occupies the FP64 pipe and delivers its predicate ~13 cycles later). Same values and
-        // order of additions for every finite state; a NaN joint makes the end effector term NaN either way.
+        // order of additions for every state (a NaN joint is "not negative" on either side, as in the reference's
+        // comparisons; the end effector term then makes the rollout NaN one step later).
         R c[2] = {R(0), R(0)};   // two partial sums: half the dependent additions (the sum differs from the sequential one by rounding only)
 #pragma unroll
         for (int i = 0; i < 10; i++) {
             const R below = q[i] - P.lim_lo[i], above = P.lim_hi[i] - q[i];
-            const R m = (sign_word(below) & 0x80000000u) ? below : above;
+            const R m = is_negative(below) ? below : above;
             const R penalty = R(1000) + R(100000) * (m * m);
-            c[i & 1] += (sign_word(m) & 0x80000000u) ? penalty : R(0);
+            c[i & 1] += is_negative(m) ? penalty : R(0);
         }
         cost += c[0] + c[1];
     }

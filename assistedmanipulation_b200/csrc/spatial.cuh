@@ -143,6 +143,10 @@ MPPI_HD unsigned int sign_word(float a) {
     unsigned int b; memcpy(&b, &a, sizeof b); return b;
 #endif
 }
+// x < 0 decided on the integer pipe: sign bit set and not a NaN (-inf and -0 included; -0 never arises from a difference
+// of finite numbers). Same truth value as the FP comparison for every non-zero x, NaN included (false).
+MPPI_HD bool is_negative(double x) { return (sign_word(x) ^ 0x80000000u) <= 0x7ff00000u; }
+MPPI_HD bool is_negative(float x) { return (sign_word(x) ^ 0x80000000u) <= 0x7f800000u; }
 MPPI_HD int float_bits(float a) {
 #if defined(__CUDA_ARCH__)
     return __float_as_int(a);
