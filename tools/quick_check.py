@@ -2,9 +2,11 @@
 import sys, time, numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 t0 = time.time()
-import __graft_entry__ as g
-g.smoke()
-print('smoke %.1f s' % (time.time() - t0), flush=True)
+ONLY_CFG2 = '--cfg2-only' in sys.argv
+if not ONLY_CFG2:
+    import __graft_entry__ as g
+    g.smoke()
+    print('smoke %.1f s' % (time.time() - t0), flush=True)
 import engine_lib as el
 import cases
 from assistedmanipulation_b200 import abi
@@ -28,6 +30,9 @@ def run(label, obj, params, K, hor, prec, x0, wrench=None, n=40):
     e.close()
 x = abi.huddled_state()
 run('cfg2 f64', abi.OBJECTIVE_TRACK_POINT, abi.default_track_point(), 4096, 0.64, abi.FP64, x)
+if ONLY_CFG2:
+    print('total %.1f s' % (time.time() - t0), flush=True)
+    sys.exit(0)
 run('big f64', abi.OBJECTIVE_TRACK_POINT, abi.default_track_point(), 131072, 0.64, abi.FP64, x, n=10)
 run('cfg3 f32', abi.OBJECTIVE_ASSISTED_MANIPULATION, cases.assisted_params(True, 1), 16384, 1.28, abi.FP32, abi.huddled_state(10.0), cases.constant_wrench(128), n=12)
 run('cfg2 f32', abi.OBJECTIVE_TRACK_POINT, abi.default_track_point(), 4096, 0.64, abi.FP32, x)
