@@ -4,8 +4,10 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.cuh"
+#include "sample_core.cuh"
 
 namespace mppi_b200 {
 
@@ -27,29 +29,6 @@ __device__ __forceinline__ double decode_ordered(unsigned long long e) {
 }
 cudaError_t launch_rollout_f64(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s);
 cudaError_t launch_rollout_f32(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s);
-
-// ---- Philox4x32-10 (Salmon et al. 2011), key = seed, counter = (column lo, column hi, block, update) --
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-        const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
-    }
-    return ctr;
-}
-// two uniforms -> two standard normals (Box–Muller, single precision arithmetic; noise only needs
-// to be N(0,1) and reproducible, and the exact values are read back for any parity check)
-__device__ __forceinline__ void box_muller(unsigned a, unsigned b, float *z0, float *z1) {
-    const float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;  // (0,1]
-    const float u2 = ((float)b + 0.5f) * 2.3283064365386963e-10f;
-    // MUFU-based log / sqrt / sin / cos: the angle 2*pi*u2 - pi stays in [-pi, pi] where __sincosf is accurate to 2^-21
-    const float r = __fsqrt_rn(-2.0f * __logf(u1));
-    float s, c;
-    __sincosf(6.283185307179586f * u2 - 3.14159265358979f, &s, &c);
-    *z0 = r * c; *z1 = r * s;
-}
 
 // ---- prepare: time shift of the optimal control, rollout 1 = -U_prev, reset of the reductions -------
 // mppi.cpp:194-206 (shift), :269 (rollout[1].noise = -m_optimal_control, the UNSHIFTED optimum).
@@ -241,6 +220,30 @@ template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sa
         for (size_t i = nvec * VN + threadIdx.x; i < span; i += blockDim.x) dst[i] = tile[i];
     } else {
         for (size_t i = threadIdx.x; i < span; i += blockDim.x) dst[i] = tile[i];
+    }
+}
+
+// K1 for a diagonal transform and NU % 4 == 0 (every Franka + Ridgeback configuration): one thread per Philox block
+// = four consecutive values (sample_core.cuh), so a warp writes 32 consecutive quads straight from registers — no
+// staging tile (its column-strided 8-byte stores were 4-way bank conflicts), no barrier, a third of the Philox /
+// Box–Muller chain per thread, 32-bit index arithmetic, and kept rollouts are skipped instead of rewritten.
+// Same counters and the same arithmetic as k_sample: the noise is bit-identical.
+template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sample_quads(const __grid_constant__ DeviceState dg) {
+    const DeviceState d = controller_view(dg, blockIdx.y);
+    if (blockIdx.x == gridDim.x - 1) { prepare_block(d); return; }
+    const long long quads = d.k_count * d.T * (NU / 4);
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= quads) return;
+    long long kl; int t, b;
+    quad_coordinates<NU>(g, quads, d.T, &kl, &t, &b);
+    R v[4];
+    if (!sample_quad<R, RI, NU>(d, dg.Ldiag, kl, t, b, v)) return;
+    R *dst = static_cast<R *>(d.noise) + (size_t)g * 4;   // 16-byte aligned: the buffer is, and nu*T % 4 == 0
+    if constexpr (sizeof(R) == 8) {
+        reinterpret_cast<double2 *>(dst)[0] = make_double2((double)v[0], (double)v[1]);
+        reinterpret_cast<double2 *>(dst)[1] = make_double2((double)v[2], (double)v[3]);
+    } else {
+        *reinterpret_cast<float4 *>(dst) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
     }
 }
 
@@ -682,6 +685,16 @@ template <class R, class RI, int NU> static cudaError_t sample_tt(const DeviceSt
         ++*launches;
     }
     const long long ncols = d.k_count * d.T;
+    if constexpr (NU % 4 == 0) {
+        // MPPI_B200_SAMPLE_TILE=1 keeps the general kernel (A/B measurements)
+        static const bool tile_only = std::getenv("MPPI_B200_SAMPLE_TILE") && std::getenv("MPPI_B200_SAMPLE_TILE")[0] == '1';
+        if (d.L_is_diagonal && !tile_only) {
+            const long long quads = ncols * (NU / 4);
+            k_sample_quads<R, RI, NU><<<dim3((unsigned)((quads + 255) / 256) + 1, d.batch), 256, 0, s>>>(d);   // + the prepare block
+            ++*launches;
+            return cudaGetLastError();
+        }
+    }
     const unsigned grid = (unsigned)((ncols + 255) / 256);
     const size_t tile = sizeof(R) * 256 * (size_t)NU;
     k_sample<R, RI, NU><<<dim3(grid + 1, d.batch), 256, tile, s>>>(d);   // + the prepare block
