@@ -22,7 +22,7 @@ INS = re.compile(r"^\s*/\*([0-9a-f]{4,})\*/\s+(.*?);\s*/\* 0x([0-9a-f]{16}) \*/"
 HI = re.compile(r"^\s*/\* 0x([0-9a-f]{16}) \*/")
 
 
-def disassemble(path, pattern):
+def disassemble(path, pattern, inline=False):
     tmp = None
     if not path.endswith(".cubin"):
         tmp = tempfile.mkdtemp()
@@ -30,7 +30,7 @@ def disassemble(path, pattern):
         cubins = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")]
         assert cubins, "no cubin in " + path
         path = cubins[0]
-    text = subprocess.run(["nvdisasm", "-hex", "-g", path], check=True, capture_output=True, text=True).stdout.splitlines()
+    text = subprocess.run(["nvdisasm", "-hex", "-g"] + (["-gi"] if inline else []) + [path], check=True, capture_output=True, text=True).stdout.splitlines()
     funcs, cur, name = {}, None, None
     for line in text:
         m = re.match(r"^\s*\.section\s+\.text\.(\S+?),", line)
@@ -52,12 +52,22 @@ def parse(lines):
     """-> list of dicts(addr, text, stall, yield_, wbar, rbar, wait, label) in program order"""
     out, labels, pending = [], {}, None
     where = ("?", 0)
+    chain, in_chain = [], False   # with -gi: innermost frame first, every "inlined at" caller after it
     i = 0
     while i < len(lines):
         line = lines[i]
         mf = re.match(r'^\s*//## File "([^"]+)", line (\d+)', line)
         if mf:
-            where = (os.path.basename(mf.group(1)), int(mf.group(2)))
+            if not in_chain:
+                chain = []
+            in_chain = True
+            frame = (os.path.basename(mf.group(1)), int(mf.group(2)))
+            if not chain or chain[-1] != frame:
+                chain.append(frame)
+            where = chain[0]
+            i += 1
+            continue
+        in_chain = False
         ml = re.match(r"^(\.L_x_\d+):", line)
         if ml:
             pending = ml.group(1)
@@ -65,7 +75,7 @@ def parse(lines):
         if m:
             hi = int(HI.match(lines[i + 1]).group(1), 16)
             ins = dict(addr=int(m.group(1), 16), text=m.group(2).strip(), stall=(hi >> 41) & 0xF, yield_=(hi >> 45) & 1,
-                       wbar=(hi >> 46) & 7, rbar=(hi >> 49) & 7, wait=(hi >> 52) & 0x3F, where=where)
+                       wbar=(hi >> 46) & 7, rbar=(hi >> 49) & 7, wait=(hi >> 52) & 0x3F, where=where, chain=tuple(chain))
             if pending:
                 labels[pending] = len(out)
                 pending = None
@@ -123,8 +133,10 @@ def main():
     ap.add_argument("--dump", action="store_true", help="print every instruction of the step loop with its stall field")
     ap.add_argument("--skip", default="", help="comma-separated file:line whose instructions are left out (slow paths behind forward branches)")
     ap.add_argument("--lines", type=int, default=0, help="print the N source lines with the most stall cycles per step (needs -lineinfo)")
+    ap.add_argument("--phases", default="", help="source file (e.g. rollout_core.cuh): attribute the step to the calls made from that file, through the inline chains (nvdisasm -gi)")
+    ap.add_argument("--phase-depth", type=int, default=2, help="how many frames below the call in --phases are listed")
     a = ap.parse_args()
-    name, lines = disassemble(a.path, a.pattern)
+    name, lines = disassemble(a.path, a.pattern, inline=bool(a.phases))
     ins, labels = parse(lines)
     skip = set(tuple([w.split(":")[0], int(w.split(":")[1])]) for w in a.skip.split(",") if w)
     for it in ins:
@@ -182,6 +194,37 @@ def main():
         2 * fl["DFMA"] + fl["DMUL"] + fl["DADD"], 2 * fl["FFMA"] + fl["FMUL"] + fl["FADD"]))
     for (f, ln), (c, n) in sorted(by_line.items(), key=lambda kv: -kv[1][0])[:a.lines]:
         print("  %6.0f cycles %5.0f instructions  %s:%d" % (c, n, f, ln))
+    if a.phases:
+        # outermost frame of the chain inside the given file = the call the step function makes; the frames below it
+        # (callee side) refine it
+        src = {}
+        def text_of(f, ln):
+            if f not in src:
+                cands = [os.path.join(dp, f) for dp, _, fs in os.walk(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "assistedmanipulation_b200")) if f in fs]
+                src[f] = open(cands[0]).read().splitlines() if cands else []
+            return src[f][ln - 1].strip()[:110] if 0 < ln <= len(src[f]) else ""
+        tree = {}
+        for k in range(outer[0], outer[1] + 1):
+            it = ins[k]
+            if it.get("skipped"):
+                continue
+            w = a.trip ** sum(1 for r in inner if r[0] <= k <= r[1])
+            ch = it["chain"]
+            idx = [j for j, fr in enumerate(ch) if fr[0] == a.phases]
+            key = [("(outside " + a.phases + ")", 0)] if not idx else [ch[j] for j in range(idx[-1], max(idx[-1] - a.phase_depth, -1), -1)]
+            node = tree
+            for fr in key:
+                node = node.setdefault(fr, dict(c=0.0, n=0.0, sub={}))
+                node["c"] += w * cost(it); node["n"] += w
+                node = node["sub"]
+        def show(node, indent):
+            for fr, v in sorted(node.items(), key=lambda kv: -kv[1]["n"]):
+                if v["n"] < 20 and indent:
+                    continue
+                print("%s%6.0f instructions %6.0f stall cycles  %s:%d  %s" % ("  " * indent, v["n"], v["c"], fr[0], fr[1], text_of(*fr) if fr[1] else ""))
+                show(v["sub"], indent + 1)
+        print("step by call site (inline chains):")
+        show(tree, 1)
     if a.dump:
         for k in range(outer[0], outer[1] + 1):
             it = ins[k]
