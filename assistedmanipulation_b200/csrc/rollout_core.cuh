@@ -84,17 +84,26 @@ template <class R> struct AssistedP {
 #define MPPI_PAIR_A(i) ((i) < 5 ? 0 : (i) < 10 ? 1 : (i) < 14 ? 2 : (i) < 17 ? 3 : (i) < 19 ? 4 : 5)
 #define MPPI_PAIR_B(i) ((i) < 5 ? 3 + (i) : (i) < 10 ? 3 + (i) - 5 : (i) < 14 ? 4 + (i) - 10 : (i) < 17 ? 5 + (i) - 14 : (i) < 19 ? 6 + (i) - 17 : 7)
 
+// The link-mode test sits OUTSIDE the pair loop: tested per pair (a uniform branch) every pair was its own basic block
+// and the twenty square roots / reciprocals ran one after the other (~48 cycles each in the static model, a sixth of the
+// assisted-manipulation step); as one block the scheduler overlaps them. Same operations, same order of additions.
 template <class R, bool FLIP> MPPI_HD R self_collision_cost(const BarrierP<R> &lim, const R *radii, int link_mode, const Kinematics<R> &K) {
+    R distance[20];
+    if (link_mode != 0) {
+#pragma unroll
+        for (int i = 0; i < 20; i++) {
+            const Vec3<R> d = K.link_com[MPPI_PAIR_A(i)] - K.link_com[MPPI_PAIR_B(i)];
+            distance[i] = sqrt_(dot(d, d));
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 20; i++) distance[i] = R(0);
+    }
     R cost = R(0);
 #pragma unroll
     for (int i = 0; i < 20; i++) {
-        R distance = R(0);
-        if (link_mode != 0) {
-            const Vec3<R> d = K.link_com[MPPI_PAIR_A(i)] - K.link_com[MPPI_PAIR_B(i)];
-            distance = sqrt_(dot(d, d));
-        }
         // track_point.cpp:140 uses radii - distance, assisted_manipulation.cpp:149 distance - radii
-        cost += left_barrier(lim, FLIP ? radii[i] - distance : distance - radii[i]);
+        cost += left_barrier(lim, FLIP ? radii[i] - distance[i] : distance[i] - radii[i]);
     }
     return cost;
 }
