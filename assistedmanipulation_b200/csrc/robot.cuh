@@ -143,6 +143,13 @@ template <class R, int I> MPPI_HD void joint_transform(const RobotModel<R> &M, R
 // joints 0, 1 translate along x / y without rotating, joint 2 is Rz(q) in place, and every arm joint is Rx(alpha) Rz(q)
 // behind a fixed translation: motions and forces cross a joint by two plane rotations (8 operations per vector) and one
 // cross product instead of two 3x3 products (30), and no transform matrix is formed. The fingers keep the generic path.
+// Structural zeros of those offsets (bit k set = component k can be non-zero): the sliders move along one axis, the arm
+// joints' fixed offsets are (x, y, z), 0, (0, y, 0), (x, 0, 0), (x, y, 0), 0, (x, 0, 0) for joints 3..9 — checked
+// against the generated model by fast_structure_matches at engine creation. Products with the zeros are dropped
+// (cross_add_m / cross_sub_m, spatial.cuh).
+MPPI_HD constexpr unsigned offset_mask(int i) {
+    return i == 0 ? 1u : i == 1 ? 2u : i == 3 ? 7u : i == 5 ? 2u : i == 6 ? 1u : i == 7 ? 3u : i == 9 ? 1u : (i >= 10 ? 7u : 0u);
+}
 template <class R, int I> MPPI_HD Vec3<R> joint_offset(const RobotModel<R> &M, const R *q) {
     if (I == 0) return v3<R>(q[0] * M.sign[0], R(0), R(0));
     if (I == 1) return v3<R>(R(0), q[1] * M.sign[1], R(0));
@@ -160,7 +167,7 @@ template <class R, int I> MPPI_HD Vec3<R> rot_to_parent(const RobotModel<R> &M, 
 }
 template <class R, int I> MPPI_HD Mot<R> act_inv_joint(const RobotModel<R> &M, const R *q, const R *cs, const R *sn, const Mot<R> &m) {
     Mot<R> o;
-    o.v = rot_to_joint<R, I>(M, cs, sn, (I == 2) ? m.v : cross_sub(joint_offset<R, I>(M, q), m.w, m.v));
+    o.v = rot_to_joint<R, I>(M, cs, sn, (I == 2) ? m.v : cross_sub_m<offset_mask(I)>(joint_offset<R, I>(M, q), m.w, m.v));
     o.w = rot_to_joint<R, I>(M, cs, sn, m.w);
     return o;
 }
@@ -168,7 +175,7 @@ template <class R, int I> MPPI_HD Frc<R> act_joint(const RobotModel<R> &M, const
     Frc<R> o;
     o.f = rot_to_parent<R, I>(M, cs, sn, f.f);
     const Vec3<R> n = rot_to_parent<R, I>(M, cs, sn, f.n);
-    o.n = (I == 2) ? n : cross_add(joint_offset<R, I>(M, q), o.f, n);
+    o.n = (I == 2) ? n : cross_add_m<offset_mask(I)>(joint_offset<R, I>(M, q), o.f, n);
     return o;
 }
 

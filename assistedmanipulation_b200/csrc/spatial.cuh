@@ -202,6 +202,19 @@ template <class R> MPPI_HD Vec3<R> cross_sub(const Vec3<R> &a, const Vec3<R> &b,
     return v3<R>(fma_(a.z, b.y, fma_(-a.y, b.z, c.x)), fma_(a.x, b.z, fma_(-a.z, b.x, c.y)), fma_(a.y, b.x, fma_(-a.x, b.y, c.z)));
 }
 
+// The same two with structural zeros in `a` (bit k of MASK clear = component k is zero by the robot's structure): the
+// products with those components are dropped. The compiler may not do that by itself (0 * inf is NaN, -0 + 0 is +0), so
+// a literal or constant-memory zero still costs its multiply-add — and, in a dependency chain, its latency.
+template <bool NZ, class R> MPPI_HD R fma_nz(R a, R b, R c) { if (NZ) return fma_(a, b, c); return c; }
+template <unsigned MASK, class R> MPPI_HD Vec3<R> cross_add_m(const Vec3<R> &a, const Vec3<R> &b, const Vec3<R> &c) {
+    constexpr bool X = (MASK & 1u) != 0, Y = (MASK & 2u) != 0, Z = (MASK & 4u) != 0;
+    return v3<R>(fma_nz<Y>(a.y, b.z, fma_nz<Z>(-a.z, b.y, c.x)), fma_nz<Z>(a.z, b.x, fma_nz<X>(-a.x, b.z, c.y)), fma_nz<X>(a.x, b.y, fma_nz<Y>(-a.y, b.x, c.z)));
+}
+template <unsigned MASK, class R> MPPI_HD Vec3<R> cross_sub_m(const Vec3<R> &a, const Vec3<R> &b, const Vec3<R> &c) {
+    constexpr bool X = (MASK & 1u) != 0, Y = (MASK & 2u) != 0, Z = (MASK & 4u) != 0;
+    return v3<R>(fma_nz<Z>(a.z, b.y, fma_nz<Y>(-a.y, b.z, c.x)), fma_nz<X>(a.x, b.z, fma_nz<Z>(-a.z, b.x, c.y)), fma_nz<Y>(a.y, b.x, fma_nz<X>(-a.x, b.y, c.z)));
+}
+
 // ---- plane rotations ------------------------------------------------------------------------------
 template <class R> MPPI_HD Vec3<R> rotz(R c, R s, const Vec3<R> &v) { return v3<R>(c * v.x - s * v.y, s * v.x + c * v.y, v.z); }
 template <class R> MPPI_HD Vec3<R> rotz_t(R c, R s, const Vec3<R> &v) { return v3<R>(c * v.x + s * v.y, c * v.y - s * v.x, v.z); }

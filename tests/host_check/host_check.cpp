@@ -84,6 +84,15 @@ void host_fast_aba(int f32, const double *q, const double *u, double *qdd, doubl
         ee[0] = p.x; ee[1] = p.y; ee[2] = p.z;
     }
 }
+// the unrolled solver (UNROLL = 7: offsets with their structural zeros in the backward pass too), FP64
+void host_fast_aba_unrolled(const double *q, const double *u, double *qdd, double *ee) {
+    static const FastModel<double> F = make_fast_model<double>();
+    double c[12], s[12];
+    for (int i = 0; i < 12; i++) { c[i] = cos(q[i]); s[i] = sin(q[i]); }
+    Vec3<double> p;
+    aba_fused_fast<double, 7, true>(F, q, c, s, u, qdd, &p);
+    ee[0] = p.x; ee[1] = p.y; ee[2] = p.z;
+}
 // the device's FP64 sine / cosine (polynomial core of robot_fast.cuh) evaluated on the host
 void host_sincos_poly(int n, const double *a, double *s, double *c) {
     static const FastModel<double> F = make_fast_model<double>();
@@ -100,7 +109,7 @@ int host_topology_matches() { std::string w; return topology_matches(&w) ? 1 : 0
 #include "params_convert.h"
 #include "rollout_core.cuh"
 
-template <class R, int VAR, bool FAITHFUL, class CP>
+template <class R, int VAR, bool FAITHFUL, class CP, bool BIG = false>
 static void run_rollouts(const CP &cp, const double *x0, const double *U, const double *W, const double *eps, int K, int T, double dt, double discount, double *costs, double *bd) {
     static const RobotModel<R> M = make_robot_model<R>();
     static const FastModel<R> F = make_fast_model<R>();
@@ -112,12 +121,13 @@ static void run_rollouts(const CP &cp, const double *x0, const double *U, const 
     RolloutInputs<R> in{x.data(), u.data(), W ? w.data() : nullptr, T, (R)dt, discount};
     for (int k = 0; k < K; k++) {
         for (size_t i = 0; i < e.size(); i++) e[i] = (R)eps[(size_t)k * 12 * T + i];
-        costs[k] = rollout_franka<R, VAR, FAITHFUL>(M, F, P, in, e.data(), bd);
+        costs[k] = rollout_franka<R, VAR, FAITHFUL, decltype(P), BIG>(M, F, P, in, e.data(), bd);
     }
 }
 
 extern "C" {
-// objective: 1 track point, 2 assisted manipulation; flags: bit0 FAITHFUL, bit2 float
+// objective: 1 track point, 2 assisted manipulation; flags: bit0 FAITHFUL, bit2 float, bit3 the unrolled build of the lean
+// reach-to-pose kernel (k_rollout.cuh BIG: the arm joints' loop index is a constant, so the offsets' structural zeros apply)
 void host_rollouts(int objective, int flags, const void *params, const double *x0, const double *U, const double *W, const double *eps, int K, int T,
                    double dt, double discount, double *costs, double *bd7) {
     const bool faithful = flags & 1, f32 = flags & 4;
@@ -126,6 +136,11 @@ void host_rollouts(int objective, int flags, const void *params, const double *x
     if (objective == 1) {
         const auto &cp = *static_cast<const mppi_b200_track_point *>(params);
         int var = variant_for(cp);
+        if ((flags & 8) && var == VAR_TP_LEAN && !faithful) {
+            if (f32) run_rollouts<float, VAR_TP_LEAN, false, mppi_b200_track_point, true>(cp, x0, U, W, eps, K, T, dt, discount, costs, bd7);
+            else run_rollouts<double, VAR_TP_LEAN, false, mppi_b200_track_point, true>(cp, x0, U, W, eps, K, T, dt, discount, costs, bd7);
+            return;
+        }
         if (f32) { if (var == VAR_TP_LEAN) RUN(float, VAR_TP_LEAN, cp); else RUN(float, VAR_TP_FULL, cp); }
         else { if (var == VAR_TP_LEAN) RUN(double, VAR_TP_LEAN, cp); else RUN(double, VAR_TP_FULL, cp); }
     } else {

@@ -144,6 +144,29 @@ def test_fused_step_by_joint_structure_matches_oracle(oracle, hc, f32, tol):
         assert np.abs(kin[10:].reshape(8, 3) - lc.reshape(13, 3)[3:11]).max() <= tol
 
 
+def test_unrolled_solver_matches_loop_body_solver_and_oracle(oracle, hc):
+    """aba_fused_fast with the arm joints unrolled (the build for large rollout sets) drops the products with the
+    structural zeros of the joint offsets in both passes; same accelerations and end effector point as the oracle."""
+    rng = np.random.default_rng(11)
+    hc.host_fast_aba_unrolled.argtypes = [_dp] * 4
+    hc.host_fast_aba.argtypes = [C.c_int] + [_dp] * 4
+    for _ in range(8):
+        q, u = rng.uniform(-1.5, 1.5, 12), np.zeros(12)
+        q[10:] = rng.uniform(0.0, 0.04, 2)
+        u[3:10] = rng.uniform(-10, 10, 7)
+        a, a1, a7, e1, e7 = np.zeros(12), np.zeros(12), np.zeros(12), np.zeros(3), np.zeros(3)
+        nle = np.zeros(12)   # the reference's tau = u + nle(q, v): the fused solver returns M^-1 u
+        oracle.oracle_robot_nle(ol.ptr(q), ol.ptr(np.zeros(12)), ol.ptr(nle))
+        oracle.oracle_robot_aba(ol.ptr(q), ol.ptr(np.zeros(12)), ol.ptr(u + nle), ol.ptr(a))
+        hc.host_fast_aba(0, ol.ptr(q), ol.ptr(u), ol.ptr(a1), ol.ptr(e1))
+        hc.host_fast_aba_unrolled(ol.ptr(q), ol.ptr(u), ol.ptr(a7), ol.ptr(e7))
+        assert np.abs(a7 - a).max() <= 1e-12 * np.abs(a).max() and np.abs(a7 - a1).max() <= 1e-12 * np.abs(a).max()
+        assert np.abs(e7 - e1).max() <= 1e-14
+        pos, lin, ang, J = np.zeros(3), np.zeros(3), np.zeros(3), np.zeros(72)
+        oracle.oracle_robot_kinematics(ol.ptr(q), ol.ptr(np.zeros(12)), ol.ptr(pos), ol.ptr(lin), ol.ptr(ang), ol.ptr(J))
+        assert np.abs(e7 - pos).max() <= 1e-12
+
+
 def _track_point_full():
     tp = abi.default_track_point()
     tp.enable_self_collision_avoidance, tp.enable_reach_limits, tp.link_position_mode = 1, 1, abi.LINKS_BODY_COM
@@ -154,7 +177,7 @@ CASES["track_point_all_terms"] = (abi.OBJECTIVE_TRACK_POINT, _track_point_full, 
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-@pytest.mark.parametrize("flags,tol", [(0, 1e-9), (1, 1e-9), (4, 2e-4)])
+@pytest.mark.parametrize("flags,tol", [(0, 1e-9), (1, 1e-9), (4, 2e-4), (8, 1e-9), (12, 2e-4)])
 def test_rollout_costs_match_oracle(oracle, hc, name, flags, tol):
     objective, make, wrench = CASES[name]
     params = make()
