@@ -150,6 +150,9 @@ template <class R, int I> MPPI_HD void joint_transform(const RobotModel<R> &M, R
 MPPI_HD constexpr unsigned offset_mask(int i) {
     return i == 0 ? 1u : i == 1 ? 2u : i == 3 ? 7u : i == 5 ? 2u : i == 6 ? 1u : i == 7 ? 3u : i == 9 ? 1u : (i >= 10 ? 7u : 0u);
 }
+// The first arm joint's fixed placement does not rotate (alpha = 0: the arm stands upright on its mount); the others
+// turn by ~ +-90 degrees about x, with the URDF's rounded pi/2, so their cosine is 4.9e-12 and stays in the arithmetic.
+MPPI_HD constexpr bool placement_is_flat(int i) { return i == 3; }
 template <class R, int I> MPPI_HD Vec3<R> joint_offset(const RobotModel<R> &M, const R *q) {
     if (I == 0) return v3<R>(q[0] * M.sign[0], R(0), R(0));
     if (I == 1) return v3<R>(R(0), q[1] * M.sign[1], R(0));
@@ -157,12 +160,12 @@ template <class R, int I> MPPI_HD Vec3<R> joint_offset(const RobotModel<R> &M, c
 }
 template <class R, int I> MPPI_HD Vec3<R> rot_to_joint(const RobotModel<R> &M, const R *cs, const R *sn, const Vec3<R> &v) {   // E^T v
     if (I < 2) return v;
-    if (I == 2) return rotz_t(cs[2], sn[2], v);
+    if (I == 2 || placement_is_flat(I)) return rotz_t(cs[I], sn[I], v);
     return rotz_t(cs[I], sn[I], rotx_t(M.place_R[I][4], M.place_R[I][7], v));
 }
 template <class R, int I> MPPI_HD Vec3<R> rot_to_parent(const RobotModel<R> &M, const R *cs, const R *sn, const Vec3<R> &v) {   // E v
     if (I < 2) return v;
-    if (I == 2) return rotz(cs[2], sn[2], v);
+    if (I == 2 || placement_is_flat(I)) return rotz(cs[I], sn[I], v);
     return rotx(M.place_R[I][4], M.place_R[I][7], rotz(cs[I], sn[I], v));
 }
 template <class R, int I> MPPI_HD Mot<R> act_inv_joint(const RobotModel<R> &M, const R *q, const R *cs, const R *sn, const Mot<R> &m) {
