@@ -29,7 +29,13 @@ __device__ __forceinline__ double decode_ordered(unsigned long long e) {
 //   BIG = true   arm joints unrolled, per-joint results in registers (255)      K = 4096: 398 us   16384: 461   131072: 2075
 // (FP32: 297 / 330 / 1572 against 386 / 417 / 1577; the crossover sits near K = 12 k in FP64 and 24 k in FP32.)
 // Few rollouts = one warp per SM, which lives on a small instruction footprint; many = fewer instructions win even at
-// two blocks per SM.
+// two blocks per SM. Those crossovers were measured when the unrolled step loop was 40 KB of code (3120 instructions per
+// step) against 2600 for the loop body. Since the joint placements' structural zeros are dropped where the joint index is
+// a constant (robot.cuh offset_mask / placement_is_flat), the unrolled step is 1937 instructions / 1501 FP64 against
+// 2835 / 2095, its static model 4107 cycles against 4977 (FP32: 1919 against 3149), and its step loop is 31.0 KB — inside
+// the 32 KB instruction cache level whose overflow cost the old unrolled build ~25 % at one warp per SM. The unrolled
+// build therefore serves every rollout count by default; MPPI_B200_BIG_FROM=<rollouts> restores a crossover (12288 /
+// 24576 were the measured ones) for A/B runs.
 #ifndef MPPI_LEAN_MIN_BLOCKS
 #define MPPI_LEAN_MIN_BLOCKS 1
 #endif
@@ -104,7 +110,7 @@ cudaError_t launch_rollout_t(const DeviceState &d, const void *params, bool opti
     size_t smem = sizeof(R) * ((size_t)d.nu * d.T + 6 * (size_t)d.T + 32) + sizeof(double) * (size_t)d.T;
     auto kern = k_rollout<R, VAR, FAITHFUL, ParamsT, false>;
     if constexpr (VAR == VAR_TP_LEAN && !FAITHFUL) {
-        static const long long big_from = std::getenv("MPPI_B200_BIG_FROM") ? std::atoll(std::getenv("MPPI_B200_BIG_FROM")) : (sizeof(R) == 8 ? 12288 : 24576);   // measured crossovers
+        static const long long big_from = std::getenv("MPPI_B200_BIG_FROM") ? std::atoll(std::getenv("MPPI_B200_BIG_FROM")) : 0;   // see the note above k_rollout
         if (!optimal_only && d.k_count * (long long)d.batch >= big_from) kern = k_rollout<R, VAR, FAITHFUL, ParamsT, true>;
     }
     if (smem > 48 * 1024) {

@@ -35,11 +35,12 @@ from assistedmanipulation_b200 import abi  # noqa: E402
 # joints — ABA 4641 + RNEA 1880 + second-order FK / frames / WORLD jacobian ~2300 + cost + Euler + tank.
 FLOPS_PER_STEP = {"cfg2": 9000.0, "cfg3": 9500.0, "toy": 25.0, "cfg4_f32": 9000.0, "cfg4_f64": 9000.0}
 # What the rollout kernel EXECUTES per rollout-step (2*DFMA + DMUL + DADD per thread along the step loop, counted in the
-# SASS by tools/sass_cycles.py: 1287 / 559 / 249 for the loop-body build that config 2 launches, 858 / 431 / 212 for the
-# unrolled build of config 4; the round's first kernel executed 1197 / 837 / 534 by the ncu source page of
-# profiles/r1_cfg2_final.ncu-rep): the structure-exploiting solver needs far fewer operations than the reference's
-# generic algorithm counted above, so the algorithmic fraction can pass 1 where the pipe is full.
-EXECUTED_FLOPS_PER_STEP = {"cfg2": 3382.0, "cfg4_f64": 2359.0}
+# SASS by tools/sass_cycles.py, profiles/r1_sass_model.txt: 858 / 431 / 212 for the unrolled build, which configs 2 and 4
+# both launch (k_rollout.cuh); the loop-body build executes 1287 / 559 / 249 and the round's first kernel executed
+# 1197 / 837 / 534 by the ncu source page of profiles/r1_cfg2_final.ncu-rep): the structure-exploiting solver needs far
+# fewer operations than the reference's generic algorithm counted above, so the algorithmic fraction can pass 1 where
+# the pipe is full.
+EXECUTED_FLOPS_PER_STEP = {"cfg2": 2359.0, "cfg4_f64": 2359.0}
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_rollout launch, same capture (the noise rows, read once)
 ROLLOUT_DRAM_BYTES = {"cfg2": 25.23e6}
 
