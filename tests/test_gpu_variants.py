@@ -1,6 +1,10 @@
 """Every kernel variant (systems x objectives x FP64/FP32 x FAITHFUL/FUSED x single/batched) runs a few
 updates with keep-best, smoothing, Philox and injected noise without error and publishes finite controls
 (compute-sanitizer is closed on this pool; this is the broad exercise, parity is in test_gpu_parity.py)."""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
@@ -37,3 +41,28 @@ def test_variant_runs(run, precision, mode):
         assert np.all(np.isfinite(U))
     assert np.all(np.isfinite(e.read(abi.READ_OPTIMAL_COST, batch)))
     e.close()
+
+
+def _alt_run(tmp_path, name, precision, env):
+    out = str(tmp_path / (name + ".npz"))
+    full = dict(os.environ)
+    full.update(env)
+    subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "alt_worker.py"), out, str(precision)], check=True, env=full, timeout=300)
+    return np.load(out)
+
+
+@pytest.mark.parametrize("precision,c_tol,u_tol", [(abi.FP64, 1e-9, 1e-9), (abi.FP32, 1e-3, 2e-4)])
+def test_alternative_builds(tmp_path, precision, c_tol, u_tol):
+    """The builds kept for A/B runs against the defaults (unrolled rollout kernel, k_sample_quads), each in its own
+    process because the library reads the switches once: the tile sampling kernel (MPPI_B200_SAMPLE_TILE=1) must
+    reproduce every buffer bit for bit over updates with a kept set and a shift (same counters, same arithmetic, same
+    rollout kernel); the loop-body rollout kernel (MPPI_B200_BIG_FROM above the rollout count) sees identical noise
+    and must agree on costs and controls within the arithmetic's tolerance."""
+    base = _alt_run(tmp_path, "default", precision, {})
+    tile = _alt_run(tmp_path, "tile", precision, {"MPPI_B200_SAMPLE_TILE": "1"})
+    loop = _alt_run(tmp_path, "loop_body", precision, {"MPPI_B200_BIG_FROM": "1000000000"})
+    for k in base.files:
+        assert np.array_equal(base[k], tile[k]), k
+    assert np.array_equal(base["noise0"], loop["noise0"])
+    assert (np.abs(loop["costs0"] - base["costs0"]) / np.abs(base["costs0"])).max() <= c_tol
+    assert np.abs(loop["U0"] - base["U0"]).max() <= u_tol * np.abs(base["U0"]).max()
