@@ -189,6 +189,27 @@ MPPI_HD void pass1(const RobotModel<R> &M, const R *q, const R *qd, Scratch<R> &
     constexpr bool PL = PLANE && I <= 9;   // this joint's transform by its structure (no matrix formed)
     const R sg = M.sign[I];
     if (!PL) joint_transform<R, I>(M, q[I] * sg, S.li[I], cs, sn);
+    if (PL && I < 2) {
+        // The sliders translate without turning, and nothing below them turns either: their angular velocity and the
+        // velocity-product terms vanish identically (v x* (m v) = 0), their spatial acceleration is gravity alone. Written
+        // out, because the generic path multiplies through those zeros (~95 instructions per slider; the compiler may not
+        // fold 0 * x).
+        if (VEL) {
+            const R w = qd[I] * sg;
+            const Vec3<R> zero = v3<R>(R(0), R(0), R(0));
+            S.v[I].v = (I == 0) ? v3<R>(w, R(0), R(0)) : v3<R>(S.v[0].v.x, w, R(0));
+            S.v[I].w = zero;
+            if (NLE || BIAS) {
+                S.c[I].v = zero; S.c[I].w = zero;
+                if (NLE) {
+                    agf[I].v = v3<R>(R(0), R(0), M.gravity); agf[I].w = zero;
+                    S.f[I].f = v3<R>(R(0), R(0), M.gravity * M.mass[I]);
+                    S.f[I].n = v3<R>(M.mc[I][1] * M.gravity, -(M.mc[I][0] * M.gravity), R(0));
+                }
+                if (BIAS) { S.pA[I].f = zero; S.pA[I].n = zero; }
+            }
+        }
+    } else
     if (VEL) {
         const R w = qd[I] * sg;
         Mot<R> vj = joint_motion<R, T>(w);
