@@ -101,6 +101,10 @@ void host_sincos_poly(int n, const double *a, double *s, double *c) {
 void host_sincos_poly_f32(int n, const float *a, float *s, float *c) {
     for (int i = 0; i < n; i++) sincos_poly((const float *)nullptr, a[i], &s[i], &c[i]);
 }
+// the integer-pipe sign test of the joint-limit term (spatial.cuh)
+void host_is_negative(int n, const double *x, int *out64, int *out32) {
+    for (int i = 0; i < n; i++) { out64[i] = is_negative(x[i]) ? 1 : 0; out32[i] = is_negative((float)x[i]) ? 1 : 0; }
+}
 int host_fast_structure_matches() { std::string w; return fast_structure_matches(&w) ? 1 : 0; }
 int host_topology_matches() { std::string w; return topology_matches(&w) ? 1 : 0; }
 }

@@ -64,6 +64,28 @@ def test_device_sincos_f32_matches_libm(hc):
     assert np.isnan(s3).all() and np.isnan(c3).all()
 
 
+def test_integer_sign_test_matches_the_comparison(hc):
+    """is_negative(x) (sign bit set and not a NaN, decided on the integer pipe) has the truth value of the reference's
+    `x < 0` for every non-zero x, NaN of either sign included (false); -0, which a difference of finite numbers never
+    produces, counts as negative."""
+    rng = np.random.default_rng(2)
+    x = np.concatenate([rng.standard_normal(10000) * 10.0 ** rng.integers(-300, 300, 10000), [np.inf, -np.inf, 5e-324, -5e-324, 1e-40, -1e-40, 0.0,
+                        np.nan, -np.nan, np.float64(np.frombuffer(np.uint64(0xfff8000000000001).tobytes(), np.float64)[0]), np.float64(np.frombuffer(np.uint64(0x7ff8000000000001).tobytes(), np.float64)[0])]])
+    o64, o32 = np.zeros(x.size, np.int32), np.zeros(x.size, np.int32)
+    ip = C.POINTER(C.c_int)
+    hc.host_is_negative.argtypes = [C.c_int, _dp, ip, ip]
+    hc.host_is_negative(x.size, ol.ptr(x), o64.ctypes.data_as(ip), o32.ctypes.data_as(ip))
+    assert np.array_equal(o64.astype(bool), x < 0)
+    with np.errstate(over="ignore", under="ignore"):
+        xf = x.astype(np.float32)
+    nz = xf != 0                                 # values that underflow to -0 in single precision count as negative there
+    assert np.array_equal(o32.astype(bool)[nz], (xf < 0)[nz])
+    m0 = np.array([-0.0])
+    z64, z32 = np.zeros(1, np.int32), np.zeros(1, np.int32)
+    hc.host_is_negative(1, ol.ptr(m0), z64.ctypes.data_as(ip), z32.ctypes.data_as(ip))
+    assert z64[0] == 1 and z32[0] == 1
+
+
 def test_topology_matches_generated_model(hc):
     assert hc.host_topology_matches() == 1
 
