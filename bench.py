@@ -15,6 +15,7 @@ workload, one bounded sample per step.
 """
 import argparse
 import ctypes as C
+import gc
 import json
 import os
 import subprocess
@@ -193,6 +194,7 @@ def bench_controllers(args, rank, world, local_rank, n_gpus, dist, torch, el):
     launches0 = sum(e.query(abi.QUERY_KERNEL_LAUNCHES) for e in engines)
     sampler = ClockSampler(n_gpus, enabled=(rank == 0))
     sampler.start()
+    gc.collect(); gc.disable()   # no collector pauses of the measuring process inside the timed region
     barrier()
     ticks = []
     for _ in range(args.steps):
@@ -200,6 +202,7 @@ def bench_controllers(args, rank, world, local_rank, n_gpus, dist, torch, el):
         tick(step); step += 1
         ticks.append(time.perf_counter() - t0)
     barrier()
+    gc.enable()
     sampler.stop_flag = True
     sampler.join()
     launches = sum(e.query(abi.QUERY_KERNEL_LAUNCHES) for e in engines) - launches0
@@ -320,6 +323,7 @@ def main():
     launches0 = e.query(abi.QUERY_KERNEL_LAUNCHES)
     sampler = ClockSampler(n_gpus, enabled=(rank == 0))
     sampler.start()
+    gc.collect(); gc.disable()   # no collector pauses of the measuring process inside the timed region
     barrier()
     dev_s, wall_s = [], []
     t_region0 = time.perf_counter()
@@ -339,6 +343,7 @@ def main():
         step += 1
     barrier()
     t_region1 = time.perf_counter()
+    gc.enable()
     sampler.stop_flag = True
     sampler.join()
     launches = e.query(abi.QUERY_KERNEL_LAUNCHES) - launches0
