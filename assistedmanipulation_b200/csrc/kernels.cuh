@@ -67,7 +67,7 @@ struct DeviceState {
     double *gradient;      // normalised gradient (get_gradient())
     int *skip;             // 1 when max-min < 1e-6 (mppi.cpp:373-375): weights/gradient/U left untouched
     double *L;             // nu x nu column-major noise transform V*sqrt(Lambda) (gaussian.hpp:48-55)
-    int L_is_diagonal;     // every reference configuration (base.hpp:79-83): eps_i = Ldiag[i] * z_i
+    int L_is_diagonal;     // diagonal covariance (every reference configuration, base.hpp:79-83): eps_i = Ldiag[i] * z_i, Ldiag = sqrt(Sigma_ii) (host_math.h)
     double Ldiag[MAX_NU];
     // smoothing window state, per channel: uu[Lw], tt[Lw], then start_idx/last_trim in sg_meta
     double *sg_uu, *sg_tt;

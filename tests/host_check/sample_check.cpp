@@ -5,6 +5,7 @@
 #include <cstring>
 #include <vector>
 
+#include "host_math.h"
 #include "sample_core.cuh"
 
 using namespace mppi_b200;
@@ -49,6 +50,10 @@ long long host_sample_quads(int f32, int injected_is_double, int T, long long k_
 }
 // both branches of the index arithmetic (32-bit when the enumeration fits, 64-bit otherwise) for arbitrary sizes
 void host_quad_coordinates(long long g, long long quads, int T, long long *kl, int *t, int *b) { quad_coordinates<12>(g, quads, T, kl, t, b); }
+// engine-creation arithmetic (host_math.h)
+void host_sg_weights(int m, int n, double *out) { const auto w = host_math::sg_weights(m, n); for (size_t i = 0; i < w.size(); i++) out[i] = w[i]; }
+void host_noise_transform(int n, const double *cov, double *L) { const auto l = host_math::noise_transform(n, cov); for (size_t i = 0; i < l.size(); i++) L[i] = l[i]; }
+int host_diagonal_noise_transform(int n, const double *cov, double *ldiag) { return host_math::diagonal_noise_transform(n, cov, ldiag) ? 1 : 0; }
 void host_philox(const unsigned *ctr4, const unsigned *key2, unsigned *out4) {
     const uint4 r = philox4x32_10(make_uint4(ctr4[0], ctr4[1], ctr4[2], ctr4[3]), make_uint2(key2[0], key2[1]));
     out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;

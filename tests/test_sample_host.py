@@ -22,7 +22,7 @@ def sc():
     if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
         pytest.skip("CUDA headers not found")
     so, src = os.path.join(HC_DIR, "libsample_check.so"), os.path.join(HC_DIR, "sample_check.cpp")
-    deps = [src] + [os.path.join(CSRC, f) for f in ("sample_core.cuh", "kernels.cuh", "rollout_core.cuh", "spatial.cuh")]
+    deps = [src] + [os.path.join(CSRC, f) for f in ("sample_core.cuh", "host_math.h", "kernels.cuh", "rollout_core.cuh", "spatial.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-x", "c++", "-fPIC", "-shared", "-I" + CSRC, "-I" + CUDA_INC, "-o", so, src])
     lib = C.CDLL(so)
@@ -127,3 +127,49 @@ def test_quad_coordinates_both_widths(sc):
             sc.host_quad_coordinates(g, quads, T, C.byref(kl), C.byref(t), C.byref(b))
             assert (kl.value, t.value, b.value) == (g // (3 * T), (g // 3) % T, g % 3)
             assert (kl.value * T + t.value) * 12 + 4 * b.value == 4 * g     # the store address of the quad
+
+
+def test_savitzky_golay_taps_known_answers(sc):
+    # evaluated from gram_savitzky_golay.cpp:12-53
+    sc.host_sg_weights.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    w = np.zeros(21)
+    sc.host_sg_weights(10, 1, w.ctypes.data)
+    assert np.allclose(w, 1.0 / 21.0, rtol=1e-14)
+    w = np.zeros(5)
+    sc.host_sg_weights(2, 2, w.ctypes.data)
+    assert np.allclose(w, np.array([-3.0, 12.0, 17.0, 12.0, -3.0]) / 35.0, rtol=1e-14)
+    for m, n in [(3, 2), (5, 3), (7, 4), (10, 2)]:     # the central tap row of the least-squares polynomial smoother
+        w = np.zeros(2 * m + 1)
+        sc.host_sg_weights(m, n, w.ctypes.data)
+        x = np.arange(-m, m + 1, dtype=np.float64)
+        A = np.vander(x, n + 1, increasing=True)
+        assert np.allclose(w, np.linalg.pinv(A)[0], rtol=1e-10, atol=1e-13)
+
+
+def test_noise_transform_is_the_reference_factor(sc):
+    """V sqrt(Lambda), eigenvalues ascending (gaussian.hpp:48-55): L L^T = Sigma, column norms = sqrt of the sorted
+    eigenvalues; for a diagonal Sigma the engine instead takes eps_i = sqrt(Sigma_ii) z_i (same distribution)."""
+    sc.host_noise_transform.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    sc.host_diagonal_noise_transform.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(5)
+    for n in (2, 5, 12):
+        B = rng.standard_normal((n, n))
+        S = B @ B.T + 0.1 * np.eye(n)
+        Sc = np.asfortranarray(S)
+        L = np.zeros((n, n), order="F")
+        sc.host_noise_transform(n, Sc.ctypes.data, L.ctypes.data)
+        assert np.allclose(L @ L.T, S, rtol=1e-11, atol=1e-12)
+        ev = np.linalg.eigvalsh(S)
+        assert np.allclose(np.linalg.norm(L, axis=0), np.sqrt(ev), rtol=1e-10)
+        ld = np.zeros(n)
+        assert sc.host_diagonal_noise_transform(n, Sc.ctypes.data, ld.ctypes.data) == 0
+    d = np.array([0.1, 0.1, 0.2] + [7.5] * 7 + [0.0, 0.0])     # base.hpp:79-83
+    S = np.asfortranarray(np.diag(d))
+    L = np.zeros((12, 12), order="F")
+    sc.host_noise_transform(12, S.ctypes.data, L.ctypes.data)
+    assert np.allclose(L @ L.T, S, atol=1e-15)
+    assert np.count_nonzero(L - np.diag(np.diag(L))) > 0           # the reference's factor of this matrix is a PERMUTED diagonal ...
+    ld = np.zeros(12)
+    assert sc.host_diagonal_noise_transform(12, S.ctypes.data, ld.ctypes.data) == 1
+    assert np.array_equal(ld, np.sqrt(d))                          # ... the engine samples with the plain one
+    assert np.array_equal(np.sort(np.linalg.norm(L, axis=0)), np.sort(ld))
