@@ -2,11 +2,14 @@
 # Regenerates profiles/r1_sass_model.txt and profiles/r1_sass_phases.txt from the objects build() leaves in csrc/build
 # (static: no GPU). Run from the repo root after `make -C assistedmanipulation_b200/csrc`.
 set -e
-T=tools/sass_cycles.py; O=assistedmanipulation_b200/csrc/build; SK="--skip robot_fast.cuh:136"
+T=tools/sass_cycles.py; O=assistedmanipulation_b200/csrc/build
+# the range-reduction slow path of the FP64 sines / cosines (behind a forward branch taken only for |angle| >= 2^31)
+FOLD=$(grep -n "if (!(fabs(a\[i\]) < 2147483648.0))" assistedmanipulation_b200/csrc/robot_fast.cuh | cut -d: -f1)
+SK="--skip robot_fast.cuh:$FOLD"
 {
 echo "# Static issue-cycle model (tools/sass_cycles.py) of the rollout kernels as committed; one warp per SM sub-partition."
 echo "# Calibration on B200: cfg2 kernel of r1_cfg2_final.ncu-rep models 7597 cycles/step, measures 9015; the kernel of r1_quick_check_after_model_work.log models 5372, measures 6509."
-echo "# FP64 kernels: the range-reduction slow path of the shared sines / cosines (robot_fast.cuh:136, behind a forward branch taken only for |angle| >= 2^31) is left out (--skip)."
+echo "# FP64 kernels: the range-reduction slow path of the shared sines / cosines (robot_fast.cuh:$FOLD, behind a forward branch taken only for |angle| >= 2^31) is left out (--skip)."
 echo
 echo "## lean reach-to-pose kernel, FP64, unrolled build — configs 2 and 4 (default for every rollout count)   [start: 3120 instructions, 2515 FP64; 2445 / 1956 / 5083 cycles before the joint placements' structural zeros]"
 python $T $O/k_rollout_f64.o 'Li1ELb0ENS_11TrackPointPIdEELb1EEE' --lines 12 $SK
