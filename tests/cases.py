@@ -50,3 +50,19 @@ def config_for(case, **over):
     kw = dict(keep_best=case["keep"], threads=case["threads"], smoothing=case["smoothing"])
     kw.update(over)
     return abi.make_config(case["system"], case["objective"], case["K"], case["horison"], **kw)
+
+
+def fp32_flips(ce, co, cost_rtol):
+    """Single-precision costs against the FP64 oracle on identical noise. The objectives have jumps (1e10 at the inverse
+    barriers, cost.hpp:59-61,90-92; 1000 at the hard-coded joint limits, track_point.cpp:48-65): a rollout whose state
+    lands within FP32 rounding of such a bound at some step takes the jump on one side only (a "flip"; which rollouts
+    do depends on the kernel's rounding, i.e. on every change of its operation order). Away from flips the costs must
+    agree to `cost_rtol`, flips must be rare, and the typical rollout must be far inside the tolerance. Returns True
+    when this update has flips — the two controllers then continue from different control sequences, so a caller
+    comparing several updates stops there."""
+    ok = ~np.isnan(co)
+    rel = np.abs(ce[ok] - co[ok]) / np.abs(co[ok])
+    flipped = rel > cost_rtol
+    assert flipped.mean() <= 5e-3, (int(flipped.sum()), rel.max())
+    assert np.median(rel) <= cost_rtol / 20, np.median(rel)
+    return bool(flipped.any())
