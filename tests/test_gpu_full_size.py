@@ -32,8 +32,9 @@ def test_config3_full_size_fp32_fast_mode(oracle):
     assert flipped.mean() < 3e-3, flipped.sum()
     assert np.median(np.abs(ce - co) / np.abs(co)) < 1e-6
     assert (np.abs(ce - co) / np.abs(co))[~flipped].max() < 1e-3
-    # the published control sequence, flips included
-    assert np.abs(Ue - Uo).max() <= 5e-4 * np.abs(Uo).max(), np.abs(Ue - Uo).max() / np.abs(Uo).max()
+    # the published control sequence, flips included (measured 2e-4 with the ~16 flips of one kernel build; which rollouts
+    # flip changes with the kernel's rounding, so the bound leaves room for a few standard deviations of that count)
+    assert np.abs(Ue - Uo).max() <= 1e-3 * np.abs(Uo).max(), np.abs(Ue - Uo).max() / np.abs(Uo).max()
     # without the flipped rollouts the FP32 costs reproduce the FP64 update to the stated 1e-4 (first update: U_shift = 0)
 
     def update_from(c):
