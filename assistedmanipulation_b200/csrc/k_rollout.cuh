@@ -31,8 +31,8 @@ __device__ __forceinline__ double decode_ordered(unsigned long long e) {
 // Few rollouts = one warp per SM, which lives on a small instruction footprint; many = fewer instructions win even at
 // two blocks per SM. Those crossovers were measured when the unrolled step loop was 40 KB of code (3120 instructions per
 // step) against 2600 for the loop body. Since the joint placements' structural zeros are dropped where the joint index is
-// a constant (robot.cuh offset_mask / placement_is_flat), the unrolled step is 1937 instructions / 1501 FP64 against
-// 2835 / 2095, its static model 4107 cycles against 4977 (FP32: 1919 against 3149), and its step loop is 31.0 KB — inside
+// a constant (robot.cuh offset_mask / placement_is_flat), the unrolled step is 1927 instructions / 1501 FP64 against
+// 2835 / 2095, its static model 4048 cycles against 4977 (FP32: 1756 against 3149), and its step loop is 31.0 KB — inside
 // the 32 KB instruction cache level whose overflow cost the old unrolled build ~25 % at one warp per SM. The unrolled
 // build therefore serves every rollout count by default; MPPI_B200_BIG_FROM=<rollouts> restores a crossover (12288 /
 // 24576 were the measured ones) for A/B runs.

@@ -338,9 +338,11 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
             robot_calculate<R, true, POWER, KF>(M, q, qd, tau, qdd, nle, K);
         } else {
             // FUSED: qdd = M(q)^-1 tau through the structure-exploiting solver; joint sines / cosines are shared
-            // (the lean kernel evaluates them here, at the head of the solver: its objective has no yaw term, and this
-            // placement gives the better schedule of the inertia loop)
-            if constexpr (LEAN) { if (step != 0) joint_sincos<R>(F, q, cs, sn); }
+            // (the loop-body build of the lean kernel evaluates them here, at the head of the solver: its objective has no yaw
+            // term, and this placement gives the better schedule of the inertia loop; the unrolled build evaluates them after
+            // the integration like the other objectives — no first-step test at the head of the loop, 59 modelled cycles and
+            // the last spill less)
+            if constexpr (LEAN && !BIG) { if (step != 0) joint_sincos<R>(F, q, cs, sn); }
             qd[0] = cs[2] * u[0] - sn[2] * u[1];
             qd[1] = sn[2] * u[0] + cs[2] * u[1];
             qd[2] = u[2];
@@ -363,7 +365,7 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
             for (int i = 0; i < NJ; i++) p += (tau[i] + nle[i]) * qd[i];
             energy = std_max(R(0), energy + p * in.dt);  // energy.hpp:19-22
         }
-        if constexpr (!FAITHFUL && !LEAN) joint_sincos<R>(F, q, cs, sn);
+        if constexpr (!FAITHFUL && (!LEAN || BIG)) joint_sincos<R>(F, q, cs, sn);
     }
     return total;
 }
