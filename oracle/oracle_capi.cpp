@@ -152,6 +152,36 @@ double oracle_right_barrier(double bound, double scale, double maxc, double v) {
 double oracle_quadratic(double c0, double c1, double c2, double v) { return quadratic_cost<double>({c0, c1, c2}, v); }
 double oracle_upper_log_barrier(double bound, double scale, double offset, double maxc, double v) { return upper_log_barrier({bound, scale, offset, maxc}, v); }
 double oracle_lower_log_barrier(double bound, double scale, double offset, double maxc, double v) { return lower_log_barrier({bound, scale, offset, maxc}, v); }
+// The objectives of systems.hpp on caller-supplied kinematics (same record as ref_objective_probe, oracle/ref_driver.cpp):
+// state[31], end-effector position[3], linear velocity[3], jacobian[6][12] row-major, ARM_MOUNT_JOINT position[3],
+// link positions[13][3], tank energy, has_forecast, wrench[6] = 159 doubles in; 8 out (total + the seven terms).
+int oracle_objective_probe(int objective, const void *params, const double *in, long count, double *out) {
+    for (long n = 0; n < count; n++) {
+        const double *p = in + n * 159;
+        RobotCore<double> core;
+        for (int i = 0; i < FR_STATE; i++) core.state[i] = p[i];
+        core.ee.position = {p[31], p[32], p[33]};
+        core.ee.linear_velocity = {p[34], p[35], p[36]};
+        for (int r = 0; r < 6; r++) for (int j = 0; j < FR_NJ; j++) core.ee.jacobian[r][j] = p[37 + r * 12 + j];
+        core.data.oMf_mount.p = {p[109], p[110], p[111]};
+        for (int l = 0; l < FR_NLINK; l++) core.link_com_world[l] = {p[112 + l * 3], p[113 + l * 3], p[114 + l * 3]};
+        core.tank.set_energy(p[151]);
+        double *o = out + n * 8;
+        for (int i = 0; i < 8; i++) o[i] = 0.0;
+        if (objective == MPPI_B200_OBJECTIVE_TRACK_POINT) {
+            auto q = *static_cast<const mppi_b200_track_point *>(params);
+            q.link_position_mode = MPPI_B200_LINKS_BODY_COM;   // the probe supplies the link positions
+            o[0] = track_point_cost<double>(q, core.state, core);
+        } else {
+            auto q = *static_cast<const mppi_b200_assisted_manipulation *>(params);
+            q.link_position_mode = MPPI_B200_LINKS_BODY_COM;
+            Breakdown bd;
+            o[0] = assisted_manipulation_cost<double>(q, core.state, core, p[152] != 0.0 ? p + 153 : nullptr, &bd);
+            o[1] = bd.joint; o[2] = bd.self_collision; o[3] = bd.workspace; o[4] = bd.energy; o[5] = bd.velocity; o[6] = bd.trajectory; o[7] = bd.manipulability;
+        }
+    }
+    return 0;
+}
 void oracle_tank(double energy, double power, double dt, double *out2) { EnergyTank<double> t; t.set_energy(energy); t.step(power, dt); out2[0] = t.energy; out2[1] = t.state; }
 
 // SG window driver: runs `updates` reset/add/apply rounds exactly like mppi.cpp:424-440 on one channel

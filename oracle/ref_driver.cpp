@@ -2,14 +2,20 @@
 // filter.cpp, gaussian.hpp, gram_savitzky_golay.cpp compiled unmodified from /root/reference by
 // oracle/Makefile `ref`, against oracle/ref_shim) so the restatement in mppi_oracle.hpp can be
 // pinned against outputs of the reference itself. Only valid for rollouts + 2 <= 255 (the
-// reference's std::uint8_t indices, mppi.hpp:639,642). The robot dynamics and objectives plugged
-// in here are the oracle's (pinocchio is absent) — what this library pins is the controller:
-// sampling order, warm start, weighting, gradient step, smoothing, clamping, readout.
+// reference's std::uint8_t indices, mppi.hpp:639,642). The OBJECTIVES are the reference's own too
+// (objective/track_point.cpp, objective/assisted_manipulation.cpp, frankaridgeback/dynamics.cpp, state.cpp compiled
+// unmodified); only the rigid-body arithmetic behind FrankaRidgeback::Dynamics is the oracle's (pinocchio is absent).
+// What this library pins: the controller (sampling order, warm start, weighting, gradient step, smoothing, clamping,
+// readout), the cost functors (cost.hpp) and both objectives, term by term.
 #include <cstring>
 #include <memory>
 
 #include "controller/mppi.hpp"   // the reference's header
 #include "logging/mppi.hpp"      // the reference's CSV logger
+#include "frankaridgeback/dynamics.hpp"                         // the reference's robot-specific Dynamics interface + DynamicsForecast
+#include "frankaridgeback/objective/track_point.hpp"            // the reference's objectives
+#include "frankaridgeback/objective/assisted_manipulation.hpp"
+#include "controller/energy.hpp"                                // the reference's energy tank
 #include "systems.hpp"           // oracle systems
 
 namespace {
@@ -37,34 +43,131 @@ struct RefToyCost : mppi::Cost {
     constexpr int get_state_dof() override { return 4; }
 };
 
-struct RefFrankaDynamics : mppi::Dynamics {
+// The reference's robot-specific Dynamics interface (frankaridgeback/dynamics.hpp:416-537) over the oracle's rigid-body
+// core — the one layer that cannot come from the reference (pinocchio is absent). Accessors follow
+// PinocchioDynamics (pinocchio_dynamics.hpp:112-262): link positions are zero in that backend (:189-192; the
+// BODY_COM mode is the RaiSim intent, SURVEY A-3), powers are 0, the simulated wrench is dropped.
+struct RefFrankaDynamics : FrankaRidgeback::Dynamics {
     oracle::FrankaDynamics inner;
-    VectorXd x = VectorXd(31);
+    VectorXd x = VectorXd(31), jq = VectorXd(12), jv = VectorXd(12);
+    FrankaRidgeback::EndEffectorState ee;
+    int link_mode = MPPI_B200_LINKS_ZERO;
+    std::shared_ptr<oracle::WrenchTable> table;                         // nullptr / !present = no forecast handle
+    std::unique_ptr<FrankaRidgeback::DynamicsForecast::Handle> forecast;
+
+    RefFrankaDynamics() = default;
+    RefFrankaDynamics(const RefFrankaDynamics &o)
+        : inner(o.inner), x(o.x), jq(o.jq), jv(o.jv), ee(o.ee), link_mode(o.link_mode), table(o.table), forecast(o.forecast ? o.forecast->copy() : nullptr) {}
     std::unique_ptr<mppi::Dynamics> copy() override { return std::make_unique<RefFrankaDynamics>(*this); }
+
+    void sync() {
+        const auto &c = inner.core;
+        for (int i = 0; i < 12; i++) { jq[i] = c.q[i]; jv[i] = c.v[i]; }
+        ee.position = Vector3d(c.ee.position.x, c.ee.position.y, c.ee.position.z);
+        ee.linear_velocity = Vector3d(c.ee.linear_velocity.x, c.ee.linear_velocity.y, c.ee.linear_velocity.z);
+        ee.angular_velocity = Vector3d(c.ee.angular_velocity.x, c.ee.angular_velocity.y, c.ee.angular_velocity.z);
+        ee.linear_acceleration = Vector3d(c.ee.linear_acceleration.x, c.ee.linear_acceleration.y, c.ee.linear_acceleration.z);
+        ee.angular_acceleration = Vector3d(c.ee.angular_acceleration.x, c.ee.angular_acceleration.y, c.ee.angular_acceleration.z);
+        for (int r = 0; r < 6; r++) for (int j = 0; j < 12; j++) ee.jacobian(r, j) = c.ee.jacobian[r][j];
+    }
     Eigen::Ref<VectorXd> step(const VectorXd &u, double dt) override {
         const double *n = inner.step(u.data(), dt);
         std::copy(n, n + 31, x.data());
+        sync();
         return x;
     }
-    void set_state(const VectorXd &s, double t) override { inner.set_state(s.data(), t); x = s; }
+    void set_state(const VectorXd &s, double t) override { inner.set_state(s.data(), t); x = s; sync(); }
     Eigen::Ref<VectorXd> get_state() override { return x; }
     constexpr int get_control_dof() override { return 12; }
     constexpr int get_state_dof() override { return 31; }
+    const VectorXd &get_joint_position() const override { return jq; }
+    const VectorXd &get_joint_velocity() const override { return jv; }
+    Vector3d get_frame_position(FrankaRidgeback::Frame frame) override {
+        const auto &d = inner.core.data;
+        if (frame == FrankaRidgeback::Frame::ARM_MOUNT_JOINT) return Vector3d(d.oMf_mount.p.x, d.oMf_mount.p.y, d.oMf_mount.p.z);
+        if (frame == FrankaRidgeback::Frame::PANDA_GRASP_JOINT) return Vector3d(d.oMf_ee.p.x, d.oMf_ee.p.y, d.oMf_ee.p.z);
+        std::cerr << "ref_driver: frame " << (int)frame << " is not carried by the oracle core" << std::endl;
+        std::abort();
+    }
+    Quaterniond get_frame_orientation(FrankaRidgeback::Frame) override { return Quaterniond::Identity(); }
+    Vector3d get_link_position(FrankaRidgeback::Link link) override {
+        if (link_mode == MPPI_B200_LINKS_ZERO) return Vector3d::Zero();
+        const auto &p = inner.core.link_com_world[(std::size_t)link];
+        return Vector3d(p.x, p.y, p.z);
+    }
+    const FrankaRidgeback::EndEffectorState &get_end_effector_state() const override { return ee; }
+    double get_joint_power() const override { return 0.0; }
+    double get_external_power() const override { return 0.0; }
+    double get_tank_energy() const override { return inner.core.tank.energy; }
+    const FrankaRidgeback::DynamicsForecast::Handle *get_forecast() const override {
+        return (forecast && table && table->present) ? forecast.get() : nullptr;
+    }
+    Vector6d get_end_effector_simulated_wrench() const override { return Vector6d::Zero(); }
+    void add_end_effector_simulated_wrench(Vector6d) override {}
 };
 
-template <class Inner> struct RefFrankaCost : mppi::Cost {
-    Inner inner;
-    explicit RefFrankaCost(Inner i) : inner(std::move(i)) {}
-    std::unique_ptr<mppi::Cost> copy() override { return std::make_unique<RefFrankaCost>(*this); }
-    void reset(double t) override { inner.reset(t); }
-    double get_cost(const VectorXd &s, const VectorXd &u, mppi::Dynamics *d, double t) override {
-        return inner.get_cost(s.data(), u.data(), &static_cast<RefFrankaDynamics *>(d)->inner, t);
+// What the facade hands the engine: forecast->get_end_effector_wrench(t0 + k dt) tabulated once per update. Served to
+// the reference's objective through the reference's own DynamicsForecast (dynamics.hpp:275-278 -> Forecast::forecast).
+struct TableForecast : Forecast {
+    const oracle::WrenchTable *table;   // raw: the reference's Forecast has no virtual destructor (forecast.hpp:14-56)
+    explicit TableForecast(const std::shared_ptr<oracle::WrenchTable> &t) : table(t.get()) {}
+    void update(VectorXd, double) override {}
+    void update(double) override {}
+    VectorXd forecast(double time) override {
+        VectorXd w(6);
+        const double *row = table->at(time);
+        for (int i = 0; i < 6; i++) w[i] = row ? row[i] : 0.0;
+        return w;
     }
-    constexpr int get_control_dof() override { return 12; }
-    constexpr int get_state_dof() override { return 31; }
 };
+struct TableDynamicsForecast : FrankaRidgeback::DynamicsForecast {   // its constructor is protected (dynamics.hpp:344-349)
+    TableDynamicsForecast(const Configuration &c, std::unique_ptr<Forecast> &&f, unsigned steps)
+        : DynamicsForecast(c, nullptr, std::move(f), steps) {}
+};
+
+FrankaRidgeback::TrackPoint::Configuration track_point_configuration(const mppi_b200_track_point &p) {
+    auto c = FrankaRidgeback::TrackPoint::DEFAULT_CONFIGURATION;
+    c.point = Vector3d(p.point[0], p.point[1], p.point[2]);
+    c.enable_joint_limits = p.enable_joint_limits; c.enable_self_collision_avoidance = p.enable_self_collision_avoidance;
+    c.enable_power_limit = p.enable_power_limit; c.enable_reach_limits = p.enable_reach_limits;
+    for (int i = 0; i < 12; i++) {
+        c.lower_joint_limit[i] = {p.lower_joint_limit[i].bound, p.lower_joint_limit[i].scale, p.lower_joint_limit[i].maximum_cost};
+        c.upper_joint_limit[i] = {p.upper_joint_limit[i].bound, p.upper_joint_limit[i].scale, p.upper_joint_limit[i].maximum_cost};
+    }
+    c.self_collision_limit = {p.self_collision_limit.bound, p.self_collision_limit.scale, p.self_collision_limit.maximum_cost};
+    for (int i = 0; i < 8; i++) c.self_collision_radii[i] = p.self_collision_radii[i];
+    c.maximum_reach_limit = {p.maximum_reach_limit.bound, p.maximum_reach_limit.scale, p.maximum_reach_limit.maximum_cost};
+    return c;
+}
+
+FrankaRidgeback::AssistedManipulation::Configuration assisted_configuration(const mppi_b200_assisted_manipulation &p) {
+    auto c = FrankaRidgeback::AssistedManipulation::DEFAULT_CONFIGURATION;
+    auto left = [](const mppi_b200_barrier &b) { return LeftInverseBarrierFunction{b.bound, b.scale, b.maximum_cost}; };
+    auto right = [](const mppi_b200_barrier &b) { return RightInverseBarrierFunction{b.bound, b.scale, b.maximum_cost}; };
+    auto quad = [](const mppi_b200_quadratic &q) { return QuadraticCost{q.constant_cost, q.linear_cost, q.quadratic_cost}; };
+    c.enable_joint_limit = p.enable_joint_limit; c.enable_self_collision_limit = p.enable_self_collision_limit;
+    c.enable_workspace_limit = p.enable_workspace_limit; c.enable_energy_limit = p.enable_energy_limit;
+    c.enable_velocity_cost = p.enable_velocity_cost; c.enable_trajectory_cost = p.enable_trajectory_cost;
+    c.enable_manipulability_cost = p.enable_manipulability_cost;
+    for (int i = 0; i < 12; i++) {
+        c.lower_joint_limit[i] = left(p.lower_joint_limit[i]); c.upper_joint_limit[i] = right(p.upper_joint_limit[i]);
+        c.velocity_cost[i] = quad(p.velocity_cost[i]);
+    }
+    c.self_collision_limit = left(p.self_collision_limit);
+    for (int i = 0; i < 8; i++) c.self_collision_radii[i] = p.self_collision_radii[i];
+    c.workspace_limit_above = left(p.workspace_limit_above); c.workspace_limit_infront = left(p.workspace_limit_infront);
+    c.workspace_limit_reach = right(p.workspace_limit_reach); c.workspace_cost_yaw = quad(p.workspace_cost_yaw);
+    c.energy_limit_below = left(p.energy_limit_below); c.energy_limit_above = right(p.energy_limit_above);
+    c.trajectory_target_scale = p.trajectory_target_scale; c.trajectory_target_maximum = p.trajectory_target_maximum;
+    c.trajectory_position_cost = quad(p.trajectory_position_cost); c.trajectory_position_threshold = p.trajectory_position_threshold;
+    c.trajectory_velocity_cost = quad(p.trajectory_velocity_cost); c.trajectory_velocity_minimum = p.trajectory_velocity_minimum;
+    c.trajectory_velocity_maximum = p.trajectory_velocity_maximum; c.trajectory_velocity_dropoff = p.trajectory_velocity_dropoff;
+    c.manipulability_cost = quad(p.manipulability_cost);
+    return c;
+}
 
 struct Handle {
+    std::unique_ptr<TableDynamicsForecast> dynamics_forecast;   // outlives the trajectory's handles
     std::unique_ptr<mppi::Trajectory> traj;
     std::shared_ptr<oracle::WrenchTable> table;
     double dt;
@@ -99,13 +202,26 @@ void *ref_create(const mppi_b200_config *c, const void *params, size_t) {
         dyn = std::make_unique<RefToyDynamics>();
         cost = std::make_unique<RefToyCost>(*static_cast<const mppi_b200_toy_objective *>(params));
     } else if (c->objective == MPPI_B200_OBJECTIVE_TRACK_POINT) {
-        dyn = std::make_unique<RefFrankaDynamics>();
-        cost = std::make_unique<RefFrankaCost<oracle::TrackPointCost>>(oracle::TrackPointCost(*static_cast<const mppi_b200_track_point *>(params)));
+        // the reference's own objective (objective/track_point.cpp, compiled unmodified)
+        const auto &p = *static_cast<const mppi_b200_track_point *>(params);
+        auto d = std::make_unique<RefFrankaDynamics>();
+        d->link_mode = p.link_position_mode;
+        dyn = std::move(d);
+        cost = FrankaRidgeback::TrackPoint::create(track_point_configuration(p));
     } else {
-        dyn = std::make_unique<RefFrankaDynamics>();
+        // the reference's own objective (objective/assisted_manipulation.cpp) reading the forecast wrench through the
+        // reference's own DynamicsForecast handle (frankaridgeback/dynamics.cpp)
+        const auto &p = *static_cast<const mppi_b200_assisted_manipulation *>(params);
         h->table = std::make_shared<oracle::WrenchTable>();
-        cost = std::make_unique<RefFrankaCost<oracle::AssistedManipulationCost>>(
-            oracle::AssistedManipulationCost(*static_cast<const mppi_b200_assisted_manipulation *>(params), h->table));
+        FrankaRidgeback::DynamicsForecast::Configuration fc{};
+        fc.time_step = c->time_step; fc.horison = c->horison;
+        h->dynamics_forecast = std::make_unique<TableDynamicsForecast>(fc, std::make_unique<TableForecast>(h->table), (unsigned)std::ceil(c->horison / c->time_step));
+        auto d = std::make_unique<RefFrankaDynamics>();
+        d->link_mode = p.link_position_mode;
+        d->table = h->table;
+        d->forecast = h->dynamics_forecast->create_handle();
+        dyn = std::move(d);
+        cost = FrankaRidgeback::AssistedManipulation::create(assisted_configuration(p));
     }
     h->traj = mppi::Trajectory::create(cfg, std::move(dyn), std::move(cost));
     if (!h->traj) return nullptr;
@@ -146,6 +262,106 @@ int ref_read(void *p, int what, double *out, size_t bytes) {
         case MPPI_B200_READ_OPTIMAL_COST: if (bytes != 8) return -1; out[0] = t.get_optimal_total_cost(); return 0;
     }
     return -1;
+}
+
+// ---- the reference's objectives and cost functors evaluated on caller-supplied kinematics ------------------------
+// `in` (OBJECTIVE_PROBE_DOUBLES = 159): state[31], end-effector position[3], linear velocity[3], jacobian[6][12]
+// row-major, ARM_MOUNT_JOINT position[3], link positions[13][3] (Link enum order), tank energy, has_forecast, wrench[6].
+namespace {
+struct ProbeDynamics : FrankaRidgeback::Dynamics {
+    VectorXd x = VectorXd(31), jq = VectorXd(12), jv = VectorXd(12);
+    FrankaRidgeback::EndEffectorState ee;
+    Vector3d mount; double links[13][3]; double energy = 0.0;
+    std::unique_ptr<FrankaRidgeback::DynamicsForecast::Handle> forecast;
+    std::unique_ptr<mppi::Dynamics> copy() override { return nullptr; }
+    Eigen::Ref<VectorXd> step(const VectorXd &, double) override { return x; }
+    void set_state(const VectorXd &s, double) override { x = s; }
+    Eigen::Ref<VectorXd> get_state() override { return x; }
+    constexpr int get_control_dof() override { return 12; }
+    constexpr int get_state_dof() override { return 31; }
+    const VectorXd &get_joint_position() const override { return jq; }
+    const VectorXd &get_joint_velocity() const override { return jv; }
+    Vector3d get_frame_position(FrankaRidgeback::Frame) override { return mount; }
+    Quaterniond get_frame_orientation(FrankaRidgeback::Frame) override { return Quaterniond::Identity(); }
+    Vector3d get_link_position(FrankaRidgeback::Link l) override { return Vector3d(links[(int)l][0], links[(int)l][1], links[(int)l][2]); }
+    const FrankaRidgeback::EndEffectorState &get_end_effector_state() const override { return ee; }
+    double get_joint_power() const override { return 0.0; }
+    double get_external_power() const override { return 0.0; }
+    double get_tank_energy() const override { return energy; }
+    const FrankaRidgeback::DynamicsForecast::Handle *get_forecast() const override { return forecast.get(); }
+    Vector6d get_end_effector_simulated_wrench() const override { return Vector6d::Zero(); }
+    void add_end_effector_simulated_wrench(Vector6d) override {}
+};
+}  // namespace
+
+// out[8]: total, joint, self_collision, workspace, energy, velocity, trajectory, manipulability (assisted manipulation);
+// out[0] only for track point. One get_cost call per probe after reset (the getters are the logger's running totals).
+int ref_objective_probe(int objective, const void *params, const double *in, long count, double *out) {
+    auto table = std::make_shared<oracle::WrenchTable>();
+    FrankaRidgeback::DynamicsForecast::Configuration fc{};
+    fc.time_step = 0.01; fc.horison = 1.0;
+    TableDynamicsForecast df(fc, std::make_unique<TableForecast>(table), 100);
+    std::unique_ptr<FrankaRidgeback::TrackPoint> tp;
+    std::unique_ptr<FrankaRidgeback::AssistedManipulation> am;
+    if (objective == MPPI_B200_OBJECTIVE_TRACK_POINT) tp = FrankaRidgeback::TrackPoint::create(track_point_configuration(*static_cast<const mppi_b200_track_point *>(params)));
+    else am = FrankaRidgeback::AssistedManipulation::create(assisted_configuration(*static_cast<const mppi_b200_assisted_manipulation *>(params)));
+    for (long n = 0; n < count; n++) {
+        const double *p = in + n * 159;
+        ProbeDynamics d;
+        for (int i = 0; i < 31; i++) d.x[i] = p[i];
+        for (int i = 0; i < 12; i++) { d.jq[i] = p[i]; d.jv[i] = p[12 + i]; }
+        d.ee.position = Vector3d(p[31], p[32], p[33]);
+        d.ee.linear_velocity = Vector3d(p[34], p[35], p[36]);
+        for (int r = 0; r < 6; r++) for (int j = 0; j < 12; j++) d.ee.jacobian(r, j) = p[37 + r * 12 + j];
+        d.mount = Vector3d(p[109], p[110], p[111]);
+        for (int l = 0; l < 13; l++) for (int k = 0; k < 3; k++) d.links[l][k] = p[112 + l * 3 + k];
+        d.energy = p[151];
+        if (p[152] != 0.0) {
+            table->present = true; table->t0 = 0.0; table->dt = 0.01;
+            table->w.assign(p + 153, p + 159);
+            d.forecast = df.create_handle();
+        }
+        VectorXd control(12);
+        double *o = out + n * 8;
+        if (tp) {
+            o[0] = tp->get_cost(d.x, control, &d, 0.0);
+            for (int i = 1; i < 8; i++) o[i] = 0.0;
+        } else {
+            am->reset(0.0);
+            o[0] = am->get_cost(d.x, control, &d, 0.0);
+            o[1] = am->get_joint_limit_cost(); o[2] = am->get_self_collision_cost(); o[3] = am->get_workspace_cost();
+            o[4] = am->get_energy_tank_cost(); o[5] = am->get_joint_velocity_cost(); o[6] = am->get_trajectory_cost();
+            o[7] = am->get_manipulability_cost();
+        }
+    }
+    return 0;
+}
+
+// cost.hpp functors: kind 0 QuadraticCost{a=constant,b=linear,c=quadratic}, 1 LeftInverseBarrier{a=bound,b=scale,c=max},
+// 2 RightInverseBarrier, 3 UpperLogarithmicBarrier{a=bound,b=scale,c=offset,d=max}, 4 LowerLogarithmicBarrier
+void ref_cost_functor(int kind, double a, double b, double c, double d, const double *values, long count, double *out) {
+    for (long i = 0; i < count; i++) {
+        const double v = values[i];
+        switch (kind) {
+            case 0: out[i] = QuadraticCost{a, b, c}(v); break;
+            case 1: out[i] = LeftInverseBarrierFunction{a, b, c}(v); break;
+            case 2: out[i] = RightInverseBarrierFunction{a, b, c}(v); break;
+            case 3: out[i] = UpperLogarithmicBarrierFunction{a, b, c, d}(v); break;
+            default: out[i] = LowerLogarithmicBarrierFunction{a, b, c, d}(v); break;
+        }
+    }
+}
+
+// energy.hpp (compiled as it lies): n steps of EnergyTank::step from an initial energy; out = energy after each step
+void ref_energy_tank(double initial, const double *power, double dt, long count, double *out) {
+    EnergyTank tank(initial);
+    for (long i = 0; i < count; i++) { tank.step(power[i], dt); out[i] = tank.get_energy(); }
+}
+
+// frankaridgeback/state.cpp: make_state(Preset)
+void ref_make_state(int preset, double *out) {
+    FrankaRidgeback::State s = FrankaRidgeback::make_state((FrankaRidgeback::Preset)preset);
+    for (int i = 0; i < 31; i++) out[i] = s[i];
 }
 
 // gram_sg::ComputeWeights straight from the reference (gram_savitzky_golay.cpp:46-53)

@@ -40,6 +40,7 @@ def load():
     for f in (lib.oracle_upper_log_barrier, lib.oracle_lower_log_barrier):
         f.argtypes = [C.c_double] * 5
         f.restype = C.c_double
+    lib.oracle_objective_probe.argtypes = [C.c_int, C.c_void_p, _dp, C.c_long, _dp]
     lib.oracle_tank.argtypes = [C.c_double, C.c_double, C.c_double, _dp]
     lib.oracle_sg_run.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_int, _dp, C.c_double, _dp, _dp]
     lib.oracle_robot_fk.argtypes = [_dp, _dp, _dp, _dp]
