@@ -143,7 +143,9 @@ inline std::unique_ptr<Forecast> Forecast::create(const Configuration &configura
             if (!configuration.locf) { std::cerr << "locf forecast selected with no configuration provided" << std::endl; return nullptr; }
             return LOCFForecast::create(*configuration.locf);
         case Configuration::AVERAGE:
-            if (!configuration.average) { std::cerr << "average forecast selected with no configuration provided" << std::endl; return nullptr; }
+            // the reference tests `locf` here (forecast.cpp:20) and then dereferences `average`: an average forecaster needs
+            // both present there; without `average` the reference is undefined, here it is the same refusal
+            if (!configuration.locf || !configuration.average) { std::cerr << "average forecast selected with no configuration provided" << std::endl; return nullptr; }
             return AverageForecast::create(*configuration.average);
         case Configuration::KALMAN:
             if (!configuration.kalman) { std::cerr << "kalman forecast selected with no configuration provided" << std::endl; return nullptr; }

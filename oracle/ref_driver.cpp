@@ -17,6 +17,7 @@
 #include "frankaridgeback/objective/assisted_manipulation.hpp"
 #include "controller/energy.hpp"                                // the reference's energy tank
 #include "systems.hpp"           // oracle systems
+#include "dynamics_forecast_oracle.hpp"   // rotation_to_quaternion, record layout
 
 namespace {
 
@@ -69,6 +70,9 @@ struct RefFrankaDynamics : FrankaRidgeback::Dynamics {
         ee.linear_acceleration = Vector3d(c.ee.linear_acceleration.x, c.ee.linear_acceleration.y, c.ee.linear_acceleration.z);
         ee.angular_acceleration = Vector3d(c.ee.angular_acceleration.x, c.ee.angular_acceleration.y, c.ee.angular_acceleration.z);
         for (int r = 0; r < 6; r++) for (int j = 0; j < 12; j++) ee.jacobian(r, j) = c.ee.jacobian[r][j];
+        double xyzw[4];
+        oracle::rotation_to_quaternion(c.ee.orientation, xyzw);   // Quaterniond(rotation), pinocchio_dynamics.cpp:219
+        ee.orientation = Quaterniond(xyzw[3], xyzw[0], xyzw[1], xyzw[2]);
     }
     Eigen::Ref<VectorXd> step(const VectorXd &u, double dt) override {
         const double *n = inner.step(u.data(), dt);
@@ -362,6 +366,61 @@ void ref_energy_tank(double initial, const double *power, double dt, long count,
 void ref_make_state(int preset, double *out) {
     FrankaRidgeback::State s = FrankaRidgeback::make_state((FrankaRidgeback::Preset)preset);
     for (int i = 0; i < 31; i++) out[i] = s[i];
+}
+
+// ---- the reference's DynamicsForecast (frankaridgeback/dynamics.cpp:58-138 + dynamics.hpp:122-408) with its own wrench
+// forecaster (forecast.cpp / kalman.cpp), rolling the oracle's rigid-body core forward: SURVEY 8f-2. ----
+// type: 0 LOCF, 1 AVERAGE, 2 KALMAN (Forecast::Configuration::Type)
+void *ref_dynamics_forecast_create(double time_step, double horison, int type, double forecast_horison_or_window, double forecast_time_step, unsigned order) {
+    FrankaRidgeback::DynamicsForecast::Configuration c{};
+    c.time_step = time_step; c.horison = horison;
+    VectorXd zero(6);
+    c.end_effector_wrench_forecast.type = (Forecast::Configuration::Type)type;
+    if (type == 0) c.end_effector_wrench_forecast.locf = LOCFForecast::Configuration{.observation = zero, .horison = forecast_horison_or_window};
+    else if (type == 1) {
+        c.end_effector_wrench_forecast.average = AverageForecast::Configuration{.states = 6, .window = forecast_horison_or_window};
+        c.end_effector_wrench_forecast.locf = LOCFForecast::Configuration{.observation = zero, .horison = 0.0};   // Forecast::create tests `locf` for AVERAGE (forecast.cpp:20)
+    }
+    else c.end_effector_wrench_forecast.kalman = KalmanForecast::Configuration{.observed_states = 6, .time_step = forecast_time_step, .horison = forecast_horison_or_window,
+                                                                              .order = order, .variance = zero, .initial_state = zero};
+    return FrankaRidgeback::DynamicsForecast::create(c, std::make_unique<RefFrankaDynamics>()).release();
+}
+void ref_dynamics_forecast_destroy(void *h) { delete static_cast<FrankaRidgeback::DynamicsForecast *>(h); }
+int ref_dynamics_forecast_steps(void *h) { return (int)static_cast<FrankaRidgeback::DynamicsForecast *>(h)->get_end_effector_trajectory().size(); }
+void ref_dynamics_forecast_observe(void *h, const double *wrench, double time) {
+    Vector6d w;
+    for (int i = 0; i < 6; i++) w[i] = wrench[i];
+    static_cast<FrankaRidgeback::DynamicsForecast *>(h)->observe_wrench(w, time);
+}
+void ref_dynamics_forecast_observe_time(void *h, double time) { static_cast<FrankaRidgeback::DynamicsForecast *>(h)->observe_time(time); }
+void ref_dynamics_forecast_run(void *h, const double *state, double time) {
+    FrankaRidgeback::State s;
+    for (int i = 0; i < 31; i++) s[i] = state[i];
+    static_cast<FrankaRidgeback::DynamicsForecast *>(h)->forecast(s, time);
+}
+// steps x MPPI_B200_DYNAMICS_FORECAST_RECORD, the layout of include/mppi_b200.h
+void ref_dynamics_forecast_read(void *h, double *out) {
+    auto &f = *static_cast<FrankaRidgeback::DynamicsForecast *>(h);
+    const std::size_t steps = f.get_end_effector_trajectory().size();
+    for (std::size_t k = 0; k < steps; k++) {
+        double *r = out + k * oracle::DF_RECORD;
+        const auto &e = f.get_end_effector_trajectory()[k];
+        for (int i = 0; i < 12; i++) r[i] = f.get_joint_position()[k][i];
+        for (int i = 0; i < 3; i++) { r[12 + i] = e.position[i]; r[19 + i] = e.linear_velocity[i]; r[22 + i] = e.angular_velocity[i]; r[25 + i] = e.linear_acceleration[i]; r[28 + i] = e.angular_acceleration[i]; }
+        r[15] = e.orientation.x(); r[16] = e.orientation.y(); r[17] = e.orientation.z(); r[18] = e.orientation.w();
+        r[31] = f.get_joint_power_trajectory()[k]; r[32] = f.get_external_power_trajectory()[k]; r[33] = f.get_energy_trajectory()[k];
+        for (int i = 0; i < 6; i++) r[34 + i] = f.get_wrench_trajectory()[k][i];
+        for (int a = 0; a < 6; a++) for (int j = 0; j < 12; j++) r[40 + a * 12 + j] = e.jacobian(a, j);
+    }
+}
+// parameterise() is protected (dynamics.hpp:361-376): recovered from the record get_end_effector_state(time) returns
+long ref_dynamics_forecast_parameterise(void *h, double time) {
+    auto &f = *static_cast<FrankaRidgeback::DynamicsForecast *>(h);
+    return (long)(&f.get_end_effector_state(time) - f.get_end_effector_trajectory().data());
+}
+void ref_dynamics_forecast_wrench(void *h, double time, double *out) {
+    Vector6d w = static_cast<FrankaRidgeback::DynamicsForecast *>(h)->get_end_effector_wrench(time);
+    for (int i = 0; i < 6; i++) out[i] = w[i];
 }
 
 // gram_sg::ComputeWeights straight from the reference (gram_savitzky_golay.cpp:46-53)

@@ -68,6 +68,22 @@ def test_state_presets_match_the_reference():
     assert (presets[1:, 30] == 100.0).all()
 
 
+@pytest.mark.parametrize("case", ["kalman1", "locf", "average"])
+def test_dynamics_forecast_oracle_matches_the_reference(oracle, case):
+    """the reference's own DynamicsForecast (frankaridgeback/dynamics.cpp) and wrench forecasters over the
+    oracle's rigid-body core against the oracle's restatement of the loop: recording order, wrench lookups, indexing."""
+    import dynamics_forecast_script as dfs
+    name, typ, hw, fdt, order = [c for c in dfs.CASES if c[0] == case][0]
+    f = dfs.Oracle(oracle, typ, hw, fdt, order)
+    rec, idx = dfs.run_session(f, 31)
+    f.close()
+    want = GOLDEN["dynamics_forecast/%s/records" % case]
+    assert rec.shape == want.shape == (3, 20, abi.DYNAMICS_FORECAST_RECORD)
+    assert np.array_equal(rec, want), np.abs(rec - want).max()
+    assert np.array_equal(idx, GOLDEN["dynamics_forecast/%s/parameterise" % case])
+    assert np.abs(want[..., abi.DF_WRENCH]).max() > 1.0
+
+
 @pytest.mark.skipif(not ref_lib.available(), reason="oracle/_ref not built here")
 def test_objective_golden_is_reproducible_from_the_reference_build():
     import importlib.util
