@@ -238,11 +238,10 @@ public:
         if (m_reference_rng) sample_like_the_reference(time);
         const void *noise = m_reference_rng ? m_reference_noise.data() : m_injected;
         const int source = noise ? MPPI_B200_NOISE_HOST : MPPI_B200_NOISE_PHILOX;
-        int rc;
-        {
-            std::scoped_lock lock(m_optimal_control_mutex);  // get() may run concurrently (mppi.cpp:179,492)
-            rc = mppi_b200_update(m_engine, m_rollout_state.data(), time, wrench, noise, source, m_seed);
-        }
+        // get() may run concurrently (mppi.cpp:179,492): the engine takes its own lock around the publication of the new
+        // sequence only, like the reference around `m_optimal_control = m_optimal_control_shifted` (mppi.cpp:178-182) —
+        // a control thread calling get() never waits for a running update
+        const int rc = mppi_b200_update(m_engine, m_rollout_state.data(), time, wrench, noise, source, m_seed);
         if (rc == MPPI_B200_ERR_ALL_NAN) throw std::runtime_error("all nan rollouts");          // mppi.cpp:370
         if (rc == MPPI_B200_ERR_TIME) throw std::runtime_error(mppi_b200_last_error(m_engine));   // filter.cpp:37-44
         if (rc != MPPI_B200_OK) throw std::runtime_error(std::string("mppi_b200: ") + mppi_b200_last_error(m_engine));
@@ -278,7 +277,6 @@ public:
 
     // mppi.cpp:481-512
     void get(Ref<VectorXd> control, double time) {
-        std::scoped_lock lock(m_optimal_control_mutex);
         if (mppi_b200_get(m_engine, control.data(), time) != MPPI_B200_OK) throw std::logic_error("time >= m_last_rollout_time");
     }
     inline VectorXd operator()(double time) { VectorXd control(m_control_dof); get(control, time); return control; }
@@ -367,7 +365,6 @@ private:
     mutable MatrixXd m_gradient, m_optimal_control;
     mutable std::vector<Rollout> m_rollouts;
     std::vector<double> m_wrench;
-    std::mutex m_optimal_control_mutex;
     const double *m_injected = nullptr;
     bool m_reference_rng = false;
     std::unique_ptr<mppi_b200::ReferenceGaussian> m_gaussian;

@@ -65,15 +65,18 @@ struct mppi_b200_engine {
     int variant = VAR_TOY;
     bool faithful = false;
     std::vector<unsigned char> params;  // objective block in kernel arithmetic
-    // SLOTS snapshot slots, each with its own side stream: the optimal re-rollout of an update is one thread per
-    // controller for T steps (milliseconds for the assisted-manipulation objective), so several of them must be in
-    // flight for the side work to keep up with short updates (32 controllers per GPU: 1.25 ms per update)
-    static constexpr int SLOTS = 4;
-    cudaStream_t stream = nullptr, side[SLOTS] = {};
-    cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_main_done = nullptr, ev_side_done[SLOTS] = {};
-    bool side_pending[SLOTS] = {};
-    double *d_opt[SLOTS] = {};          // per slot: optimal cost [batch] | breakdown [8 x batch]
-    double *h_opt = nullptr;            // pinned, SLOTS x 9 x batch
+    // The optimal re-rollout (Trajectory::filter, mppi.cpp:450-479) is evaluated ON DEMAND: every update leaves a snapshot
+    // of its inputs and of the sequence it published, and the first read of the optimal cost / breakdown after an update
+    // runs the one-thread-per-controller rollout over that snapshot. (Round 1 ran it eagerly on side streams; next to the
+    // following update's rollout grid it cost that grid up to 38 % — config 2 FP32: 147 us per update without it, 204 us
+    // with it — for a value only the logger reads.)
+    static constexpr int SLOTS = 1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_end = nullptr;
+    long long optimal_for = -1;         // update_count the host copy of the optimal cost belongs to
+    bool snapshot_valid = false;        // the last update published (its snapshot is complete)
+    double *d_opt[SLOTS] = {};          // optimal cost [batch] | breakdown [8 x batch]
+    double *h_opt = nullptr;            // pinned, 9 x batch
     // host mirrors (pinned)
     unsigned char *h_frame = nullptr;  // Frame + wrench
     double *h_U = nullptr;             // nu*T (stable copy of the published sequence for get())
@@ -109,6 +112,7 @@ struct mppi_b200_engine {
     std::vector<void *> peer_mappings;
     unsigned long long attempts = 0;
     std::string error;
+    std::mutex publish_mutex;            // guards h_U + last_rollout_time: mppi_b200_get may run on another thread during an update (mppi.cpp:178-182,492)
     float last_ms = 0.f;
     bool profiling = false;
     std::vector<double> weights_total;   // per controller
@@ -148,7 +152,6 @@ void mppi_b200_destroy(mppi_b200_engine *e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    for (cudaStream_t s : e->side) if (s) cudaStreamSynchronize(s);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (void *p : e->peer_mappings) cudaIpcCloseMemHandle(p);
     if (e->mailbox) cudaFree(e->mailbox);
@@ -158,13 +161,11 @@ void mppi_b200_destroy(mppi_b200_engine *e) {
     if (e->h_U) cudaFreeHost(e->h_U);
     if (e->h_result) cudaFreeHost(e->h_result);
     if (e->h_stats) cudaFreeHost(e->h_stats);
-    for (cudaEvent_t ev : {e->ev_start, e->ev_end, e->ev_main_done}) if (ev) cudaEventDestroy(ev);
-    for (cudaEvent_t ev : e->ev_side_done) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {e->ev_start, e->ev_end}) if (ev) cudaEventDestroy(ev);
     if (e->h_opt) cudaFreeHost(e->h_opt);
     for (cudaGraphExec_t g : e->graph) if (g) cudaGraphExecDestroy(g);
     for (cudaEvent_t ev : e->ev_stage) if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
-    for (cudaStream_t s : e->side) if (s) cudaStreamDestroy(s);
     delete e;
 }
 
@@ -253,10 +254,7 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     e->frame_bytes = sizeof(Frame) + sizeof(double) * 6 * T;   // per controller
 
     CREATE_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    for (cudaStream_t &s : e->side) CREATE_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (cudaEvent_t *ev : {&e->ev_start, &e->ev_end}) CREATE_TRY(cudaEventCreate(ev));
-    CREATE_TRY(cudaEventCreateWithFlags(&e->ev_main_done, cudaEventDisableTiming));
-    for (cudaEvent_t &ev : e->ev_side_done) CREATE_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CREATE_TRY(cudaMallocHost(&e->h_frame, e->frame_bytes * B));
     CREATE_TRY(cudaMallocHost(&e->h_U, n * B * sizeof(double)));
     CREATE_TRY(cudaMallocHost(&e->h_stats, 16 * B * sizeof(double)));
@@ -346,9 +344,6 @@ int host_prepare(mppi_b200_engine *e, const double *state, double time, const do
         if (wrench && !e->wrench_device) std::memcpy(base + sizeof(Frame), wrench + (size_t)c * 6 * d.T, sizeof(double) * 6 * d.T);
     }
     e->attempts++;
-    // snapshot slot for the side-stream re-rollout
-    const int slot = (int)(e->update_count % mppi_b200_engine::SLOTS);
-    d.frame_snap = e->d_frame_snap[slot]; d.U_snap = e->d_U_snap[slot];
     return MPPI_B200_OK;
 }
 
@@ -420,26 +415,23 @@ int enqueue_exchange(mppi_b200_engine *e, int kind) {
     return MPPI_B200_OK;
 }
 
-// Optimal re-rollout (Trajectory::filter, mppi.cpp:450-479) off the critical path: with no mppi::Filter
-// attached (actor.cpp:100) it only produces the optimal cost and its per-term breakdown, so it runs on a
-// side stream over the snapshot the prepare block of k_sample / k_finish left in this update's slot.
-int launch_optimal(mppi_b200_engine *e) {
+// Optimal re-rollout (Trajectory::filter, mppi.cpp:450-479), on demand: with no mppi::Filter attached (actor.cpp:100) it
+// only produces the optimal cost and its per-term breakdown, which nothing but the logger reads. Runs one thread per
+// controller over the snapshot the prepare block of k_sample / k_finish left behind; the engine is idle when this is
+// called (mppi_b200_read synchronises first).
+int run_optimal(mppi_b200_engine *e) {
     DeviceState &d = e->d;
-    const int slot = (int)(e->update_count % mppi_b200_engine::SLOTS);
-    cudaStream_t side = e->side[slot];
-    CUDA_TRY(e, cudaEventRecord(e->ev_main_done, e->stream));
-    CUDA_TRY(e, cudaStreamWaitEvent(side, e->ev_main_done, 0));
     DeviceState o = d;
-    o.frame = reinterpret_cast<const Frame *>(e->d_frame_snap[slot]);
-    o.wrench = e->d_frame_snap[slot] + sizeof(Frame) / sizeof(double);
-    o.U_shift = e->d_U_snap[slot];
+    o.frame = reinterpret_cast<const Frame *>(e->d_frame_snap[0]);
+    o.wrench = e->d_frame_snap[0] + sizeof(Frame) / sizeof(double);
+    o.U_shift = e->d_U_snap[0];
     o.noise = e->d_zero_row;
-    o.optimal_cost = e->d_opt[slot]; o.breakdown = e->d_opt[slot] + e->batch;   // [batch] | [8 x batch], per slot: slots overlap
-    CUDA_TRY(e, launch_rollout(o, e->cfg.precision, e->variant, e->faithful, e->params.data(), true, side));
+    o.optimal_cost = e->d_opt[0]; o.breakdown = e->d_opt[0] + e->batch;   // [batch] | [8 x batch]
+    CUDA_TRY(e, launch_rollout(o, e->cfg.precision, e->variant, e->faithful, e->params.data(), true, e->stream));
     e->launches += 1;
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_opt + (size_t)slot * 9 * e->batch, e->d_opt[slot], 9 * e->batch * sizeof(double), cudaMemcpyDeviceToHost, side));
-    CUDA_TRY(e, cudaEventRecord(e->ev_side_done[slot], side));
-    e->side_pending[slot] = true;
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_opt, e->d_opt[0], 9 * e->batch * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    e->optimal_for = e->update_count;
     return MPPI_B200_OK;
 }
 
@@ -455,6 +447,9 @@ int host_complete(mppi_b200_engine *e) {
     e->in_update = false;
     if (e->p2p && *e->h_p2p_error) { *e->h_p2p_error = 0; return fail(e, MPPI_B200_ERR_NCCL, "peer exchange timed out: a rank of the sharded rollout set did not arrive"); }
     bool all_nan = false, smoothed = false;
+    // the only section a concurrent mppi_b200_get waits for: the copy of the published sequence (the reference holds its
+    // mutex around `m_optimal_control = m_optimal_control_shifted` only, mppi.cpp:178-182)
+    std::lock_guard<std::mutex> publish(e->publish_mutex);
     for (int c = 0; c < e->batch; c++) {
         const double *res = e->h_result + (size_t)c * (n + 8);
         double *st = e->h_stats + 5 * c;
@@ -467,17 +462,11 @@ int host_complete(mppi_b200_engine *e) {
         if (!early_return) { e->weights_total[c] = st[4]; e->weights_valid[c] = 1; smoothed = true; }
     }
     if (all_nan && e->batch == 1) return fail(e, MPPI_B200_ERR_ALL_NAN, "all nan rollouts");
+    e->snapshot_valid = e->snapshot_valid || !all_nan;   // an update that threw leaves the previous optimal cost in place (the reference throws before filter())
     if (d.sg_enabled && smoothed) e->sg_last_trim = reinterpret_cast<Frame *>(e->h_frame)->time;
     e->last_rollout_time = reinterpret_cast<Frame *>(e->h_frame)->time;
     e->update_count++;
     if (all_nan) return fail(e, MPPI_B200_ERR_ALL_NAN, "all nan rollouts (in at least one controller of the batch)");
-    return MPPI_B200_OK;
-}
-
-// the previous user of this update's snapshot slot (SLOTS updates ago) must have finished
-int wait_slot(mppi_b200_engine *e) {
-    const int slot = (int)(e->update_count % mppi_b200_engine::SLOTS);
-    if (e->side_pending[slot]) CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_side_done[slot], 0));
     return MPPI_B200_OK;
 }
 
@@ -508,7 +497,6 @@ int mppi_b200_update_begin(mppi_b200_engine *e, const double *state, double time
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     int rc = host_prepare(e, state, time, wrench, noise, noise_source, seed);
     if (rc) return rc;
-    if ((rc = wait_slot(e))) return rc;
     CUDA_TRY(e, cudaEventRecord(e->ev_start, e->stream));
     if ((rc = enqueue_begin(e, noise, noise_source))) return rc;
     e->in_update = true;
@@ -528,7 +516,6 @@ int mppi_b200_update_finish(mppi_b200_engine *e) {
     if (rc) return rc;
     CUDA_TRY(e, cudaEventRecord(e->ev_end, e->stream));
     STAGE(e, 8);
-    if ((rc = launch_optimal(e))) return rc;
     return host_complete(e);
 }
 
@@ -541,7 +528,7 @@ int mppi_b200_update_launch(mppi_b200_engine *e, const double *state, double tim
     const bool graph_ok = e->use_graphs && noise_source == MPPI_B200_NOISE_PHILOX && !e->comm && !e->profiling;
     int rc = host_prepare(e, state, time, wrench, noise, noise_source, seed);
     if (rc) return rc;
-    const int slot = (int)(e->update_count % mppi_b200_engine::SLOTS);
+    const int slot = 0;
     if (graph_ok && !e->graph[slot]) {
         cudaGraph_t g = nullptr;
         const long long before = e->launches;
@@ -560,7 +547,6 @@ int mppi_b200_update_launch(mppi_b200_engine *e, const double *state, double tim
         cudaGraphDestroy(g);
         if (ce != cudaSuccess) return fail(e, MPPI_B200_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
     }
-    if ((rc = wait_slot(e))) return rc;
     CUDA_TRY(e, cudaEventRecord(e->ev_start, e->stream));
     if (graph_ok) {
         CUDA_TRY(e, cudaGraphLaunch(e->graph[slot], e->stream));
@@ -582,7 +568,6 @@ int mppi_b200_update_launch(mppi_b200_engine *e, const double *state, double tim
     }
     CUDA_TRY(e, cudaEventRecord(e->ev_end, e->stream));
     STAGE(e, 8);
-    if ((rc = launch_optimal(e))) return rc;
     e->in_update = true;
     return MPPI_B200_OK;
 }
@@ -617,7 +602,6 @@ int mppi_b200_synchronize(mppi_b200_engine *e) {
     if (!e) return MPPI_B200_ERR_INVALID;
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-    for (cudaStream_t s : e->side) CUDA_TRY(e, cudaStreamSynchronize(s));
     return MPPI_B200_OK;
 }
 
@@ -708,7 +692,8 @@ int mppi_b200_p2p_init(mppi_b200_engine *e, const void *handles) {
 int mppi_b200_get(mppi_b200_engine *e, double *control, double time) {
     if (!e || !control) return MPPI_B200_ERR_INVALID;
     const int nu = e->d.nu, T = e->d.T;
-    if (time < e->last_rollout_time) return fail(e, MPPI_B200_ERR_INVALID, "time >= m_last_rollout_time (assert, mppi.cpp:483)");
+    std::lock_guard<std::mutex> publish(e->publish_mutex);
+    if (time < e->last_rollout_time) return MPPI_B200_ERR_INVALID;   // "time >= m_last_rollout_time" (assert, mppi.cpp:483); no message: e->error belongs to the updating thread
     const double t0 = (time - e->last_rollout_time) / e->d.dt;
     const int lower = (int)t0, upper = lower + 1;
     for (int c = 0; c < e->batch; c++) {
@@ -759,9 +744,14 @@ int mppi_b200_read(mppi_b200_engine *e, int32_t what, void *dst, size_t bytes) {
             for (size_t c = 0; c < B; c++) { static_cast<double *>(dst)[2 * c] = -e->h_stats[5 * c]; static_cast<double *>(dst)[2 * c + 1] = e->h_stats[5 * c + 1]; }
             return MPPI_B200_OK;
         }
-        // the re-rollout of the LAST update: its slot's pinned copy (every stream was synchronised above)
-        case MPPI_B200_READ_OPTIMAL_COST: if (!need(B * 8)) break; std::memcpy(dst, e->h_opt + ((e->update_count + mppi_b200_engine::SLOTS - 1) % mppi_b200_engine::SLOTS) * 9 * B, bytes); return MPPI_B200_OK;
-        case MPPI_B200_READ_BREAKDOWN: if (!need(B * 64)) break; std::memcpy(dst, e->h_opt + ((e->update_count + mppi_b200_engine::SLOTS - 1) % mppi_b200_engine::SLOTS) * 9 * B + B, bytes); return MPPI_B200_OK;
+        // the re-rollout of the LAST update, evaluated by the first read after it (run_optimal)
+        case MPPI_B200_READ_OPTIMAL_COST:
+        case MPPI_B200_READ_BREAKDOWN: {
+            if (!need(what == MPPI_B200_READ_OPTIMAL_COST ? B * 8 : B * 64)) break;
+            if (e->snapshot_valid && e->optimal_for != e->update_count) { rc = run_optimal(e); if (rc) return rc; }
+            std::memcpy(dst, e->h_opt + (what == MPPI_B200_READ_OPTIMAL_COST ? 0 : B), bytes);
+            return MPPI_B200_OK;
+        }
         case MPPI_B200_READ_KEPT: {
             const size_t k = bytes / 8;
             if (bytes % 8 || k > B * (size_t)std::max<long long>(d.keep_best, 1)) break;

@@ -6,6 +6,7 @@
 // After the horizon the block folds its costs into the running min / max (warp shuffles, then one
 // order-preserving atomicMin / atomicMax per block) so no separate reduction pass is needed.
 #pragma once
+#include <algorithm>
 #include <cstdlib>
 #include "kernels.cuh"
 
@@ -40,7 +41,7 @@ __device__ __forceinline__ double decode_ordered(unsigned long long e) {
 #define MPPI_LEAN_MIN_BLOCKS 1
 #endif
 template <class R, int VAR, bool FAITHFUL, class ParamsT, bool BIG = false>
-__global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG) ? MPPI_LEAN_MIN_BLOCKS : 1) k_rollout(const __grid_constant__ DeviceState d, const __grid_constant__ ParamsT P, int optimal_only) {
+__global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG) ? MPPI_LEAN_MIN_BLOCKS : 1) k_rollout(const __grid_constant__ DeviceState d, const __grid_constant__ ParamsT P, int optimal_only, int lockstep) {
     // blockIdx.y = controller of a batched engine. Only the handful of buffers this kernel touches are offset
     // by hand (a full controller_view copy of the state costs ~40 registers here, i.e. a resident warp per SM).
     const size_t c = blockIdx.y;
@@ -57,28 +58,39 @@ __global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG)
     const int has_w = frame->has_wrench;
     for (int i = threadIdx.x; i < 6 * d.T; i += blockDim.x) sW[i] = has_w ? (R)wrench[i] : R(0);
     for (int i = threadIdx.x; i < 32; i += blockDim.x) sx[i] = (R)frame->x0[i];
+    double *sx64 = sDisc + d.T;                            // 32: the initial state unrounded (FP32 fast mode)
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) sx64[i] = frame->x0[i];
+    // the control sequence unrounded, for the FP64 state path of the fast mode (only those kernels reserve the room)
+    constexpr bool STATE_PATH64 = sizeof(R) == 4 && MPPI_MIXED_STATE >= 2 && !FAITHFUL && (VAR == VAR_TP_FULL || VAR == VAR_AM || VAR == VAR_AM_ENERGY);
+    double *sU64 = sx64 + 32;
+    if constexpr (STATE_PATH64) for (int i = threadIdx.x; i < d.nu * d.T; i += blockDim.x) sU64[i] = Usrc[i];
     for (int i = threadIdx.x; i < d.T; i += blockDim.x) sDisc[i] = discount_pow(d.discount, i);
     __syncthreads();
 
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double cost = 0.0;
-    bool active = optimal_only ? (k == 0) : (k < d.k_count);
-    if (active) {
+    const bool active = optimal_only ? (k == 0) : (k < d.k_count);
+    // lockstep blocks meet at barriers inside the step loop: the threads past the end of the rollout set run the last
+    // rollout once more (and write nothing) instead of leaving
+    if (lockstep && !optimal_only && !active) k = d.k_count - 1;
+    if (active || (lockstep && !optimal_only)) {
         // the optimal re-rollout (Trajectory::filter, mppi.cpp:450-479) reads a row of zeros shared by all controllers
         const R *eps = static_cast<const R *>(d.noise) + (optimal_only ? (size_t)0 : (c * (size_t)d.k_count + (size_t)k) * n);
         if constexpr (VAR == VAR_TOY) {
             cost = rollout_toy<R>(P, sx, sU, eps, d.T, (R)d.dt, d.discount);
         } else {
             RolloutInputs<R> in;
-            in.x0 = sx; in.U = sU; in.W = has_w ? sW : nullptr; in.T = d.T; in.dt = (R)d.dt; in.discount = d.discount; in.discount_table = sDisc;
+            in.x0 = sx; in.x0_64 = sx64; in.U = sU; in.W = has_w ? sW : nullptr; in.T = d.T; in.dt = (R)d.dt; in.dt64 = d.dt; in.discount = d.discount; in.discount_table = sDisc;
+            in.lockstep = optimal_only ? 0 : lockstep;
+            if constexpr (STATE_PATH64) in.U64 = sU64;
             double bd[7] = {0, 0, 0, 0, 0, 0, 0};
-            cost = rollout_franka<R, VAR, FAITHFUL, ParamsT, BIG>(MPPI_DEVICE_MODEL, MPPI_DEVICE_FAST_MODEL, P, in, eps, optimal_only ? bd : nullptr);
-            if (optimal_only) {
+            cost = rollout_franka<R, VAR, FAITHFUL, ParamsT, BIG>(MPPI_DEVICE_MODEL, MPPI_DEVICE_FAST_MODEL, P, in, eps, optimal_only ? bd : nullptr, MPPI_DEVICE_FAST_MODEL64);
+            if (optimal_only && active) {
                 for (int i = 0; i < 7; i++) d.breakdown[8 * c + i] = bd[i];
                 d.breakdown[8 * c + 7] = cost;
             }
         }
-        if (optimal_only) d.optimal_cost[c] = cost; else d.costs[c * (size_t)d.k_count + k] = cost;
+        if (active) { if (optimal_only) d.optimal_cost[c] = cost; else d.costs[c * (size_t)d.k_count + k] = cost; }
     }
     if (optimal_only) return;
 
@@ -105,19 +117,31 @@ cudaError_t launch_rollout_t(const DeviceState &d, const void *params, bool opti
     const ParamsT &P = *static_cast<const ParamsT *>(params);
     // few rollouts: one warp per block spreads them over the SMs; many: 128-thread blocks
     int block = d.k_count <= 148 * 64 ? 32 : (d.k_count <= 148 * 256 ? 64 : 128);
+    // the kernels with the 75 KB step body are bound by instruction fetch, which the warps of an SM share: 128-thread
+    // blocks once there are enough rollouts to keep most SMs busy with them (config 3: 1225 -> 1200 us)
+    if ((VAR == VAR_AM || VAR == VAR_AM_ENERGY || VAR == VAR_TP_FULL) && d.k_count >= 148 * 96) block = 128;
     long long grid = optimal_only ? 1 : (d.k_count + block - 1) / block;
     if (optimal_only) block = 32;
-    size_t smem = sizeof(R) * ((size_t)d.nu * d.T + 6 * (size_t)d.T + 32) + sizeof(double) * (size_t)d.T;
+    size_t smem = sizeof(R) * ((size_t)d.nu * d.T + 6 * (size_t)d.T + 32) + sizeof(double) * ((size_t)d.T + 32);
+    if (sizeof(R) == 4 && MPPI_MIXED_STATE >= 2 && !FAITHFUL && (VAR == VAR_TP_FULL || VAR == VAR_AM || VAR == VAR_AM_ENERGY)) smem += sizeof(double) * (size_t)d.nu * d.T;
+    int lockstep = 0;
+    if constexpr (VAR == VAR_AM || VAR == VAR_AM_ENERGY || VAR == VAR_TP_FULL) {
+        // experiment switches (A/B runs): block size and barriers per step of the kernels with the large step body
+        static const int env_block = std::getenv("MPPI_B200_AM_BLOCK") ? std::atoi(std::getenv("MPPI_B200_AM_BLOCK")) : 0;
+        static const int env_lockstep = std::getenv("MPPI_B200_LOCKSTEP") ? std::atoi(std::getenv("MPPI_B200_LOCKSTEP")) : 0;
+        if (!optimal_only && env_block > 0) { block = env_block; grid = (d.k_count + block - 1) / block; }
+        lockstep = env_lockstep;
+    }
     auto kern = k_rollout<R, VAR, FAITHFUL, ParamsT, false>;
     if constexpr (VAR == VAR_TP_LEAN && !FAITHFUL) {
         static const long long big_from = std::getenv("MPPI_B200_BIG_FROM") ? std::atoll(std::getenv("MPPI_B200_BIG_FROM")) : 0;   // see the note above k_rollout
-        if (!optimal_only && d.k_count * (long long)d.batch >= big_from) kern = k_rollout<R, VAR, FAITHFUL, ParamsT, true>;
+        if (d.k_count * (long long)d.batch >= big_from) kern = k_rollout<R, VAR, FAITHFUL, ParamsT, true>;   // the on-demand re-rollout runs the same build
     }
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<dim3((unsigned)grid, d.batch), block, smem, s>>>(d, P, optimal_only ? 1 : 0);
+    kern<<<dim3((unsigned)grid, d.batch), block, smem, s>>>(d, P, optimal_only ? 1 : 0, lockstep);
     return cudaGetLastError();
 }
 

@@ -7,6 +7,7 @@ __constant__ FastModel<double> c_fast_f64;
 }
 #define MPPI_DEVICE_MODEL c_model_f64
 #define MPPI_DEVICE_FAST_MODEL c_fast_f64
+#define MPPI_DEVICE_FAST_MODEL64 nullptr
 #include "k_rollout.cuh"
 namespace mppi_b200 {
 cudaError_t upload_robot_model_f64() {

@@ -21,7 +21,7 @@ template <class R> inline TrackPointP<R> convert(const mppi_b200_track_point &p)
     for (int i = 0; i < 3; i++) o.point[i] = (R)p.point[i];
     static const double lo[10] = {-2.0, -2.0, -6.28, -2.8973, -1.7628, -2.8973, -3.0718, -2.8973, -0.0175, -2.8973};   // track_point.cpp:48-65
     static const double hi[10] = {2.0, 2.0, 6.28, 2.8973, 1.7628, 2.8973, 0.0698, 2.8973, 3.7525, 2.8973};
-    for (int i = 0; i < 10; i++) { o.lim_lo[i] = (R)lo[i]; o.lim_hi[i] = (R)hi[i]; }
+    for (int i = 0; i < 10; i++) { o.lim_lo[i] = (R)lo[i]; o.lim_hi[i] = (R)hi[i]; o.lim_lo64[i] = lo[i]; o.lim_hi64[i] = hi[i]; }
     o.joint_limits = p.enable_joint_limits; o.self_collision = p.enable_self_collision_avoidance; o.reach = p.enable_reach_limits;
     o.link_mode = p.link_position_mode;
     o.collision_limit = cvt<R>(p.self_collision_limit);
@@ -35,6 +35,8 @@ template <class R> inline AssistedP<R> convert(const mppi_b200_assisted_manipula
     o.energy = p.enable_energy_limit; o.velocity = p.enable_velocity_cost; o.trajectory = p.enable_trajectory_cost;
     o.manipulability = p.enable_manipulability_cost; o.link_mode = p.link_position_mode;
     for (int i = 0; i < 12; i++) { o.lower[i] = cvt<R>(p.lower_joint_limit[i]); o.upper[i] = cvt<R>(p.upper_joint_limit[i]); o.vel_quad[i] = (R)p.velocity_cost[i].quadratic_cost; }
+    for (int i = 0; i < 12; i++) { o.lower64[i] = p.lower_joint_limit[i].bound; o.upper64[i] = p.upper_joint_limit[i].bound; }
+    o.energy_below64 = p.energy_limit_below.bound; o.energy_above64 = p.energy_limit_above.bound;
     o.collision_limit = cvt<R>(p.self_collision_limit);
     pair_radii<R>(p.self_collision_radii, o.radii);
     o.ws_above = cvt<R>(p.workspace_limit_above); o.ws_infront = cvt<R>(p.workspace_limit_infront); o.ws_reach = cvt<R>(p.workspace_limit_reach);

@@ -10,6 +10,16 @@
 #include "robot.cuh"
 #include "robot_fast.cuh"
 
+// FP32 fast mode: 0 = everything single precision; 1 = the state (q, v, tank energy) carried and integrated in FP64 with
+// FP64 barrier sides; 2 = additionally the whole state path in FP64 for the objectives with barrier steps on kinematic
+// quantities (see MIXED_SOLVER in rollout_franka). A/B builds set it on the command line.
+#ifndef MPPI_MIXED_STATE
+#define MPPI_MIXED_STATE 2
+#endif
+#ifndef MPPI_MIXED_SOLVER_UNROLL
+#define MPPI_MIXED_SOLVER_UNROLL 7
+#endif
+
 namespace mppi_b200 {
 
 template <class R> struct BarrierP { R bound, scale, maxc; };
@@ -55,12 +65,25 @@ template <class R> MPPI_HD R left_barrier(const BarrierP<R> &b, R v) {
     return (v <= b.bound) ? outside : inside;
 }
 
+// FP32 fast mode, barriers on a STATE variable (joint positions, tank energy). The rollout carries those in FP64 (see
+// rollout_franka): which side of the bound the state is on is decided on the FP64 value against the FP64 bound — the
+// reference's 1e10 steps (cost.hpp:59-61,90-92) are then taken by exactly the rollouts that take them in FP64 unless the
+// state itself differs — while the magnitudes (distance squared, scale / distance) stay single precision.
+// d = v - bound (right) or bound - v (left): not negative = at or beyond the bound. The sign is read on the integer pipe.
+template <class R> MPPI_HD R barrier_signed(const BarrierP<R> &b, double d) {
+    const R df = (R)d;
+    const R outside = b.maxc + b.scale * (df * df);
+    const R inside = std_min(barrier_div(b.scale, -df), b.maxc);
+    return is_negative(d) ? inside : outside;
+}
+
 // ---- objective parameter blocks in kernel arithmetic -----------------------------------------
 template <class R> struct ToyP { R target[2]; R qp, qv, qu; };
 
 template <class R> struct TrackPointP {
     R point[3];
     R lim_lo[10], lim_hi[10];   // track_point.cpp:48-65 (hard-coded there); here in the parameter block so they are constant-bank operands
+    double lim_lo64[10], lim_hi64[10];   // the same limits unrounded: the FP32 fast mode tests its FP64 joint positions against these
     int joint_limits, self_collision, reach, link_mode;
     BarrierP<R> collision_limit;
     R radii[20];  // sum of the two sphere radii per checked pair
@@ -78,6 +101,7 @@ template <class R> struct AssistedP {
     R vel_quad[12];
     R traj_scale, traj_max, traj_threshold, traj_vmin, traj_vmax, traj_dropoff;
     QuadP<R> traj_position, traj_velocity, manip;
+    double lower64[12], upper64[12], energy_below64, energy_above64;   // unrounded bounds for the FP32 fast mode's FP64 state (barrier_signed)
 };
 
 // pairs of Link enum values minus 3 (PIVOT = 0 ... PANDA_LINK7 = 7): track_point.cpp:81-118
@@ -142,7 +166,8 @@ template <class R, int FLAGS> MPPI_HD void robot_kinematics(const RobotModel<R> 
 // objective/track_point.cpp:10-79,120-174
 // LEAN: the engine picked the variant without self-collision and reach terms, so they are compiled out
 // yaw: cos / sin of q[2] when the caller already has them (FUSED mode shares the step's joint sines / cosines), else null
-template <class R, bool LEAN = false> MPPI_HD R track_point_cost(const TrackPointP<R> &P, const R *q, const Kinematics<R> &K, const R *yaw = nullptr) {
+// q64: the FP64 joint positions of the FP32 fast mode (null in FP64 builds, where q is already that)
+template <class R, bool LEAN = false> MPPI_HD R track_point_cost(const TrackPointP<R> &P, const R *q, const Kinematics<R> &K, const R *yaw = nullptr, const double *q64 = nullptr) {
     const Vec3<R> e = K.ee_pos - v3<R>(P.point[0], P.point[1], P.point[2]);
     // 100 * |e|^2: the reference squares the norm it took the root of (track_point.cpp:38-41); the root is skipped here
     // (one rounding less, 1e-16 relative)
@@ -159,6 +184,16 @@ template <class R, bool LEAN = false> MPPI_HD R track_point_cost(const TrackPoin
         R c[2] = {R(0), R(0)};   // two partial sums: half the dependent additions (the sum differs from the sequential one by rounding only)
 #pragma unroll
         for (int i = 0; i < 10; i++) {
+            if constexpr (sizeof(R) == 4) {
+                if (q64) {   // sides decided on the FP64 state against the unrounded limits, magnitudes in single precision
+                    const double below = q64[i] - P.lim_lo64[i], above = P.lim_hi64[i] - q64[i];
+                    const double md = is_negative(below) ? below : above;
+                    const R m = (R)md;
+                    const R penalty = R(1000) + R(100000) * (m * m);
+                    c[i & 1] += is_negative(md) ? penalty : R(0);
+                    continue;
+                }
+            }
             const R below = q[i] - P.lim_lo[i], above = P.lim_hi[i] - q[i];
             const R m = is_negative(below) ? below : above;
             const R penalty = R(1000) + R(100000) * (m * m);
@@ -180,12 +215,19 @@ template <class R, bool LEAN = false> MPPI_HD R track_point_cost(const TrackPoin
 
 // objective/assisted_manipulation.cpp:37-319; bd (7 doubles) accumulates the per-term totals the
 // reference's logger reads after Trajectory::filter() (logging/assisted_manipulation.cpp:58-103).
-template <class R> MPPI_HD R assisted_cost(const AssistedP<R> &P, const R *q, const R *qd, R energy, const Kinematics<R> &K, const R *wrench, double *bd, const R *yaw = nullptr) {
+// q64 / energy64: the FP64 state of the FP32 fast mode (null in FP64 builds)
+template <class R> MPPI_HD R assisted_cost(const AssistedP<R> &P, const R *q, const R *qd, R energy, const Kinematics<R> &K, const R *wrench, double *bd, const R *yaw = nullptr,
+                                           const double *q64 = nullptr, double energy64 = 0.0) {
     R cost = R(0);
     if (P.joint_limit) {
         R c = R(0);
+        if (sizeof(R) == 4 && q64) {
 #pragma unroll
-        for (int i = 0; i < NJ; i++) c += left_barrier(P.lower[i], q[i]) + right_barrier(P.upper[i], q[i]);
+            for (int i = 0; i < NJ; i++) c += barrier_signed(P.lower[i], P.lower64[i] - q64[i]) + barrier_signed(P.upper[i], q64[i] - P.upper64[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NJ; i++) c += left_barrier(P.lower[i], q[i]) + right_barrier(P.upper[i], q[i]);
+        }
         if (bd) bd[0] += (double)c;
         cost += c;
     }
@@ -211,7 +253,8 @@ template <class R> MPPI_HD R assisted_cost(const AssistedP<R> &P, const R *q, co
         cost += c;
     }
     if (P.energy) {
-        const R c = left_barrier(P.energy_below, energy) + right_barrier(P.energy_above, energy);
+        const R c = (sizeof(R) == 4 && q64) ? barrier_signed(P.energy_below, P.energy_below64 - energy64) + barrier_signed(P.energy_above, energy64 - P.energy_above64)
+                                            : left_barrier(P.energy_below, energy) + right_barrier(P.energy_above, energy);
         if (bd) bd[3] += (double)c;
         cost += c;
     }
@@ -270,15 +313,27 @@ MPPI_HD void load_eps(const float *p, float *o) {
 #endif
 }
 
+// Kernels whose step is far larger than the instruction cache (assisted manipulation: 75 KB of straight-line code per
+// step) keep the warps of a block at the same place in that code, so a line fetched for one warp serves them all.
+MPPI_HD void lockstep_barrier() {
+#if defined(__CUDA_ARCH__)
+    __syncthreads();
+#endif
+}
+
 MPPI_HD double discount_pow(double g, int step) { return g == 1.0 ? 1.0 : pow(g, (double)step); }
 
 // Everything one rollout of the Franka+Ridgeback system needs that does not depend on the sample.
 template <class R> struct RolloutInputs {
     const R *x0;      // 31: q, qd, wrench, tank energy (state.hpp:113-260)
+    const double *x0_64 = nullptr;   // the same state unrounded (FP32 fast mode)
     const R *U;       // nu x T column-major: m_optimal_control_shifted
+    const double *U64 = nullptr;     // the same sequence unrounded (FP32 fast mode with the FP64 state path)
     const R *W;       // T x 6 forecast wrench table, or nullptr (no forecast handle)
     int T;
     R dt;
+    double dt64 = 0.0;   // the time step unrounded (FP32 fast mode: its FP64 state integrates with this one)
+    int lockstep = 0;    // > 0: the warps of a block meet at a barrier this many times per step (see k_rollout.cuh)
     double discount;
     const double *discount_table = nullptr;   // pow(discount, step) per step, staged by the kernel (keeps pow() out of the step loop)
 };
@@ -286,20 +341,50 @@ template <class R> struct RolloutInputs {
 // VAR selects objective + which kinematics are alive; FAITHFUL selects the dynamics evaluation.
 // eps: this rollout's noise, [t][d]. Returns the rollout cost (NaN = failed rollout, mppi.cpp:331-334).
 // BIG: the build for rollout sets that fill the machine (see k_rollout.cuh)
+// F64: the solver's model in FP64 (FP32 fast mode of the objectives with barrier steps: see MIXED_SOLVER below); null otherwise
 template <class R, int VAR, bool FAITHFUL, class ParamsT, bool BIG = false>
-MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, const ParamsT &P, const RolloutInputs<R> &in, const R *eps, double *bd) {
+MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, const ParamsT &P, const RolloutInputs<R> &in, const R *eps, double *bd, const FastModel<double> *F64 = nullptr) {
     constexpr int KF = VariantTraits<VAR>::kin;
     constexpr bool POWER = VariantTraits<VAR>::power;
     constexpr bool LEAN = !FAITHFUL && KF == 0 && !POWER;  // only the end effector position is read by the objective
+    // FP32 fast mode: the STATE (joint positions, velocities, tank energy) is carried and integrated in FP64, the dynamics
+    // and the objective read single-precision copies of it. Rounding the state to FP32 after every step moved rollouts
+    // across the reference's 1e10 barrier steps (cost.hpp:59-61,90-92) — one such "flip" changes the published control
+    // sequence by ~1e-4 of its maximum, the whole tolerance of the fast mode. The accelerations still come from the FP32
+    // solver; what is removed is the 6e-8 relative rounding of q and v per step, of the bounds and of the time step.
+    // (The lean reach-to-pose kernel stays all single precision: its only steps are the 1000-unit joint-limit penalties of
+    // track_point.cpp:48-65, a rollout on the other side of one moves the control sequence by ~1e-6, and the FP64 state
+    // cost it 7 % at config 4.)
+    constexpr bool MIXED = sizeof(R) == 4 && MPPI_MIXED_STATE && !LEAN;
+    // Objectives with 1e10 barrier steps on kinematic quantities (assisted manipulation, full reach-to-pose): the whole
+    // STATE PATH — control + noise, base velocity, joint sines / cosines, the solver qdd = M(q)^-1 tau, the integration —
+    // runs in FP64, so the trajectory is the FP64 kernel's; kinematics, RNEA (tank power) and the objective stay FP32.
+    // With the FP32 solver the trajectory drifts by ~1e-6 over the horizon and ~0.07 % of the rollouts end up on the
+    // other side of a barrier step than their FP64 twin (measured, config 3: 60 % of those at the collision spheres,
+    // 24 % at joint limits, 16 % at the workspace planes), each worth ~1e-4 of the published control sequence.
+    constexpr bool MIXED_SOLVER = MIXED && !FAITHFUL && !LEAN && MPPI_MIXED_STATE >= 2;
     R q[NJ], qd[NJ];
+    double q64[MIXED ? NJ : 1], qd64[MIXED ? NJ : 1], energy64 = 0.0;
 #pragma unroll
     for (int i = 0; i < NJ; i++) { q[i] = in.x0[i]; qd[i] = in.x0[NJ + i]; }
     R energy = in.x0[30];
+    if constexpr (MIXED) {
+        const double *x64 = in.x0_64;
+#pragma unroll
+        for (int i = 0; i < NJ; i++) { q64[i] = x64[i]; qd64[i] = x64[NJ + i]; }
+        energy64 = x64[30];
+    }
+    const double *q64p = MIXED ? q64 : nullptr;
     Kinematics<R> K;
     R cs[NJ], sn[NJ];
     // FUSED: one set of joint sines / cosines per state, evaluated when the state is formed (here and after every
     // integration) and read by the objective's yaw terms, the kinematics and the solver of the next step
-    if constexpr (!FAITHFUL) joint_sincos<R>(F, q, cs, sn);
+    double cs64[MIXED_SOLVER ? NJ : 1], sn64[MIXED_SOLVER ? NJ : 1];
+    if constexpr (MIXED_SOLVER) {
+        joint_sincos<double>(*F64, q64, cs64, sn64);
+#pragma unroll
+        for (int i = 2; i < 10; i++) { cs[i] = (R)cs64[i]; sn[i] = (R)sn64[i]; }
+    } else if constexpr (!FAITHFUL) joint_sincos<R>(F, q, cs, sn);
     if constexpr (LEAN) {
         K.ee_pos = ee_position_fast<R>(F, q, cs, sn);
     } else {
@@ -309,22 +394,30 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
     R e_next[NJ];
     load_eps(eps, e_next);
     for (int step = 0; step < in.T; ++step) {
+        if (in.lockstep > 0) lockstep_barrier();
         R u[NJ];
+        double u64[MIXED_SOLVER ? NJ : 1];
+        if constexpr (MIXED_SOLVER) {
 #pragma unroll
-        for (int d = 0; d < NJ; d++) u[d] = in.U[step * NJ + d] + e_next[d];
+            for (int d = 0; d < NJ; d++) { u64[d] = in.U64[step * NJ + d] + (double)e_next[d]; u[d] = (R)u64[d]; }
+        } else {
+#pragma unroll
+            for (int d = 0; d < NJ; d++) u[d] = in.U[step * NJ + d] + e_next[d];
+        }
         if (step + 1 < in.T) load_eps(eps + (step + 1) * NJ, e_next);  // next step's noise is in flight during this step
         R c;
         R yaw[2] = {cs[2], sn[2]};
         const R *yawp = FAITHFUL ? nullptr : yaw;
-        if constexpr (VAR == VAR_TP_LEAN) c = track_point_cost<R, true>(P, q, K);
-        else if constexpr (VAR == VAR_TP_FULL) c = track_point_cost<R>(P, q, K, yawp);
-        else c = assisted_cost<R>(P, q, qd, energy, K, in.W ? in.W + step * 6 : nullptr, bd, yawp);
+        if constexpr (VAR == VAR_TP_LEAN) c = track_point_cost<R, true>(P, q, K, nullptr, q64p);
+        else if constexpr (VAR == VAR_TP_FULL) c = track_point_cost<R>(P, q, K, yawp, q64p);
+        else c = assisted_cost<R>(P, q, qd, energy, K, in.W ? in.W + step * 6 : nullptr, bd, yawp, q64p, energy64);
         const double sc = (in.discount_table ? in.discount_table[step] : discount_pow(in.discount, step)) * (double)c;
         // A NaN stage cost ends the reference's rollout with a NaN total (mppi.cpp:331-334). NaN is absorbing in the sum,
         // so the total is the same without leaving the loop — and without a data-dependent branch at the head of every
         // step, behind which the scheduler cannot move the (independent) dynamics of the same step.
         total += sc;
         if (step + 1 == in.T) break;  // the state after the last step is never costed (mppi.cpp:316-341)
+        if (in.lockstep > 1) lockstep_barrier();
         // PinocchioDynamics::step, pinocchio_dynamics.cpp:226-260
         R tau[NJ], qdd[NJ], nle[NJ];
 #pragma unroll
@@ -349,23 +442,71 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
             // (carrying the end effector point inside the INERTIA loop was tried: +4 registers, spills, 4 % slower)
             // (LEAN: the end effector point rides the solver's forward loop as a second, independent dependency chain)
             if constexpr (!LEAN) robot_calculate<R, false, POWER, KF, false, true>(M, q, qd, tau, qdd, nle, K, cs, sn);   // the joint sines / cosines are shared
+            if (in.lockstep > 2) lockstep_barrier();
             // the objectives with kinematics (assisted manipulation, full reach-to-pose) always run the unrolled solver: with
             // the placements' structural zeros it executes 940 instructions per step fewer than the loop body (FP32 assisted
             // manipulation 5646 -> 4705, static model 6773 -> 5476 cycles), keeps its per-joint results in registers instead of
             // local memory, and adds 7 % to a step loop that is far beyond the instruction cache either way
+            if constexpr (MIXED_SOLVER) {
+                double tau64[NJ], qdd64[NJ];
+#pragma unroll
+                for (int i = 0; i < NJ; i++) tau64[i] = (i >= 3 && i < 10) ? u64[i] : 0.0;
+                aba_fused_fast<double, MPPI_MIXED_SOLVER_UNROLL, false>(*F64, q64, cs64, sn64, tau64, qdd64);
+                // base velocities from the control (pinocchio_dynamics.cpp:234-235), then semi-implicit Euler, all FP64
+                qd64[0] = cs64[2] * u64[0] - sn64[2] * u64[1];
+                qd64[1] = sn64[2] * u64[0] + cs64[2] * u64[1];
+                qd64[2] = u64[2];
+#pragma unroll
+                for (int i = 0; i < NJ; i++) qd64[i] += qdd64[i] * in.dt64;
+#pragma unroll
+                for (int i = 0; i < NJ; i++) q64[i] += qd64[i] * in.dt64;
+#pragma unroll
+                for (int i = 0; i < NJ; i++) { q[i] = (R)q64[i]; qd[i] = (R)qd64[i]; }
+            } else
             aba_fused_fast<R, (BIG || !LEAN) ? 7 : kArmUnroll, LEAN>(F, q, cs, sn, tau, qdd, &K.ee_pos);
         }
+        if constexpr (MIXED_SOLVER) {
+            if (POWER) {
+                double p = 0.0;
 #pragma unroll
-        for (int i = 0; i < NJ; i++) qd[i] += qdd[i] * in.dt;
+                for (int i = 0; i < NJ; i++) p += (double)(tau[i] + nle[i]) * qd64[i];
+                energy64 = std_max(0.0, energy64 + p * in.dt64);  // energy.hpp:19-22
+                energy = (R)energy64;
+            }
+        } else if constexpr (MIXED) {
+            // the base velocities were overwritten by the control (pinocchio_dynamics.cpp:234-235)
 #pragma unroll
-        for (int i = 0; i < NJ; i++) q[i] += qd[i] * in.dt;
-        if (POWER) {
-            R p = R(0);
+            for (int i = 0; i < 3; i++) qd64[i] = (double)qd[i];
 #pragma unroll
-            for (int i = 0; i < NJ; i++) p += (tau[i] + nle[i]) * qd[i];
-            energy = std_max(R(0), energy + p * in.dt);  // energy.hpp:19-22
+            for (int i = 0; i < NJ; i++) qd64[i] += (double)qdd[i] * in.dt64;
+#pragma unroll
+            for (int i = 0; i < NJ; i++) q64[i] += qd64[i] * in.dt64;
+#pragma unroll
+            for (int i = 0; i < NJ; i++) { q[i] = (R)q64[i]; qd[i] = (R)qd64[i]; }
+            if (POWER) {
+                double p = 0.0;
+#pragma unroll
+                for (int i = 0; i < NJ; i++) p += (double)(tau[i] + nle[i]) * qd64[i];
+                energy64 = std_max(0.0, energy64 + p * in.dt64);  // energy.hpp:19-22
+                energy = (R)energy64;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NJ; i++) qd[i] += qdd[i] * in.dt;
+#pragma unroll
+            for (int i = 0; i < NJ; i++) q[i] += qd[i] * in.dt;
+            if (POWER) {
+                R p = R(0);
+#pragma unroll
+                for (int i = 0; i < NJ; i++) p += (tau[i] + nle[i]) * qd[i];
+                energy = std_max(R(0), energy + p * in.dt);  // energy.hpp:19-22
+            }
         }
-        if constexpr (!FAITHFUL && (!LEAN || BIG)) joint_sincos<R>(F, q, cs, sn);
+        if constexpr (MIXED_SOLVER) {
+            joint_sincos<double>(*F64, q64, cs64, sn64);
+#pragma unroll
+            for (int i = 2; i < 10; i++) { cs[i] = (R)cs64[i]; sn[i] = (R)sn64[i]; }
+        } else if constexpr (!FAITHFUL && (!LEAN || BIG)) joint_sincos<R>(F, q, cs, sn);
     }
     return total;
 }

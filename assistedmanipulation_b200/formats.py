@@ -80,7 +80,7 @@ def read_csv(path):
 
 class MPPILog:
     """logger::MPPI (logging/mppi.cpp). `source` is anything with the engine's call shapes
-    (tests/engine_lib.Engine, oracle_lib.Oracle): read(what, count), query(what)."""
+    (engine.Engine, oracle_lib.Oracle): read(what, count), query(what)."""
 
     FILES = ("costs", "weights", "gradient", "optimal_rollout", "optimal_cost", "update")
 

@@ -221,7 +221,13 @@ int mppi_b200_comm_init(mppi_b200_engine *engine, const void *id128);
 int mppi_b200_p2p_handle(mppi_b200_engine *engine, void *handle64);
 int mppi_b200_p2p_init(mppi_b200_engine *engine, const void *handles /* world_size x 64 bytes, rank order */);
 
-/* mppi::Trajectory::get, mppi.cpp:481-512 (host side, linear interpolation / default control). */
+/* mppi::Trajectory::get, mppi.cpp:481-512 (host side, linear interpolation / default control).
+ * Thread safety: the one call that may run on ANOTHER thread while mppi_b200_update / _update_launch / _update_wait /
+ * _update_finish run on the engine's owner thread (the reference's control loop reads while the controller updates,
+ * mppi.cpp:179,492). It sees either the previously published sequence or the new one, never a mixture: the engine
+ * serialises it against the publication step only (the copy of the sequence and of its time stamp), not against the
+ * update. A time before the last published update returns MPPI_B200_ERR_INVALID (the reference asserts) without touching
+ * the engine's error message. Every other entry point is single-threaded per engine; distinct engines are independent. */
 int mppi_b200_get(mppi_b200_engine *engine, double *control, double time);
 
 /* read-back of the getters logger::MPPI and BaseTest use (logging/mppi.cpp:84-136) */

@@ -195,6 +195,9 @@ public:
     const std::vector<double> &weights() const { return m_weights; }
     const std::vector<double> &gradient() const { return m_gradient; }
     const std::vector<double> &optimal() const { return m_optimal_control; }
+    // TEST HOOK (no reference counterpart): start the next update from a given published sequence, so that a
+    // single-precision engine and this FP64 restatement can be compared update by update from IDENTICAL inputs
+    void set_optimal(const double *U) { std::copy(U, U + m_optimal_control.size(), m_optimal_control.begin()); m_optimal_control_shifted = m_optimal_control; }
     double optimal_total_cost() const { return m_optimal_cost; }
     double update_duration() const { return m_update_duration; }
     std::int64_t shift_by() const { return m_shift_by; }

@@ -93,6 +93,7 @@ int oracle_update(void *p, const double *state, double time, const double *wrenc
     return 0;
 }
 
+void oracle_set_optimal(void *p, const double *U) { static_cast<Handle *>(p)->traj->set_optimal(U); }
 int oracle_get(void *p, double *control, double time) { static_cast<Handle *>(p)->traj->get(control, time); return 0; }
 
 int oracle_read(void *p, int what, void *dst, size_t bytes) {

@@ -52,17 +52,19 @@ def config_for(case, **over):
     return abi.make_config(case["system"], case["objective"], case["K"], case["horison"], **kw)
 
 
-def fp32_flips(ce, co, cost_rtol):
-    """Single-precision costs against the FP64 oracle on identical noise. The objectives have jumps (1e10 at the inverse
-    barriers, cost.hpp:59-61,90-92; 1000 at the hard-coded joint limits, track_point.cpp:48-65): a rollout whose state
-    lands within FP32 rounding of such a bound at some step takes the jump on one side only (a "flip"; which rollouts
-    do depends on the kernel's rounding, i.e. on every change of its operation order). Away from flips the costs must
-    agree to `cost_rtol`, flips must be rare, and the typical rollout must be far inside the tolerance. Returns True
-    when this update has flips — the two controllers then continue from different control sequences, so a caller
-    comparing several updates stops there."""
+def fp32_costs(ce, co, cost_rtol, max_flips):
+    """Single-precision costs against the FP64 oracle on identical inputs. The objectives have steps (1e10 at the inverse
+    barriers, cost.hpp:59-61,90-92; 1000 at the hard-coded joint limits, track_point.cpp:48-65): a rollout whose barrier
+    argument lands within the fast mode's rounding of a bound at some step takes the step on one side only (a "flip").
+    The assisted-manipulation kernels run the whole state path in FP64 (rollout_core.cuh MIXED_SOLVER), so only the
+    single-precision kinematics behind the collision-sphere and workspace distances can still flip a rollout: measured
+    ~1 in 10^4 rollouts, each worth ~2e-5 of the published control sequence — the caller bounds the count (`max_flips`)
+    AND asserts the north-star tolerance on the sequence itself. Every other rollout agrees to `cost_rtol`.
+    Returns the number of flipped rollouts."""
     ok = ~np.isnan(co)
+    assert np.array_equal(np.isnan(ce), np.isnan(co))
     rel = np.abs(ce[ok] - co[ok]) / np.abs(co[ok])
     flipped = rel > cost_rtol
-    assert flipped.mean() <= 5e-3, (int(flipped.sum()), rel.max())
+    assert int(flipped.sum()) <= max_flips, (int(flipped.sum()), max_flips, rel.max())
     assert np.median(rel) <= cost_rtol / 20, np.median(rel)
-    return bool(flipped.any())
+    return int(flipped.sum())

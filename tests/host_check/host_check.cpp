@@ -117,15 +117,17 @@ template <class R, int VAR, bool FAITHFUL, class CP, bool BIG = false>
 static void run_rollouts(const CP &cp, const double *x0, const double *U, const double *W, const double *eps, int K, int T, double dt, double discount, double *costs, double *bd) {
     static const RobotModel<R> M = make_robot_model<R>();
     static const FastModel<R> F = make_fast_model<R>();
+    static const FastModel<double> F64 = make_fast_model<double>();
     auto P = convert<R>(cp);
     std::vector<R> x(31), u((size_t)12 * T), w, e((size_t)12 * T);
     for (int i = 0; i < 31; i++) x[i] = (R)x0[i];
     for (size_t i = 0; i < u.size(); i++) u[i] = (R)U[i];
     if (W) { w.resize((size_t)6 * T); for (size_t i = 0; i < w.size(); i++) w[i] = (R)W[i]; }
-    RolloutInputs<R> in{x.data(), u.data(), W ? w.data() : nullptr, T, (R)dt, discount};
+    RolloutInputs<R> in;
+    in.x0 = x.data(); in.x0_64 = x0; in.U = u.data(); in.U64 = U; in.W = W ? w.data() : nullptr; in.T = T; in.dt = (R)dt; in.dt64 = dt; in.discount = discount;
     for (int k = 0; k < K; k++) {
         for (size_t i = 0; i < e.size(); i++) e[i] = (R)eps[(size_t)k * 12 * T + i];
-        costs[k] = rollout_franka<R, VAR, FAITHFUL, decltype(P), BIG>(M, F, P, in, e.data(), bd);
+        costs[k] = rollout_franka<R, VAR, FAITHFUL, decltype(P), BIG>(M, F, P, in, e.data(), bd, &F64);
     }
 }
 

@@ -28,6 +28,7 @@ def load():
     lib.oracle_update.argtypes = [C.c_void_p, _dp, C.c_double, _dp, _dp]
     lib.oracle_update.restype = C.c_int
     lib.oracle_get.argtypes = [C.c_void_p, _dp, C.c_double]
+    lib.oracle_set_optimal.argtypes = [C.c_void_p, _dp]
     lib.oracle_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     lib.oracle_read.restype = C.c_int
     lib.oracle_query.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
@@ -89,6 +90,11 @@ class Oracle:
         rc = self.lib.oracle_read(self.h, what, out.ctypes.data_as(C.c_void_p), out.nbytes)
         assert rc == 0, rc
         return out
+
+    def set_optimal(self, U):
+        """test hook: continue from this published control sequence (see mppi_oracle.hpp set_optimal)"""
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        self.lib.oracle_set_optimal(self.h, ptr(U))
 
     def get(self, time):
         nu = self.query(abi.QUERY_CONTROL_DOF)

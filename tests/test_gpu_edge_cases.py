@@ -113,3 +113,62 @@ def test_full_covariance_oracle_transform_matches(oracle):
     assert np.abs(e.read(abi.READ_OPTIMAL, 2 * T) - Uo).max() <= 1e-9 * np.abs(Uo).max()
     o.close()
     e.close()
+
+
+def test_get_from_another_thread_during_updates():
+    """mppi.cpp:178-182,492: the control loop reads the published sequence while the controller updates. A reader thread
+    hammers mppi_b200_get during 40 updates: every answer is the interpolation of ONE published sequence (the one before
+    or the one after the concurrent update, never a mixture), and the reader never waits for a whole update."""
+    import threading
+    import time as clock
+    import engine_lib as el
+    K, T, nu = 16384, 64, 12
+    e = el.Engine(abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_TRACK_POINT, K, 0.64, dynamics_mode=abi.DYNAMICS_FUSED), abi.default_track_point())
+    x0 = abi.huddled_state()
+    assert e.update(x0, 0.0, seed=1) == 0
+    published = {0.0: e.read(abi.READ_OPTIMAL, nu * T).reshape(T, nu)}
+    samples, stop, query_time = [], [False], [0.013]
+
+    def reader():
+        out = np.zeros(nu)
+        while not stop[0]:
+            tq = query_time[0]
+            t0 = clock.perf_counter()
+            rc = e.lib.mppi_b200_get(e.h, el.ptr(out), tq)
+            samples.append((tq, rc, out.copy(), clock.perf_counter() - t0))
+
+    th = threading.Thread(target=reader)
+    th.start()
+    update_s = []
+    for u in range(1, 41):
+        t = 0.05 * u
+        t0 = clock.perf_counter()
+        assert e.update(x0, t, seed=1) == 0, e.error()
+        update_s.append(clock.perf_counter() - t0)
+        published[t] = np.frombuffer(bytes(e.read(abi.READ_OPTIMAL, nu * T)), dtype=np.float64).reshape(T, nu).copy()
+        query_time[0] = t + 0.013
+    stop[0] = True
+    th.join()
+    e.close()
+    assert len(samples) > 100
+    times = sorted(published)
+    checked = 0
+    for tq, rc, got, _ in samples:
+        if rc != 0:
+            continue   # asked for a time before the sequence published meanwhile: refused like the reference's assert
+        ok = False
+        for tn in times:
+            if tn > tq:
+                break
+            s = (tq - tn) / 0.01
+            lo = int(s)
+            if lo + 1 >= T:
+                continue
+            w = s - lo
+            ok = ok or np.array_equal(got, (1.0 - w) * published[tn][lo] + w * published[tn][lo + 1])
+        assert ok, tq
+        checked += 1
+    assert checked > 50
+    # the reader is held up by the publication copy only, not by an update (the median update here takes ~0.5 ms)
+    waits = np.array([s[3] for s in samples])
+    assert np.median(waits) < 0.2 * np.median(update_s)

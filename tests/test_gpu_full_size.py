@@ -12,37 +12,31 @@ from assistedmanipulation_b200 import abi
 pytestmark = pytest.mark.gpu
 
 
-def test_config3_full_size_fp32_fast_mode(oracle):
-    # K = 16384 x T = 128, AssistedManipulation + energy tank + body-COM links + forecast table, FP32 fast mode against
-    # the FP64 oracle. The objective has 1e10 jumps (cost.hpp:59-61,90-92): a rollout whose state sits within FP32
-    # rounding of a barrier at some step lands on the other side of the jump ("flip"). Away from flips FP32 is far
-    # inside the 1e-4 tolerance of BASELINE.json; flips are counted and bounded, and their effect on U is bounded.
+@pytest.mark.parametrize("seed", [3, 4, 5])
+def test_config3_full_size_fp32_fast_mode(oracle, seed):
+    """BASELINE.json config 3 at full size — K = 16384 x T = 128, AssistedManipulation + energy tank + body-COM links +
+    forecast table — FP32 fast mode against the FP64 oracle on the noise the kernel consumed. The north-star gate: the
+    updated control sequence within 1e-4 relative. The objective has 1e10 steps (cost.hpp:59-61,90-92); the fast mode
+    carries the whole state path in FP64 (rollout_core.cuh MIXED_SOLVER) so that a rollout takes them where its FP64 twin
+    does: measured 0 / 1 / 3 rollouts of 16386 on the other side for these seeds (single-precision link distances),
+    control sequence 5e-6 / 2e-5 / 5e-5 (round 1, all single precision: 9..15 rollouts, 1e-4..2e-4)."""
     import engine_lib as el
     K, T, nu = 16384, 128, 12
     params, W, x0 = cases.assisted_params(True, abi.LINKS_BODY_COM), cases.constant_wrench(T), abi.huddled_state(10.0)
     e = el.Engine(abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_ASSISTED_MANIPULATION, K, 1.28, precision=abi.FP32, dynamics_mode=abi.DYNAMICS_FUSED,
                                   smoothing=None, control_bound=False), params)
     o = ol.Oracle(oracle, abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_ASSISTED_MANIPULATION, K, 1.28, threads=16, smoothing=None, control_bound=False), params)
-    assert e.update(x0, 0.0, W, seed=3) == 0, e.error()
+    assert e.update(x0, 0.0, W, seed=seed) == 0, e.error()
     noise = e.read(abi.READ_NOISE, (K + 2) * T * nu)          # FP32 values widened: exactly what the kernel consumed
     assert o.update(x0, 0.0, W, noise) == 0
     Uo, Ue = o.read(abi.READ_OPTIMAL, nu * T), e.read(abi.READ_OPTIMAL, nu * T)
     co, ce = o.read(abi.READ_COSTS, K + 2), e.read(abi.READ_COSTS, K + 2)
     flipped = np.abs(ce - co) > 5e9
-    assert flipped.mean() < 3e-3, flipped.sum()
+    assert flipped.sum() <= 6, flipped.sum()
     assert np.median(np.abs(ce - co) / np.abs(co)) < 1e-6
     assert (np.abs(ce - co) / np.abs(co))[~flipped].max() < 1e-3
-    # the published control sequence, flips included (measured 2e-4 with the ~16 flips of one kernel build; which rollouts
-    # flip changes with the kernel's rounding, so the bound leaves room for a few standard deviations of that count)
-    assert np.abs(Ue - Uo).max() <= 1e-3 * np.abs(Uo).max(), np.abs(Ue - Uo).max() / np.abs(Uo).max()
-    # without the flipped rollouts the FP32 costs reproduce the FP64 update to the stated 1e-4 (first update: U_shift = 0)
-
-    def update_from(c):
-        w = np.exp(-10.0 * (c - c.min()) / (c.max() - c.min()))
-        return 2.0 * (w / w.sum()) @ noise.reshape(K + 2, -1)
-    mixed = np.where(flipped, co, ce)
-    assert np.abs(update_from(co) - Uo).max() <= 1e-12 * np.abs(Uo).max()
-    assert np.abs(update_from(mixed) - Uo).max() <= 1e-4 * np.abs(Uo).max()
+    # THE GATE (BASELINE.json north_star): updated control sequence within 1e-4 relative in the FP32 fast mode
+    assert np.abs(Ue - Uo).max() <= 1e-4 * np.abs(Uo).max(), np.abs(Ue - Uo).max() / np.abs(Uo).max()
     e.close()
     o.close()
 

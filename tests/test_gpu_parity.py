@@ -44,9 +44,9 @@ def run_pair(oracle, system, objective, params, K, horison, x0, updates, cadence
             assert np.array_equal(np.isnan(co), np.isnan(ce))
             ok = ~np.isnan(co)
             if precision == abi.FP32:
-                if cases.fp32_flips(ce, co, cost_rtol):
-                    assert np.isfinite(e.read(abi.READ_OPTIMAL, nu * T)).all()
-                    break
+                # at most one rollout on the other side of a barrier step (see cases.fp32_costs); the control sequence
+                # below must meet the tolerance regardless
+                cases.fp32_costs(ce, co, cost_rtol, max_flips=1)
             else:
                 assert (np.abs(ce[ok] - co[ok]) / np.abs(co[ok])).max() <= cost_rtol, (u, (np.abs(ce[ok] - co[ok]) / np.abs(co[ok])).max())
             if precision == abi.FP64:
@@ -65,6 +65,11 @@ def run_pair(oracle, system, objective, params, K, horison, x0, updates, cadence
             oc_o, oc_e = o.read(abi.READ_OPTIMAL_COST, 1)[0], e.read(abi.READ_OPTIMAL_COST, 1)[0]
             assert abs(oc_e - oc_o) <= max(cost_rtol, u_rtol * 10) * abs(oc_o), (oc_e, oc_o)
             assert np.allclose(e.get(t + 0.013), o.get(t + 0.013), rtol=u_rtol, atol=u_rtol * np.abs(Uo).max())
+            if precision == abi.FP32:
+                # every update of the fast mode is compared FROM IDENTICAL INPUTS: the oracle continues from the sequence the
+                # engine published (1e-5 apart after one update, which would otherwise move rollouts across barrier steps
+                # through the inputs rather than through the arithmetic under test)
+                o.set_optimal(Ue)
     finally:
         o.close()
         e.close()

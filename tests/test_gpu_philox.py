@@ -61,11 +61,14 @@ def test_philox_update_matches_oracle_on_read_back_noise(oracle, precision, u_to
             assert e.query(abi.QUERY_ARGMIN) == o.query(abi.QUERY_ARGMIN)
         co, ce = o.read(abi.READ_COSTS, K + 2), e.read(abi.READ_COSTS, K + 2)
         if precision == abi.FP32:
-            if cases.fp32_flips(ce, co, c_tol):
-                break
+            # lean reach-to-pose kernel, all single precision: its steps are the 1000-unit joint-limit penalties, worth ~1e-6
+            # of the control sequence each — a handful of rollouts may take one on the other side
+            cases.fp32_costs(ce, co, c_tol, max_flips=(K + 2) // 100)
         else:
             assert (np.abs(ce - co) / np.abs(co)).max() <= c_tol
         Uo, Ue = o.read(abi.READ_OPTIMAL, 12 * T), e.read(abi.READ_OPTIMAL, 12 * T)
         assert np.abs(Ue - Uo).max() <= u_tol * np.abs(Uo).max()
+        if precision == abi.FP32:
+            o.set_optimal(Ue)   # next update from identical inputs (see test_gpu_parity.run_pair)
     o.close()
     e.close()

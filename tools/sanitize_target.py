@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
-import engine_lib as el  # noqa: E402
+from assistedmanipulation_b200 import engine as el  # noqa: E402
 import cases  # noqa: E402
 from assistedmanipulation_b200 import abi  # noqa: E402
 
