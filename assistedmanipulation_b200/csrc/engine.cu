@@ -4,7 +4,6 @@
 // only evaluates the scalar bookkeeping the reference evaluates in double on its caller thread
 // (shift_by, mppi.cpp:194; the lerp readout, mppi.cpp:481-512).
 #include <dlfcn.h>
-#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -29,7 +28,17 @@ namespace {
 
 thread_local std::string g_create_error;
 
-// ---- NCCL, resolved at run time so the library loads on machines without it ---------------------
+// ---- NCCL, resolved at run time so the library loads — and builds — on machines without it: the handful of types and
+// enumerators of nccl.h this file uses are declared here (values as in nccl.h 2.x; checked against the loaded library's
+// behaviour by the 2-GPU tests) ---------------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+typedef int ncclDataType_t;
+typedef int ncclRedOp_t;
+constexpr ncclResult_t ncclSuccess = 0;
+constexpr ncclDataType_t ncclDouble = 8;          // ncclFloat64
+constexpr ncclRedOp_t ncclSum = 0, ncclMax = 2;
 struct Nccl {
     void *handle = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
@@ -193,6 +202,9 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     if (c->batch < 0) return fail_create(MPPI_B200_ERR_INVALID, "batch");
     if (c->batch > 1 && c->world_size > 1) return fail_create(MPPI_B200_ERR_UNSUPPORTED, "a batched engine cannot also be sharded: give each GPU its own batch");
     if (c->batch > 65535) return fail_create(MPPI_B200_ERR_UNSUPPORTED, "batch exceeds the grid's y extent");
+    if (c->world_size > MPPI_MAX_WORLD) return fail_create(MPPI_B200_ERR_UNSUPPORTED, "world_size exceeds " + std::to_string(MPPI_MAX_WORLD));
+    // every rank must own at least one rollout: an empty shard would launch empty grids and leave its peers waiting
+    if (c->world_size > 1 && c->rollouts + 2 < c->world_size) return fail_create(MPPI_B200_ERR_INVALID, "world_size exceeds the rollout count (rollouts + 2): a rank would own no rollout");
     if (!(c->time_step > 0) || !(c->horison > 0)) return fail_create(MPPI_B200_ERR_INVALID, "time_step and horison must be positive");
     if (c->smoothing && c->smoothing_window > (unsigned)MAX_WINDOW) return fail_create(MPPI_B200_ERR_UNSUPPORTED, "smoothing window too large");
     const int T = (int)std::ceil(c->horison / c->time_step);  // mppi.cpp:85
@@ -287,6 +299,8 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     d.world = c->world_size; d.rank = c->rank;
     A(d.cand, (size_t)2 * std::max<long long>(d.keep_best, 1)); A(d.cand_all, (size_t)2 * std::max<long long>(d.keep_best, 1) * c->world_size);
     A(d.minmax_enc, 2); A(d.valid_count, 1); A(d.argmin, 1); A(d.finish_count, 1); A(d.minmax, 4); A(d.sums, 1 + n + (size_t)c->world_size);
+    A(d.minmax_local, 3 + MPPI_MAX_WORLD); A(d.rollout_done, 1); A(d.reduce_done, 1);
+    d.px = nullptr;
     d.weight_blocks = (int)((d.k_count + 255) / 256);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -387,8 +401,7 @@ int enqueue_begin(mppi_b200_engine *e, const void *noise, int32_t noise_source) 
     STAGE(e, 3);
     CUDA_TRY(e, launch_rollout(d, prec, e->variant, e->faithful, e->params.data(), false, e->stream)); launches++;
     STAGE(e, 4);
-    if (d.world > 1) { CUDA_TRY(e, launch_minmax_publish(d, e->stream)); launches++; }  // exchange buffer for the MAX all-reduce
-    e->launches += launches;
+    e->launches += launches;   // (sharded: the rollout grid's last block has published — and with the peer exchange pushed — the min / max payload)
     return MPPI_B200_OK;
 }
 
@@ -533,10 +546,8 @@ int mppi_b200_update_launch(mppi_b200_engine *e, const double *state, double tim
         cudaGraph_t g = nullptr;
         const long long before = e->launches;
         CUDA_TRY(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-        rc = enqueue_begin(e, nullptr, MPPI_B200_NOISE_PHILOX);
-        if (!rc && e->p2p) rc = enqueue_exchange(e, EX_MINMAX);
+        rc = enqueue_begin(e, nullptr, MPPI_B200_NOISE_PHILOX);   // (peer exchange: inside the kernels, no launch of its own)
         if (!rc) rc = enqueue_weights(e);
-        if (!rc && e->p2p) rc = enqueue_exchange(e, EX_SUMS);
         if (!rc) rc = enqueue_finish(e);
         cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
         e->graph_launches = (int)(e->launches - before);
@@ -553,14 +564,12 @@ int mppi_b200_update_launch(mppi_b200_engine *e, const double *state, double tim
         e->launches += e->graph_launches;
     } else {
         if ((rc = enqueue_begin(e, noise, noise_source))) return rc;
-        if (e->p2p) { if ((rc = enqueue_exchange(e, EX_MINMAX))) return rc; }
-        else if (e->comm) {
-            ncclResult_t r = g_nccl.AllReduce(e->d.minmax, e->d.minmax, 3, ncclDouble, ncclMax, e->comm, e->stream);
+        if (e->comm && !e->p2p) {
+            ncclResult_t r = g_nccl.AllReduce(e->d.minmax_local, e->d.minmax_local, 3 + (size_t)e->d.world, ncclDouble, ncclMax, e->comm, e->stream);
             if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-reduce failed");
         }
         if ((rc = enqueue_weights(e))) return rc;
-        if (e->p2p) { if ((rc = enqueue_exchange(e, EX_SUMS))) return rc; }
-        else if (e->comm) {
+        if (e->comm && !e->p2p) {
             ncclResult_t r = g_nccl.AllReduce(e->d.sums, e->d.sums, 1 + (size_t)e->d.nu * e->d.T + (size_t)e->d.world, ncclDouble, ncclSum, e->comm, e->stream);
             if (r != ncclSuccess) return fail(e, MPPI_B200_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl all-reduce failed");
         }
@@ -585,8 +594,8 @@ int mppi_b200_update(mppi_b200_engine *e, const double *state, double time, cons
 
 int mppi_b200_reduce_buffers(mppi_b200_engine *e, void **minmax, size_t *minmax_count, void **sums, size_t *sums_count) {
     if (!e) return MPPI_B200_ERR_INVALID;
-    if (minmax) *minmax = e->d.minmax;
-    if (minmax_count) *minmax_count = 3;
+    if (minmax) *minmax = e->d.minmax_local;
+    if (minmax_count) *minmax_count = e->d.world > 1 ? 3 + (size_t)e->d.world : 3;
     if (sums) *sums = e->d.sums;
     if (sums_count) *sums_count = 1 + (size_t)e->d.nu * e->d.T + (e->d.world > 1 ? (size_t)e->d.world : 0);
     return MPPI_B200_OK;
@@ -636,7 +645,7 @@ static int p2p_allocate(mppi_b200_engine *e) {
     PeerExchange &px = e->px;
     px.world = d.world; px.rank = d.rank;
     const long long keep = std::max<long long>(1, std::min<long long>(d.keep_best, d.K_total - 2));
-    px.count[EX_MINMAX] = 3; px.count[EX_SUMS] = 1 + d.nu * d.T + d.world; px.count[EX_CAND] = (int)(2 * keep);
+    px.count[EX_MINMAX] = 3 + d.world; px.count[EX_SUMS] = 1 + d.nu * d.T + d.world; px.count[EX_CAND] = (int)(2 * keep);
     long long at = 0;
     for (int parity = 0; parity < 2; parity++)
         for (int k = 0; k < EX_KINDS; k++) { px.offset[parity][k] = at; at += (long long)d.world * ((px.count[k] + 1) & ~1); }
@@ -684,6 +693,11 @@ int mppi_b200_p2p_init(mppi_b200_engine *e, const void *handles) {
     }
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     for (cudaGraphExec_t &g : e->graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    // the kernels read the exchange description through a device copy (keeps their parameter blocks small)
+    PeerExchange *d_px = dev_alloc<PeerExchange>(e, 1, false);
+    if (!d_px) return fail(e, MPPI_B200_ERR_CUDA, "device allocation failed");
+    CUDA_TRY(e, cudaMemcpy(d_px, &e->px, sizeof(PeerExchange), cudaMemcpyHostToDevice));
+    e->d.px = d_px;
     e->p2p = true;
     return MPPI_B200_OK;
 }

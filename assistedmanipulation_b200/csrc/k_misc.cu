@@ -163,7 +163,7 @@ template <class R, class RI, int NU> __device__ __forceinline__ void fresh_colum
     }
     if (d.L_is_diagonal) {
 #pragma unroll
-        for (int i = 0; i < nu; i++) dst[i] = (R)(d.Ldiag[i] * (double)z[i]);   // constant indices: Ldiag stays in the parameter bank
+        for (int i = 0; i < nu; i++) dst[i] = scale_noise(d.Ldiag[i], z[i], (R *)nullptr);   // constant indices: Ldiag stays in the parameter bank
         return;
     }
 #pragma unroll
@@ -247,6 +247,49 @@ template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sa
     }
 }
 
+// K1, one thread per COLUMN (NU values = NU/4 Philox blocks). The quad kernel above executed 246 instructions per thread
+// for four values and was bound by exactly that (ncu, K = 131 072: 78 % issue active, 3.3 TB/s of writes in FP64 and
+// the same 226 us for half the bytes in FP32); here the index arithmetic, the case analysis and the frame / kept reads
+// are shared by the column's three blocks, the Philox products are 32 x 32 -> 64 multiplies, the square root is one
+// MUFU and FP32 buffers are scaled in FP32. A thread stores its NU values as consecutive 16-byte vectors; a warp covers
+// 32 consecutive columns = one contiguous span. Same counters as every other sampling path: bit-identical noise.
+template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sample_columns(const __grid_constant__ DeviceState dg) {
+    const DeviceState d = controller_view(dg, blockIdx.y);
+    if (blockIdx.x == gridDim.x - 1) { prepare_block(d); return; }
+    const long long cols = d.k_count * d.T;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= cols) return;
+    long long kl; int t;
+    column_coordinates(g, cols, d.T, &kl, &t);
+    R v[NU];
+    if (!sample_column<R, RI, NU>(d, dg.Ldiag, kl, t, v)) return;
+    R *dst = static_cast<R *>(d.noise) + (size_t)g * NU;   // 16-byte aligned: the buffer is, and NU % 4 == 0
+    // 32-byte stores (sm_100: STG.256) wherever the address allows: every store then fills whole 32-byte sectors. With
+    // 16-byte stores the column's sectors arrived in halves from different instructions and the write stream stalled
+    // at 3.5 TB/s whatever the instruction count.
+    if constexpr (sizeof(R) == 8 && NU % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < NU / 4; i++)   // NU * 8 bytes per column: a multiple of 32, so every column starts on a sector
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i), "d"((double)v[4 * i]), "d"((double)v[4 * i + 1]), "d"((double)v[4 * i + 2]), "d"((double)v[4 * i + 3]) : "memory");
+    } else if constexpr (sizeof(R) == 4 && NU == 12) {
+        // 48 bytes per column: even columns start on a sector (32 + 16), odd ones 16 bytes into one (16 + 32)
+        const float *f = reinterpret_cast<const float *>(v);
+        if ((g & 1) == 0) {
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]) : "memory");
+            *reinterpret_cast<float4 *>(dst + 8) = make_float4(f[8], f[9], f[10], f[11]);
+        } else {
+            *reinterpret_cast<float4 *>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 4), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]), "f"(f[8]), "f"(f[9]), "f"(f[10]), "f"(f[11]) : "memory");
+        }
+    } else if constexpr (sizeof(R) == 8) {
+#pragma unroll
+        for (int i = 0; i < NU / 2; i++) reinterpret_cast<double2 *>(dst)[i] = make_double2((double)v[2 * i], (double)v[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NU / 4; i++) reinterpret_cast<float4 *>(dst)[i] = make_float4((float)v[4 * i], (float)v[4 * i + 1], (float)v[4 * i + 2], (float)v[4 * i + 3]);
+    }
+}
+
 // kept rollouts: one block per kept rollout (mppi.cpp:243-252); nothing happens when shift_by <= 0
 template <class R, class RI, int NU> __global__ void k_shift_kept(const __grid_constant__ DeviceState dg) {
     const DeviceState d = controller_view(dg, blockIdx.y);
@@ -277,17 +320,6 @@ template <class R, class RI, int NU> __global__ void k_shift_kept(const __grid_c
 }
 
 // ---- K3 ---------------------------------------------------------------------------------------------
-// publish {-min, max, valid} into the exchange buffer (all-reduced with MAX when sharded)
-__global__ void k_minmax_publish(const __grid_constant__ DeviceState dg) {
-    const DeviceState d = controller_view(dg, blockIdx.y);
-    if (threadIdx.x == 0) {
-        const int n = *d.valid_count;
-        d.minmax[0] = n > 0 ? -decode_ordered(d.minmax_enc[0]) : -CUDART_INF;
-        d.minmax[1] = n > 0 ? decode_ordered(d.minmax_enc[1]) : -CUDART_INF;
-        d.minmax[2] = n >= 2 ? 2.0 : (double)n;
-    }
-}
-
 // w_k = exp(-cost_scale (c_k - min) / (max - min)), NaN -> 0 (mppi.cpp:381-397); block partial sums
 __global__ void __launch_bounds__(256) k_weights(const __grid_constant__ DeviceState dg) {
     const DeviceState d = controller_view(dg, blockIdx.y);
@@ -301,7 +333,22 @@ __global__ void __launch_bounds__(256) k_weights(const __grid_constant__ DeviceS
         mm2 = nvalid >= 2 ? 2.0 : (double)nvalid;
         if (blockIdx.x == 0 && threadIdx.x == 0) { d.minmax[0] = mm0; d.minmax[1] = mm1; d.minmax[2] = mm2; }
     } else {
-        mm0 = d.minmax[0]; mm1 = d.minmax[1]; mm2 = d.minmax[2];
+        // sharded: this rank's payload {-min, max, 0, valid slots} was published by the last block of the rollout grid.
+        // Peer-memory exchange: wait for the peers' payloads in the local mailbox and combine in rank order (MAX; the
+        // valid slots are disjoint, so MAX gathers them). NCCL / split ABI: the buffer was all-reduced (MAX) in place.
+        const unsigned long long attempt = d.frame->attempt;
+        if (d.px) exchange_wait(*d.px, EX_MINMAX, attempt);
+        mm0 = d.minmax_local[0]; mm1 = d.minmax_local[1];
+        double valid = 0.0;
+        for (int q = 0; q < d.world; q++) {
+            if (d.px && q != d.rank) {
+                mm0 = fmax(mm0, exchange_peer(*d.px, EX_MINMAX, attempt, q, 0));
+                mm1 = fmax(mm1, exchange_peer(*d.px, EX_MINMAX, attempt, q, 1));
+                valid += exchange_peer(*d.px, EX_MINMAX, attempt, q, 3 + q);
+            } else valid += d.minmax_local[3 + q];
+        }
+        mm2 = valid >= 2.0 ? 2.0 : valid;   // saturate AFTER the sum: two ranks with one valid rollout each are two valid rollouts (mppi.cpp:368-370)
+        if (blockIdx.x == 0 && threadIdx.x == 0) { d.minmax[0] = mm0; d.minmax[1] = mm1; d.minmax[2] = mm2; }
     }
     const double minimum = -mm0, maximum = mm1;
     const double difference = maximum - minimum;
@@ -342,31 +389,51 @@ __device__ __forceinline__ void fma_vec(double *acc, double w, const float4 &v) 
     acc[0] = fma(w, (double)v.x, acc[0]); acc[1] = fma(w, (double)v.y, acc[1]); acc[2] = fma(w, (double)v.z, acc[2]); acc[3] = fma(w, (double)v.w, acc[3]);
 }
 
-template <class R> __global__ void __launch_bounds__(512) k_gradient(const __grid_constant__ DeviceState dg) {
+// Row groups: when a row has fewer 16-byte vectors than a block has threads (FP32 rows at T = 64: 192), the block's
+// threads split into G groups that walk different rows, so every thread has loads in flight (the FP32 kernel ran 192 of
+// 256 threads and reached 2.3 TB/s where the FP64 one reaches 5.7); the groups' sums meet in shared memory in group order.
+template <class R> __global__ void __launch_bounds__(512) k_gradient(const __grid_constant__ DeviceState dg, int groups) {
     const DeviceState d = controller_view(dg, blockIdx.y);
     typedef typename Vec16<R>::type V;
     constexpr int VN = Vec16<R>::n;
+    extern __shared__ __align__(16) double s_group[];   // (groups - 1) x n partial sums
     if (*d.skip) return;
     const int n = d.nu * d.T;
     const int nvec = n / VN;  // host guarantees divisibility
     const V *noise = static_cast<const V *>(d.noise);
-    for (int e = threadIdx.x; e < nvec; e += blockDim.x) {
+    const int g = groups > 1 ? (int)threadIdx.x / nvec : 0;
+    const int lanes = groups > 1 ? nvec : (int)blockDim.x;          // threads that walk a row together
+    const long long first = (long long)blockIdx.x * groups + g, stride = (long long)gridDim.x * groups;
+    for (int e = groups > 1 ? (int)threadIdx.x - g * nvec : (int)threadIdx.x; e < nvec && g < groups; e += lanes) {
         double acc[VN];
 #pragma unroll
         for (int i = 0; i < VN; i++) acc[i] = 0.0;
-        long long k = blockIdx.x;
+        long long k = first;
         // 4 rows in flight per thread
-        for (; k + 3 * (long long)gridDim.x < d.k_count; k += 4 * (long long)gridDim.x) {
+        for (; k + 3 * stride < d.k_count; k += 4 * stride) {
             const V v0 = __ldg(noise + (size_t)k * nvec + e);
-            const V v1 = __ldg(noise + (size_t)(k + gridDim.x) * nvec + e);
-            const V v2 = __ldg(noise + (size_t)(k + 2 * (long long)gridDim.x) * nvec + e);
-            const V v3 = __ldg(noise + (size_t)(k + 3 * (long long)gridDim.x) * nvec + e);
-            const double w0 = d.weights[k], w1 = d.weights[k + gridDim.x], w2 = d.weights[k + 2 * (long long)gridDim.x], w3 = d.weights[k + 3 * (long long)gridDim.x];
+            const V v1 = __ldg(noise + (size_t)(k + stride) * nvec + e);
+            const V v2 = __ldg(noise + (size_t)(k + 2 * stride) * nvec + e);
+            const V v3 = __ldg(noise + (size_t)(k + 3 * stride) * nvec + e);
+            const double w0 = d.weights[k], w1 = d.weights[k + stride], w2 = d.weights[k + 2 * stride], w3 = d.weights[k + 3 * stride];
             fma_vec(acc, w0, v0); fma_vec(acc, w1, v1); fma_vec(acc, w2, v2); fma_vec(acc, w3, v3);
         }
-        for (; k < d.k_count; k += gridDim.x) fma_vec(acc, d.weights[k], __ldg(noise + (size_t)k * nvec + e));
+        for (; k < d.k_count; k += stride) fma_vec(acc, d.weights[k], __ldg(noise + (size_t)k * nvec + e));
+        if (g == 0) {
 #pragma unroll
-        for (int i = 0; i < VN; i++) d.grad_partial[(size_t)blockIdx.x * n + e * VN + i] = acc[i];
+            for (int i = 0; i < VN; i++) d.grad_partial[(size_t)blockIdx.x * n + e * VN + i] = acc[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < VN; i++) s_group[(size_t)(g - 1) * n + e * VN + i] = acc[i];
+        }
+    }
+    if (groups > 1) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            double sum = d.grad_partial[(size_t)blockIdx.x * n + i];
+            for (int q = 1; q < groups; q++) sum += s_group[(size_t)(q - 1) * n + i];
+            d.grad_partial[(size_t)blockIdx.x * n + i] = sum;
+        }
     }
 }
 
@@ -376,13 +443,17 @@ template <class R> __global__ void __launch_bounds__(512) k_gradient(const __gri
 __global__ void __launch_bounds__(1024) k_gradient_reduce(const __grid_constant__ DeviceState dg) {
     const DeviceState d = controller_view(dg, blockIdx.y);
     __shared__ double part[32][33];
-    if (*d.skip) return;
+    // A skipped update (max - min < 1e-6 or fewer than two valid rollouts, mppi.cpp:368-375) leaves weights and gradient
+    // untouched, but a sharded set still exchanges this buffer (the argmin slots ride it, and every rank must find its
+    // peers' flags): it is rewritten on EVERY update — zeros for the sums — so nothing stale is ever combined twice.
+    const int skip = *d.skip;
+    if (skip && d.world == 1) return;
     const int n = d.nu * d.T;
     const int rows = d.grad_blocks;
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + lane;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    if (e < n) {
+    if (e < n && !skip) {
         int b = slice;
         for (; b + 96 < rows; b += 128) {
             s0 += d.grad_partial[(size_t)b * n + e];
@@ -403,7 +474,7 @@ __global__ void __launch_bounds__(1024) k_gradient_reduce(const __grid_constant_
     if (blockIdx.x == 0 && slice == 1) {
         // sum of the weights: warp-strided partial sums, then a fixed-order shuffle tree
         double s = 0.0;
-        for (int b = lane; b < d.weight_blocks; b += 32) s += d.wsum_partial[b];
+        if (!skip) for (int b = lane; b < d.weight_blocks; b += 32) s += d.wsum_partial[b];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) {
@@ -414,6 +485,20 @@ __global__ void __launch_bounds__(1024) k_gradient_reduce(const __grid_constant_
                 const long long a = *d.argmin;
                 for (int r = 0; r < d.world; r++) d.sums[1 + d.nu * d.T + r] = (r == d.rank && a != 0x7fffffffffffffffll) ? (double)(a + 1) : 0.0;
             }
+        }
+    }
+    if (d.world > 1 && d.px) {
+        // the LAST block to get here stores this rank's {sum w, sum w*eps, argmin slots} into the peers' mailboxes:
+        // the second exchange of the update rides this kernel's tail (k_finish combines the slots)
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(d.reduce_done, 1) == (int)gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (threadIdx.x == 0) *d.reduce_done = 0;
+            exchange_push(*d.px, EX_SUMS, d.frame->attempt, d.sums);
         }
     }
 }
@@ -461,15 +546,25 @@ __device__ __forceinline__ bool sg_recurrence_dispatch(int nr, const double *F, 
     }
 }
 
+// element e of the exchanged {sum w, sum w*eps, argmin slots}: combined here in rank order from the peers' slots in the
+// local mailbox (peer-memory exchange; identical bits on every rank), or already all-reduced in place (NCCL, split ABI)
+__device__ __forceinline__ double combined_sum(const DeviceState &d, int e) {
+    if (d.world == 1 || !d.px) return d.sums[e];
+    const unsigned long long attempt = d.frame->attempt;
+    double acc = 0.0;
+    for (int q = 0; q < d.world; q++) acc += (q == d.rank) ? d.sums[e] : exchange_peer(*d.px, EX_SUMS, attempt, q, e);
+    return acc;
+}
+
 __device__ __forceinline__ void finish_publish_stats(const DeviceState &d, int n) {
     d.result[n + 0] = d.minmax[0]; d.result[n + 1] = d.minmax[1]; d.result[n + 2] = d.minmax[2];
     long long best = *d.argmin;
     if (d.world > 1) {   // lowest global index among the ranks that hold the global minimum (mppi.cpp:363-366 order)
         best = 0x7fffffffffffffffll;
-        for (int r = 0; r < d.world; r++) { const double v = d.sums[1 + n + r]; if (v > 0.0 && (long long)v - 1 < best) best = (long long)v - 1; }
+        for (int r = 0; r < d.world; r++) { const double v = combined_sum(d, 1 + n + r); if (v > 0.0 && (long long)v - 1 < best) best = (long long)v - 1; }
     }
     d.result[n + 3] = __longlong_as_double(best);
-    d.result[n + 4] = d.sums[0];
+    d.result[n + 4] = combined_sum(d, 0);
 }
 
 __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DeviceState dg) {
@@ -483,17 +578,20 @@ __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DeviceSt
     double *sw = tm + d.sg_len;                            // 2w+1 taps
     const int n = d.nu * d.T, ch = blockIdx.x;
     const int skip = *d.skip;
-    const bool dead = !(d.minmax[2] >= 2.0);  // "all nan rollouts" (mppi.cpp:368-370): the reference throws before publishing
+    if (d.world > 1 && d.px) exchange_wait(*d.px, EX_SUMS, d.frame->attempt);   // the peers' {sum w, sum w*eps, argmin slots} have arrived
+    // "all nan rollouts" (mppi.cpp:368-370): the reference throws before publishing. A peer that never arrived (exchange
+    // time-out) is handled the same way: the engine keeps its last good control sequence, the host reports the error.
+    const bool dead = !(d.minmax[2] >= 2.0) || (d.px && *d.px->error);
     if (dead) {   // nothing is published but the statistics
         if (ch == 0 && threadIdx.x == 0) finish_publish_stats(d, n);
         return;
     }
-    const double total = d.sums[0];
+    const double total = combined_sum(d, 0);
     for (int t = threadIdx.x; t < d.T; t += blockDim.x) {
         const int e = t * d.nu + ch;
         double v = d.U_shift[e];
         if (!skip) {
-            const double g = d.sums[1 + e] / total;   // weights are normalised by the total (mppi.cpp:403-408)
+            const double g = combined_sum(d, 1 + e) / total;   // weights are normalised by the total (mppi.cpp:403-408)
             d.gradient[e] = g;
             v += g * d.gradient_step;
         }
@@ -686,8 +784,14 @@ template <class R, class RI, int NU> static cudaError_t sample_tt(const DeviceSt
     }
     const long long ncols = d.k_count * d.T;
     if constexpr (NU % 4 == 0) {
-        // MPPI_B200_SAMPLE_TILE=1 keeps the general kernel (A/B measurements)
-        static const bool tile_only = std::getenv("MPPI_B200_SAMPLE_TILE") && std::getenv("MPPI_B200_SAMPLE_TILE")[0] == '1';
+        // MPPI_B200_SAMPLE_TILE=1 keeps the general kernel, =2 the one-thread-per-Philox-block kernel (A/B measurements)
+        static const int sample_switch = std::getenv("MPPI_B200_SAMPLE_TILE") ? std::atoi(std::getenv("MPPI_B200_SAMPLE_TILE")) : 0;
+        const bool tile_only = sample_switch == 1;
+        if (d.L_is_diagonal && sample_switch == 0) {
+            k_sample_columns<R, RI, NU><<<dim3((unsigned)((ncols + 255) / 256) + 1, d.batch), 256, 0, s>>>(d);   // + the prepare block
+            ++*launches;
+            return cudaGetLastError();
+        }
         if (d.L_is_diagonal && !tile_only) {
             const long long quads = ncols * (NU / 4);
             k_sample_quads<R, RI, NU><<<dim3((unsigned)((quads + 255) / 256) + 1, d.batch), 256, 0, s>>>(d);   // + the prepare block
@@ -723,7 +827,7 @@ __global__ void __launch_bounds__(256) k_exchange(const __grid_constant__ Device
     const unsigned long long update = d.frame->attempt;
     const int parity = (int)(update & 1ull);
     const unsigned long long seq = update * 4ull + (unsigned long long)kind + 1ull;   // never 0, unique per (update, kind)
-    double *payload = kind == EX_MINMAX ? d.minmax : (kind == EX_SUMS ? d.sums : d.cand);
+    double *payload = kind == EX_MINMAX ? d.minmax_local : (kind == EX_SUMS ? d.sums : d.cand);
     const long long slot0 = px.offset[parity][kind];
     const long long flag0 = px.flags_offset + ((long long)parity * EX_KINDS + kind) * px.world;
     const int p = blockIdx.x;
@@ -777,11 +881,6 @@ cudaError_t launch_exchange(const DeviceState &d, const PeerExchange &px, int ki
     return cudaGetLastError();
 }
 
-cudaError_t launch_minmax_publish(const DeviceState &d, cudaStream_t s) {
-    k_minmax_publish<<<1, 32, 0, s>>>(d);
-    return cudaGetLastError();
-}
-
 cudaError_t launch_weights(const DeviceState &d, cudaStream_t s) {
     k_weights<<<dim3(d.weight_blocks, d.batch), 256, 0, s>>>(d);
     return cudaGetLastError();
@@ -790,8 +889,10 @@ cudaError_t launch_weights(const DeviceState &d, cudaStream_t s) {
 cudaError_t launch_gradient(const DeviceState &d, int precision, cudaStream_t s, int *launches) {
     const int n = d.nu * d.T;
     const int nvec = n / (precision == 0 ? 2 : 4);
-    const int threads = std::min(512, ((nvec + 127) / 128) * 128);
-    if (precision == 0) k_gradient<double><<<dim3(d.grad_blocks, d.batch), threads, 0, s>>>(d); else k_gradient<float><<<dim3(d.grad_blocks, d.batch), threads, 0, s>>>(d);
+    int threads = std::min(512, ((nvec + 127) / 128) * 128), groups = 1;
+    if (nvec <= 256 && d.k_count >= 4096) { groups = std::min(512 / nvec, 4); threads = ((groups * nvec + 31) / 32) * 32; }   // short rows: several rows per block pass
+    const size_t smem = groups > 1 ? sizeof(double) * (size_t)(groups - 1) * n : 0;
+    if (precision == 0) k_gradient<double><<<dim3(d.grad_blocks, d.batch), threads, smem, s>>>(d, groups); else k_gradient<float><<<dim3(d.grad_blocks, d.batch), threads, smem, s>>>(d, groups);
     k_gradient_reduce<<<dim3((n + 31) / 32, d.batch), 1024, 0, s>>>(d);
     *launches += 2;
     return cudaGetLastError();

@@ -8,6 +8,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdlib>
+#include <math_constants.h>
 #include "kernels.cuh"
 
 namespace mppi_b200 {
@@ -23,6 +24,31 @@ __device__ __forceinline__ unsigned long long encode_ordered(double v) {
 __device__ __forceinline__ double decode_ordered(unsigned long long e) {
     unsigned long long b = (e & 0x8000000000000000ull) ? (e & 0x7fffffffffffffffull) : ~e;
     return __longlong_as_double((long long)b);
+}
+
+// Sharded rollout set (never batched): the LAST block of the rollout grid to get here publishes this rank's
+// {-min, max, 0, valid slots} exchange payload and, with the peer-memory exchange attached, stores it into the peers'
+// mailboxes — the first exchange of the update rides the rollout grid's tail instead of two launches of its own.
+__device__ __forceinline__ void rollout_grid_epilogue(const DeviceState &d, const Frame *frame) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(d.rollout_done, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (threadIdx.x == 0) {
+            const int nvalid = atomicAdd(d.valid_count, 0);
+            d.minmax_local[0] = nvalid > 0 ? -decode_ordered(atomicMin(&d.minmax_enc[0], ~0ull)) : -CUDART_INF;
+            d.minmax_local[1] = nvalid > 0 ? decode_ordered(atomicMax(&d.minmax_enc[1], 0ull)) : -CUDART_INF;
+            d.minmax_local[2] = 0.0;
+            for (int r = 0; r < d.world; r++) d.minmax_local[3 + r] = (r == d.rank) ? (nvalid >= 2 ? 2.0 : (double)nvalid) : 0.0;
+            *d.rollout_done = 0;
+            __threadfence();
+        }
+        __syncthreads();
+        if (d.px) exchange_push(*d.px, EX_MINMAX, frame->attempt, d.minmax_local);
+    }
 }
 
 // Two builds of the lean reach-to-pose variant, chosen by the launcher (measured on B200, FP64, update time):
@@ -110,7 +136,172 @@ __global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG)
         atomicMax(&d.minmax_enc[2 * c + 1], encode_ordered(mx));
         atomicAdd(d.valid_count + c, cnt);
     }
+    if (d.world > 1) rollout_grid_epilogue(d, frame);
 }
+
+// ---- K2 for the FP32 fast mode of the objectives with kinematics (assisted manipulation, full reach-to-pose) ----------
+// TWO WARPS PER 32 ROLLOUTS. With the state path in FP64 (rollout_core.cuh MIXED_SOLVER) a step is two computations
+// that meet only in the state:
+//   state warp  control + noise -> base velocity, joint sines / cosines, qdd = M(q)^-1 tau (the unrolled FP64 solver),
+//               semi-implicit Euler                                        — needs nothing from the other warp
+//   cost warp   single-precision kinematics + RNEA of that state, tank power and energy, the objective's stage cost,
+//               the rollout's total                                         — consumes the states, one step behind
+// As one warp they ran back to back through 84 KB of straight-line code per step, bound by instruction fetch (ncu, config
+// 3: 51 % of the issue slots empty for lack of an instruction); as a producer and a consumer on two sub-partitions of
+// the SM each runs its half, in parallel. States travel through a ring of shared-memory slots (lane-contiguous), handed
+// over with named barriers (bar.arrive / bar.sync: the producer waits for the consumer only when the ring is full).
+// Same arithmetic, same order as rollout_franka's MIXED_SOLVER path: costs are bit-identical (MPPI_B200_SPLIT=0 runs that
+// path for A/B tests).
+constexpr int SPLIT_DEPTH = 4;
+struct SplitSlot {          // one step's state of 32 rollouts, lane fastest: every access is conflict-free
+    double q[NJ][32];
+    double qd[NJ][32];
+    float cs[8][32], sn[8][32];   // joints 2..9
+    float u[10][32];              // the control applied at this step (channels 10, 11 — the gripper — are ignored by the dynamics)
+};
+__device__ __forceinline__ void split_arrive(int id) { __threadfence_block(); asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void split_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+#if defined(MPPI_ROLLOUT_F32)
+template <int VAR, class ParamsT>
+__global__ void __launch_bounds__(64, 1) k_rollout_split(const __grid_constant__ DeviceState d, const __grid_constant__ ParamsT P) {
+    typedef float R;
+    constexpr int KF = VariantTraits<VAR>::kin;
+    constexpr bool POWER = VariantTraits<VAR>::power;
+    const size_t c = blockIdx.y;
+    const size_t n = (size_t)d.nu * d.T;
+    const Frame *frame = reinterpret_cast<const Frame *>(reinterpret_cast<const double *>(d.frame) + c * d.frame_doubles);
+    const double *wrench = d.wrench + c * d.frame_doubles;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SplitSlot *ring = reinterpret_cast<SplitSlot *>(smem_raw);
+    double *sU64 = reinterpret_cast<double *>(ring + SPLIT_DEPTH);   // nu*T
+    double *sDisc = sU64 + d.nu * d.T;                                // T
+    double *sx64 = sDisc + d.T;                                       // 32
+    R *sW = reinterpret_cast<R *>(sx64 + 32);                         // 6*T
+    const double *Usrc = d.U_shift + c * n;
+    for (int i = threadIdx.x; i < d.nu * d.T; i += blockDim.x) sU64[i] = Usrc[i];
+    const int has_w = frame->has_wrench;
+    for (int i = threadIdx.x; i < 6 * d.T; i += blockDim.x) sW[i] = has_w ? (R)wrench[i] : R(0);
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) sx64[i] = frame->x0[i];
+    for (int i = threadIdx.x; i < d.T; i += blockDim.x) sDisc[i] = discount_pow(d.discount, i);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    long long k = (long long)blockIdx.x * 32 + lane;
+    const bool active = k < d.k_count;
+    if (!active) k = d.k_count - 1;   // both warps of a block walk the ring together: lanes past the end repeat the last rollout and write nothing
+    const int T = d.T;
+    const double dt64 = d.dt;
+    if (role == 0) {
+        // ---- state warp -------------------------------------------------------------------------------------------------
+        const FastModel<double> &F64 = *MPPI_DEVICE_FAST_MODEL64;
+        const R *eps = static_cast<const R *>(d.noise) + (c * (size_t)d.k_count + (size_t)k) * n;
+        double q64[NJ], qd64[NJ], cs64[NJ], sn64[NJ];
+#pragma unroll
+        for (int i = 0; i < NJ; i++) { q64[i] = sx64[i]; qd64[i] = sx64[NJ + i]; }
+        joint_sincos<double>(F64, q64, cs64, sn64);
+        R e_next[NJ];
+        load_eps(eps, e_next);
+        for (int step = 0; step < T; ++step) {
+            double u64[NJ];
+#pragma unroll
+            for (int i = 0; i < NJ; i++) u64[i] = sU64[step * NJ + i] + (double)e_next[i];
+            if (step + 1 < T) load_eps(eps + (step + 1) * NJ, e_next);
+            const int s = step % SPLIT_DEPTH;
+            if (step >= SPLIT_DEPTH) split_sync(1 + SPLIT_DEPTH + s);    // the cost warp has read what this slot held
+            SplitSlot &slot = ring[s];
+#pragma unroll
+            for (int i = 0; i < NJ; i++) { slot.q[i][lane] = q64[i]; slot.qd[i][lane] = qd64[i]; }
+#pragma unroll
+            for (int i = 0; i < 8; i++) { slot.cs[i][lane] = (R)cs64[2 + i]; slot.sn[i][lane] = (R)sn64[2 + i]; }
+#pragma unroll
+            for (int i = 0; i < 10; i++) slot.u[i][lane] = (R)u64[i];
+            split_arrive(1 + s);                                          // full
+            if (step + 1 == T) break;
+            double tau64[NJ], qdd64[NJ];
+#pragma unroll
+            for (int i = 0; i < NJ; i++) tau64[i] = (i >= 3 && i < 10) ? u64[i] : 0.0;
+            aba_fused_fast<double, MPPI_MIXED_SOLVER_UNROLL, false>(F64, q64, cs64, sn64, tau64, qdd64);
+            qd64[0] = cs64[2] * u64[0] - sn64[2] * u64[1];
+            qd64[1] = sn64[2] * u64[0] + cs64[2] * u64[1];
+            qd64[2] = u64[2];
+#pragma unroll
+            for (int i = 0; i < NJ; i++) qd64[i] += qdd64[i] * dt64;
+#pragma unroll
+            for (int i = 0; i < NJ; i++) q64[i] += qd64[i] * dt64;
+            joint_sincos<double>(F64, q64, cs64, sn64);
+        }
+    } else {
+        // ---- cost warp --------------------------------------------------------------------------------------------------
+        const RobotModel<R> &M = MPPI_DEVICE_MODEL;
+        double cost = 0.0;
+        double energy64 = sx64[30];
+        R energy = (R)energy64;
+        Kinematics<R> K;
+        R taunle[NJ];
+#pragma unroll
+        for (int i = 0; i < NJ; i++) taunle[i] = R(0);
+        for (int step = 0; step < T; ++step) {
+            const int s = step % SPLIT_DEPTH;
+            split_sync(1 + s);                                            // the state warp has filled this slot
+            const SplitSlot &slot = ring[s];
+            double q64[NJ], qd64[NJ];
+            R q[NJ], qd[NJ], cs[NJ], sn[NJ], u[NJ];
+#pragma unroll
+            for (int i = 0; i < NJ; i++) { q64[i] = slot.q[i][lane]; qd64[i] = slot.qd[i][lane]; }
+#pragma unroll
+            for (int i = 0; i < 8; i++) { cs[2 + i] = slot.cs[i][lane]; sn[2 + i] = slot.sn[i][lane]; }
+#pragma unroll
+            for (int i = 0; i < 10; i++) u[i] = slot.u[i][lane];
+            u[10] = u[11] = R(0); cs[0] = cs[1] = cs[10] = cs[11] = R(1); sn[0] = sn[1] = sn[10] = sn[11] = R(0);
+            split_arrive(1 + SPLIT_DEPTH + s);                            // empty: the slot is in registers
+#pragma unroll
+            for (int i = 0; i < NJ; i++) { q[i] = (R)q64[i]; qd[i] = (R)qd64[i]; }
+            if (POWER && step > 0) {   // tank: P = tau^T v with the velocities AFTER the step that produced this state (energy.hpp:19-22)
+                double p = 0.0;
+#pragma unroll
+                for (int i = 0; i < NJ; i++) p += (double)taunle[i] * qd64[i];
+                energy64 = std_max(0.0, energy64 + p * dt64);
+                energy = (R)energy64;
+            }
+            if (step == 0) robot_kinematics<R, KF>(M, q, qd, K);          // PinocchioDynamics::set_state -> calculate()
+            const R yaw[2] = {cs[2], sn[2]};
+            R cst;
+            if constexpr (VAR == VAR_TP_FULL) cst = track_point_cost<R>(P, q, K, yaw, q64);
+            else cst = assisted_cost<R>(P, q, qd, energy, K, has_w ? sW + step * 6 : nullptr, nullptr, yaw, q64, energy64);
+            cost += sDisc[step] * (double)cst;
+            if (step + 1 == T) break;
+            R tau[NJ], qdd[NJ], nle[NJ];
+#pragma unroll
+            for (int i = 0; i < NJ; i++) { tau[i] = (i >= 3 && i < 10) ? u[i] : R(0); nle[i] = R(0); }
+            qd[0] = cs[2] * u[0] - sn[2] * u[1];
+            qd[1] = sn[2] * u[0] + cs[2] * u[1];
+            qd[2] = u[2];
+            robot_calculate<R, false, POWER, KF, false, true>(M, q, qd, tau, qdd, nle, K, cs, sn);
+#pragma unroll
+            for (int i = 0; i < NJ; i++) taunle[i] = tau[i] + nle[i];
+        }
+        if (active) d.costs[c * (size_t)d.k_count + k] = cost;
+        // block min / max over the non-NaN costs (this warp holds them)
+        const bool valid = active && !(cost != cost);
+        double mn = valid ? cost : __longlong_as_double(0x7ff0000000000000ll);
+        double mx = valid ? cost : __longlong_as_double(0xfff0000000000000ll);
+        int cnt = valid ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        if (lane == 0 && cnt > 0) {
+            atomicMin(&d.minmax_enc[2 * c], encode_ordered(mn));
+            atomicMax(&d.minmax_enc[2 * c + 1], encode_ordered(mx));
+            atomicAdd(d.valid_count + c, cnt);
+        }
+    }
+    if (d.world > 1) rollout_grid_epilogue(d, frame);
+}
+#endif
 
 template <class R, int VAR, bool FAITHFUL, class ParamsT>
 cudaError_t launch_rollout_t(const DeviceState &d, const void *params, bool optimal_only, cudaStream_t s) {
@@ -132,6 +323,21 @@ cudaError_t launch_rollout_t(const DeviceState &d, const void *params, bool opti
         if (!optimal_only && env_block > 0) { block = env_block; grid = (d.k_count + block - 1) / block; }
         lockstep = env_lockstep;
     }
+#if defined(MPPI_ROLLOUT_F32)
+    if constexpr (sizeof(R) == 4 && MPPI_MIXED_STATE >= 2 && !FAITHFUL && (VAR == VAR_TP_FULL || VAR == VAR_AM || VAR == VAR_AM_ENERGY)) {
+        static const bool split = !(std::getenv("MPPI_B200_SPLIT") && std::getenv("MPPI_B200_SPLIT")[0] == '0');
+        if (split && !optimal_only) {
+            const size_t ssmem = sizeof(SplitSlot) * SPLIT_DEPTH + sizeof(double) * ((size_t)d.nu * d.T + (size_t)d.T + 32) + sizeof(float) * 6 * (size_t)d.T;
+            auto skern = k_rollout_split<VAR, ParamsT>;
+            if (ssmem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
+                if (e != cudaSuccess) return e;
+            }
+            skern<<<dim3((unsigned)((d.k_count + 31) / 32), d.batch), 64, ssmem, s>>>(d, P);
+            return cudaGetLastError();
+        }
+    }
+#endif
     auto kern = k_rollout<R, VAR, FAITHFUL, ParamsT, false>;
     if constexpr (VAR == VAR_TP_LEAN && !FAITHFUL) {
         static const long long big_from = std::getenv("MPPI_B200_BIG_FROM") ? std::atoll(std::getenv("MPPI_B200_BIG_FROM")) : 0;   // see the note above k_rollout

@@ -9,6 +9,7 @@ __constant__ FastModel<double> c_fast_f32_state;   // the FP64 state path of the
 #define MPPI_DEVICE_MODEL c_model_f32
 #define MPPI_DEVICE_FAST_MODEL c_fast_f32
 #define MPPI_DEVICE_FAST_MODEL64 (&c_fast_f32_state)
+#define MPPI_ROLLOUT_F32 1
 #include "k_rollout.cuh"
 namespace mppi_b200 {
 cudaError_t upload_robot_model_f32() {

@@ -12,6 +12,7 @@ namespace mppi_b200 {
 
 constexpr int MAX_NU = 12;
 constexpr int MAX_WINDOW = 64;  // Savitzky–Golay half window supported by the finish kernel
+constexpr int MPPI_MAX_WORLD = 16;
 
 // Per-update inputs, written by the host into pinned memory and copied to the device in ONE
 // transfer; kernels read it from global memory so a captured CUDA graph stays valid.
@@ -58,8 +59,13 @@ struct DeviceState {
     int *valid_count;      // number of non-NaN local rollouts
     long long *argmin;     // global index of the best rollout
     int *finish_count;     // channel blocks of k_finish that are done (the last one publishes)
-    double *minmax;        // exchange buffer {-min, max, valid(<=2)}
-    double *sums;          // exchange buffer {sum w, sum w*eps [nu*T]}
+    double *minmax;        // {-min, max, valid(<=2)} of the WHOLE rollout set (written by k_weights; read by k_finish and the host)
+    double *minmax_local;  // exchange buffer of a sharded set: {-min, max, 0, valid_0 .. valid_{world-1}} with only this rank's valid slot
+                           // filled (<= 2) — combined with MAX elementwise, which gathers the slots; their sum is the valid count
+    double *sums;          // exchange buffer {sum w, sum w*eps [nu*T], argmin slot per rank}: this rank's part (p2p) / all-reduced in place (NCCL, split ABI)
+    const struct PeerExchange *px;   // device copy of the peer-memory exchange description, or nullptr
+    int *rollout_done;     // blocks of the rollout grid that are done (the last one publishes / pushes the min-max payload)
+    int *reduce_done;      // blocks of k_gradient_reduce that are done (the last one pushes the sums payload)
     double *wsum_partial;  // per block of the weights kernel
     double *grad_partial;  // [grad_blocks][nu*T]
     int grad_blocks;
@@ -104,7 +110,8 @@ __device__ __forceinline__ DeviceState controller_view(const DeviceState &g, int
     d.costs = g.costs + c * K; d.weights = g.weights + c * K; d.kept = g.kept + c * K;
     d.kept_list = g.kept_list + c * keep;
     d.minmax_enc = g.minmax_enc + 2 * c; d.valid_count = g.valid_count + c; d.argmin = g.argmin + c; d.finish_count = g.finish_count + c;
-    d.minmax = g.minmax + 4 * c; d.sums = g.sums + c * (1 + n);
+    d.minmax = g.minmax + 4 * c; d.minmax_local = g.minmax_local + (size_t)c * (3 + MPPI_MAX_WORLD); d.sums = g.sums + c * (1 + n);
+    d.rollout_done = g.rollout_done + c; d.reduce_done = g.reduce_done + c;
     d.wsum_partial = g.wsum_partial + (size_t)c * g.weight_blocks; d.grad_partial = g.grad_partial + (size_t)c * g.grad_blocks * n;
     d.skip = g.skip + c;
     d.sg_uu = g.sg_uu + (size_t)c * g.nu * g.sg_len; d.sg_tt = g.sg_tt + (size_t)c * g.nu * g.sg_len; d.sg_started = g.sg_started + c * g.nu;
@@ -117,12 +124,14 @@ __device__ __forceinline__ DeviceState controller_view(const DeviceState &g, int
 
 // ---- exchange between the ranks of a sharded rollout set over NVLink peer memory ---------------------------
 // Every rank owns a mailbox (device memory, IPC-mapped into its peers): per update parity and per kind one slot per
-// rank plus one flag per rank. A rank stores its payload into its slot of every peer's mailbox, fences, raises the
-// flag with the update's sequence number; its own block waits for the peers' flags and combines the slots in rank
-// order (identical result on every rank). Replaces the two NCCL all-reduces and the warm-start all-gather: ~20 us each
-// through NCCL at 24 B / 6 KB, a few us as direct stores — and nothing on the stream is a library call, so the
-// sharded update is captured in the CUDA graph like the single-GPU one.
-constexpr int MPPI_MAX_WORLD = 16;
+// rank plus one flag per rank. The exchanges ride the kernels that produce and consume their payloads — no launch of
+// their own: the LAST block of the rollout grid to finish stores this rank's {-min, max, valid} into its slot of every
+// peer's mailbox, fences, and raises its flag there with the update's sequence number (exchange_push); every block of
+// k_weights waits for the peers' flags in the local mailbox and combines the slots in rank order (exchange_wait /
+// exchange_peer). Likewise the last block of k_gradient_reduce pushes {sum w, sum w*eps, argmin slots} and the blocks of
+// k_finish combine them — identical bits on every rank. Replaces two NCCL all-reduces (~20 us each at 24 B / 6 KB) and,
+// against round 1, two exchange launches per update (+45 us at 8 GPUs). Only the warm-start candidates (keep_best > 0
+// on a sharded set) still use the stand-alone exchange kernel.
 enum ExchangeKind { EX_MINMAX = 0, EX_SUMS = 1, EX_CAND = 2, EX_KINDS = 3 };
 struct PeerExchange {
     int world, rank;
@@ -131,9 +140,61 @@ struct PeerExchange {
     long long flags_offset;            // doubles: start of the flags, unsigned long long [2][EX_KINDS][world]
     int count[EX_KINDS];               // doubles per slot
     int *error;                        // host-mapped: a peer did not arrive in time
-    int *copies_done;                  // device: copy blocks of the running launch that have read the payload
+    int *copies_done;                  // device: copy blocks of a running k_exchange launch that have read the payload
     long long timeout_cycles;
 };
+
+#if defined(__CUDACC__)
+// sequence number of an exchange: never 0, unique per (update attempt, kind)
+__device__ __forceinline__ unsigned long long exchange_seq(unsigned long long attempt, int kind) { return attempt * 4ull + (unsigned long long)kind + 1ull; }
+
+// ONE WARP (warp 0 of the calling block; the other warps return at once): this rank's payload -> its slot of every peer's
+// mailbox, ONE system-scope fence, then the flags. The payload must be complete and visible to the block (the callers are
+// "last block" epilogues behind a fence + counter + block barrier). A single warp on purpose: a system-scope fence waits
+// for the peer's acknowledgement of everything the SM has in flight, and a thousand threads each issuing one turned a
+// 6 KB push into 10 us (measured at 2 GPUs).
+__device__ __forceinline__ void exchange_push(const PeerExchange &px, int kind, unsigned long long attempt, const double *payload) {
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const int count = px.count[kind], parity = (int)(attempt & 1ull);
+    const long long slot0 = px.offset[parity][kind] + (long long)px.rank * count;
+    const long long flag0 = px.flags_offset + ((long long)parity * EX_KINDS + kind) * px.world;
+    for (int p = 0; p < px.world; p++) {
+        if (p == px.rank) continue;
+        double *dst = px.mail[p] + slot0;
+        for (int i = lane; i < count; i += 32) dst[i] = __ldcg(payload + i);
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane < px.world && lane != px.rank)
+        *(reinterpret_cast<volatile unsigned long long *>(px.mail[lane] + flag0) + px.rank) = exchange_seq(attempt, kind);
+}
+
+// every block that consumes an exchange: wait until every peer's flag in the LOCAL mailbox carries this exchange's
+// sequence number (volatile loads, 2 s timeout -> *px.error instead of a hung device). Only the polling threads fence
+// (acquire); the block barrier hands the ordering on to the others, which read the slots from L2 (__ldcg).
+__device__ __forceinline__ void exchange_wait(const PeerExchange &px, int kind, unsigned long long attempt) {
+    const int parity = (int)(attempt & 1ull);
+    const long long flag0 = px.flags_offset + ((long long)parity * EX_KINDS + kind) * px.world;
+    if (threadIdx.x < px.world && (int)threadIdx.x != px.rank) {
+        const volatile unsigned long long *flag = reinterpret_cast<const volatile unsigned long long *>(px.mail[px.rank] + flag0) + threadIdx.x;
+        const unsigned long long seq = exchange_seq(attempt, kind);
+        const long long t0 = clock64();
+        while (*flag != seq) {
+            if (clock64() - t0 > px.timeout_cycles) { *px.error = 1; break; }   // never hang the device on a missing peer
+            __nanosleep(32);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
+// element e of rank q's payload as it arrived in the local mailbox (q != rank)
+__device__ __forceinline__ double exchange_peer(const PeerExchange &px, int kind, unsigned long long attempt, int q, int e) {
+    return __ldcg(px.mail[px.rank] + px.offset[(int)(attempt & 1ull)][kind] + (long long)q * px.count[kind] + e);
+}
+#endif
+
 cudaError_t launch_exchange(const DeviceState &d, const PeerExchange &px, int kind, cudaStream_t s);
 
 cudaError_t upload_robot_model();  // once per device
@@ -143,7 +204,6 @@ cudaError_t launch_merge_kept(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_sample(const DeviceState &d, int precision, cudaStream_t s, int *launches);
 // objective params: pointer to the host-side block in kernel arithmetic (ToyP/TrackPointP/AssistedP<R>)
 cudaError_t launch_rollout(const DeviceState &d, int precision, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s);
-cudaError_t launch_minmax_publish(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_weights(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_gradient(const DeviceState &d, int precision, cudaStream_t s, int *launches);
 cudaError_t launch_finish(const DeviceState &d, cudaStream_t s);

@@ -20,13 +20,21 @@ def shard_range(total, rank, world):
     return total * rank // world, total * (rank + 1) // world
 
 
-def local_minmax(costs):
-    """{-min, max, valid} over the non-NaN local costs (valid saturates at 2, like the engine)."""
+def local_minmax(costs, rank=0, world=1):
+    """The engine's first exchange payload: {-min, max, 0, valid_0 .. valid_{world-1}} over the non-NaN local costs, with
+    only this rank's valid slot filled (saturated at 2). Combined with an elementwise MAX, which gathers the disjoint slots;
+    `valid_total` sums them — saturating per rank BEFORE a MAX would turn two ranks with one valid rollout each into one."""
     ok = ~np.isnan(costs)
     n = int(ok.sum())
-    if n == 0:
-        return np.array([-np.inf, -np.inf, 0.0])
-    return np.array([-costs[ok].min(), costs[ok].max(), float(min(n, 2))])
+    out = np.zeros(3 + world)
+    out[0], out[1] = (-np.inf, -np.inf) if n == 0 else (-costs[ok].min(), costs[ok].max())
+    out[3 + rank] = float(min(n, 2))
+    return out
+
+
+def valid_total(minmax):
+    """valid rollouts of the whole set from a combined payload, saturated at 2 (mppi.cpp:368-370 needs two)"""
+    return min(float(np.sum(minmax[3:])), 2.0)
 
 
 def local_weights(costs, minmax, cost_scale):

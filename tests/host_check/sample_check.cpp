@@ -40,7 +40,42 @@ static long long run(int T, long long k_begin, long long k_count, const double *
     return stored;
 }
 
+// the column kernel's enumeration (one thread per column) must store exactly what the quad enumeration stores
+template <class R, class RI>
+static long long run_columns(int T, long long k_begin, long long k_count, const double *U, const unsigned char *kept, const double *ldiag, unsigned long long seed,
+                             unsigned long long update_index, int noise_source, const void *injected, void *noise_out) {
+    constexpr int NU = 12;
+    Frame f;
+    std::memset(&f, 0, sizeof f);
+    f.seed = seed; f.update_index = update_index; f.noise_source = noise_source;
+    DeviceState d;
+    std::memset(&d, 0, sizeof d);
+    d.batch = 1; d.elem_bytes = sizeof(R); d.nu = NU; d.T = T; d.k_begin = k_begin; d.k_count = k_count;
+    d.frame = &f; d.U = const_cast<double *>(U); d.kept = const_cast<unsigned char *>(kept); d.injected = injected;
+    d.L_is_diagonal = 1;
+    for (int i = 0; i < NU; i++) d.Ldiag[i] = ldiag[i];
+    const long long cols = k_count * T;
+    long long stored = 0;
+    R *noise = static_cast<R *>(noise_out);
+    for (long long g = 0; g < (cols + 255) / 256 * 256; g++) {
+        if (g >= cols) continue;
+        long long kl; int t;
+        column_coordinates(g, cols, T, &kl, &t);
+        R v[NU];
+        if (!sample_column<R, RI, NU>(d, d.Ldiag, kl, t, v)) continue;
+        for (int i = 0; i < NU; i++) noise[(size_t)g * NU + i] = v[i];
+        stored += NU / 4;
+    }
+    return stored;
+}
+
 extern "C" {
+long long host_sample_columns(int f32, int injected_is_double, int T, long long k_begin, long long k_count, const double *U, const unsigned char *kept,
+                              const double *ldiag, unsigned long long seed, unsigned long long update_index, int noise_source, const void *injected, void *noise_out) {
+    if (f32) return injected_is_double ? run_columns<float, double>(T, k_begin, k_count, U, kept, ldiag, seed, update_index, noise_source, injected, noise_out)
+                                       : run_columns<float, float>(T, k_begin, k_count, U, kept, ldiag, seed, update_index, noise_source, injected, noise_out);
+    return run_columns<double, double>(T, k_begin, k_count, U, kept, ldiag, seed, update_index, noise_source, injected, noise_out);
+}
 // f32: engine arithmetic is float; injected_is_double: the injected rows are doubles whatever the engine arithmetic
 long long host_sample_quads(int f32, int injected_is_double, int T, long long k_begin, long long k_count, const double *U, const unsigned char *kept,
                             const double *ldiag, unsigned long long seed, unsigned long long update_index, int noise_source, const void *injected, void *noise_out) {

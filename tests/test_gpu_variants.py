@@ -43,12 +43,25 @@ def test_variant_runs(run, precision, mode):
     e.close()
 
 
-def _alt_run(tmp_path, name, precision, env):
+def _alt_run(tmp_path, name, precision, env, objective="trackpoint"):
     out = str(tmp_path / (name + ".npz"))
     full = dict(os.environ)
     full.update(env)
-    subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "alt_worker.py"), out, str(precision)], check=True, env=full, timeout=300)
+    subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "alt_worker.py"), out, str(precision), objective], check=True, env=full, timeout=300)
     return np.load(out)
+
+
+@pytest.mark.parametrize("objective", ["assisted", "trackpoint_full"])
+def test_two_warp_rollout_kernel_is_bit_identical_with_the_one_warp_path(tmp_path, objective):
+    """FP32 fast mode of the objectives with kinematics: the production kernel splits a rollout over a state warp (FP64 state
+    path) and a cost warp (FP32 kinematics / RNEA / objective) that meet in a shared-memory ring (k_rollout.cuh
+    k_rollout_split); MPPI_B200_SPLIT=0 runs the same arithmetic in one warp (rollout_franka, the code the CPU tests
+    compile). Same operations in the same order: every cost, and therefore everything downstream, is bit-identical —
+    over updates with a kept set and a time shift."""
+    split = _alt_run(tmp_path, "split", abi.FP32, {}, objective)
+    one = _alt_run(tmp_path, "one_warp", abi.FP32, {"MPPI_B200_SPLIT": "0"}, objective)
+    for k in split.files:
+        assert np.array_equal(split[k], one[k], equal_nan=True), k
 
 
 @pytest.mark.parametrize("precision,c_tol,u_tol", [(abi.FP64, 1e-9, 1e-9), (abi.FP32, 1e-3, 2e-4)])

@@ -29,6 +29,8 @@ def sc():
     lib.host_sample_quads.restype = C.c_longlong
     lib.host_sample_quads.argtypes = [C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_ulonglong,
                                       C.c_int, C.c_void_p, C.c_void_p]
+    lib.host_sample_columns.restype = C.c_longlong
+    lib.host_sample_columns.argtypes = lib.host_sample_quads.argtypes
     lib.host_quad_coordinates.argtypes = [C.c_longlong, C.c_longlong, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.host_philox.argtypes = [C.c_void_p] * 3
     return lib
@@ -77,7 +79,7 @@ def _expected(T, k_begin, k_count, U, kept, ldiag, seed, upd, noise_source, inje
             z0, z1 = _box_muller_np(r[0], r[1])
             z2, z3 = _box_muller_np(r[2], r[3])
             for i, z in enumerate((z0, z1, z2, z3)):
-                fresh[:, :, 4 * b + i] = ldiag[4 * b + i] * z.astype(np.float64)
+                fresh[:, :, 4 * b + i] = ldiag[4 * b + i] * z.astype(np.float64)   # (FP32 buffers: float(l) * z, one rounding apart)
     else:
         fresh = injected.reshape(k_count, T, 12).astype(np.float64)
     for kl in range(k_count):
@@ -117,6 +119,11 @@ def test_quad_enumeration_matches_independent_construction(sc, f32, k_begin, k_c
     assert np.allclose(got[~exact], want[~exact], rtol=2e-5, atol=2e-6)
     if noise_source == 0 and (~exact).any():
         assert np.all(got[~exact][..., 10:] == 0.0) and np.abs(got[~exact][..., :10]).min() > 0.0
+    # the production kernel enumerates COLUMNS (one thread per NU values): same stores, bit for bit
+    out2 = prefill.copy()
+    stored2 = sc.host_sample_columns(f32, inj_is_double, T, k_begin, k_count, U.ctypes.data, kept.ctypes.data, ldiag.ctypes.data, seed, upd, noise_source,
+                                     injected.ctypes.data, out2.ctypes.data)
+    assert stored2 == stored and np.array_equal(out2, out)
 
 
 def test_quad_coordinates_both_widths(sc):

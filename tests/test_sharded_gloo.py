@@ -30,7 +30,8 @@ def _worker(rank, world, port, K, T, nu, cost_scale, out):
     data = np.load(out + "/oracle.npz")
     b, e = sharding.shard_range(K + 2, rank, world)
     costs, noise = data["costs"][b:e], data["noise"].reshape(K + 2, T * nu)[b:e]
-    mm = sharding.all_reduce(dist, sharding.local_minmax(costs), dist.ReduceOp.MAX)
+    mm = sharding.all_reduce(dist, sharding.local_minmax(costs, rank, world), dist.ReduceOp.MAX)
+    assert sharding.valid_total(mm) == 2.0
     w = sharding.local_weights(costs, mm, cost_scale)
     sums = sharding.all_reduce(dist, sharding.local_sums(w, noise), dist.ReduceOp.SUM)
     np.savez(out + "/rank%d.npz" % rank, minmax=mm, weights=w / sums[0], gradient=sums[1:] / sums[0], begin=b, end=e)
@@ -62,6 +63,19 @@ def test_two_rank_exchange_reproduces_the_oracle(oracle, tmp_path, K):
         assert -p["minmax"][0] == mm[0] and p["minmax"][1] == mm[1]   # min / max are exact
         assert np.allclose(p["gradient"], gradient, rtol=1e-12, atol=1e-15)
     assert np.allclose(np.concatenate([p["weights"] for p in parts]), weights, rtol=1e-12, atol=0)
+
+
+def test_valid_rollouts_are_counted_after_the_exchange():
+    """mppi.cpp:368-370 needs two valid rollouts in the WHOLE set: two ranks holding one each must not combine to one
+    (saturating each rank's count before a MAX did that); the payload carries one slot per rank instead."""
+    from assistedmanipulation_b200 import sharding
+    nan = float("nan")
+    parts = [sharding.local_minmax(np.array([nan, 3.0, nan]), 0, 2), sharding.local_minmax(np.array([nan, nan, 5.0]), 1, 2)]
+    mm = np.max(np.stack(parts), axis=0)
+    assert (-mm[0], mm[1]) == (3.0, 5.0) and sharding.valid_total(mm) == 2.0
+    one = np.max(np.stack([sharding.local_minmax(np.array([nan, 3.0]), 0, 2), sharding.local_minmax(np.array([nan, nan]), 1, 2)]), axis=0)
+    assert sharding.valid_total(one) == 1.0
+    assert sharding.valid_total(sharding.local_minmax(np.array([1.0, 2.0, 3.0]))) == 2.0
 
 
 def test_shard_ranges_are_contiguous_and_ordered():
