@@ -300,7 +300,7 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     A(d.cand, (size_t)2 * std::max<long long>(d.keep_best, 1)); A(d.cand_all, (size_t)2 * std::max<long long>(d.keep_best, 1) * c->world_size);
     A(d.minmax_enc, 2); A(d.valid_count, 1); A(d.argmin, 1); A(d.finish_count, 1); A(d.minmax, 4); A(d.sums, 1 + n + (size_t)c->world_size);
     A(d.minmax_local, 3 + MPPI_MAX_WORLD); A(d.rollout_done, 1); A(d.reduce_done, 1);
-    d.px = nullptr;
+    d.has_px = 0;
     d.weight_blocks = (int)((d.k_count + 255) / 256);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -458,7 +458,7 @@ int host_complete(mppi_b200_engine *e) {
         for (int i = 0; i < MPPI_B200_STAGES; i++) { float ms = 0.f; cudaEventElapsedTime(&ms, e->ev_stage[i], e->ev_stage[i + 1]); e->stage_s[i] = ms * 1e-3; }
     }
     e->in_update = false;
-    if (e->p2p && *e->h_p2p_error) { *e->h_p2p_error = 0; return fail(e, MPPI_B200_ERR_NCCL, "peer exchange timed out: a rank of the sharded rollout set did not arrive"); }
+    if (e->p2p && *e->h_p2p_error) { *e->h_p2p_error = 0; cudaMemsetAsync(e->px.error_dev, 0, sizeof(int), e->stream); return fail(e, MPPI_B200_ERR_NCCL, "peer exchange timed out: a rank of the sharded rollout set did not arrive"); }
     bool all_nan = false, smoothed = false;
     // the only section a concurrent mppi_b200_get waits for: the copy of the published sequence (the reference holds its
     // mutex around `m_optimal_control = m_optimal_control_shifted` only, mppi.cpp:178-182)
@@ -651,13 +651,17 @@ static int p2p_allocate(mppi_b200_engine *e) {
         for (int k = 0; k < EX_KINDS; k++) { px.offset[parity][k] = at; at += (long long)d.world * ((px.count[k] + 1) & ~1); }
     px.flags_offset = at;
     at += 2ll * EX_KINDS * d.world;
+    // flag-in-data slots of the two per-update exchanges: two 8-byte words per double (kernels.cuh)
+    for (int parity = 0; parity < 2; parity++)
+        for (int k = 0; k < 2; k++) { px.ll_offset[parity][k] = at; at += 2ll * d.world * px.count[k]; }
     CUDA_TRY(e, cudaMalloc(&e->mailbox, (size_t)at * sizeof(double)));
     CUDA_TRY(e, cudaMemset(e->mailbox, 0, (size_t)at * sizeof(double)));
     CUDA_TRY(e, cudaHostAlloc(&e->h_p2p_error, sizeof(int), cudaHostAllocMapped));
     *e->h_p2p_error = 0;
     CUDA_TRY(e, cudaHostGetDevicePointer((void **)&px.error, e->h_p2p_error, 0));
     px.copies_done = dev_alloc<int>(e, 1);
-    if (!px.copies_done) return fail(e, MPPI_B200_ERR_CUDA, "device allocation failed");
+    px.error_dev = dev_alloc<int>(e, 1);
+    if (!px.copies_done || !px.error_dev) return fail(e, MPPI_B200_ERR_CUDA, "device allocation failed");
     px.timeout_cycles = 4000000000ll;   // ~2 s
     for (int q = 0; q < MPPI_MAX_WORLD; q++) px.mail[q] = nullptr;
     px.mail[d.rank] = e->mailbox;
@@ -693,11 +697,8 @@ int mppi_b200_p2p_init(mppi_b200_engine *e, const void *handles) {
     }
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     for (cudaGraphExec_t &g : e->graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
-    // the kernels read the exchange description through a device copy (keeps their parameter blocks small)
-    PeerExchange *d_px = dev_alloc<PeerExchange>(e, 1, false);
-    if (!d_px) return fail(e, MPPI_B200_ERR_CUDA, "device allocation failed");
-    CUDA_TRY(e, cudaMemcpy(d_px, &e->px, sizeof(PeerExchange), cudaMemcpyHostToDevice));
-    e->d.px = d_px;
+    e->d.px = e->px;       // by value in the kernels' parameter bank
+    e->d.has_px = 1;
     e->p2p = true;
     return MPPI_B200_OK;
 }

@@ -337,14 +337,15 @@ __global__ void __launch_bounds__(256) k_weights(const __grid_constant__ DeviceS
         // Peer-memory exchange: wait for the peers' payloads in the local mailbox and combine in rank order (MAX; the
         // valid slots are disjoint, so MAX gathers them). NCCL / split ABI: the buffer was all-reduced (MAX) in place.
         const unsigned long long attempt = d.frame->attempt;
-        if (d.px) exchange_wait(*d.px, EX_MINMAX, attempt);
+        // (the exchange description is read from the kernel's parameter bank, `dg`: indexing its arrays through the
+        // controller view's copy would park the whole state in local memory; exchange_peer polls until the element is there)
         mm0 = d.minmax_local[0]; mm1 = d.minmax_local[1];
         double valid = 0.0;
         for (int q = 0; q < d.world; q++) {
-            if (d.px && q != d.rank) {
-                mm0 = fmax(mm0, exchange_peer(*d.px, EX_MINMAX, attempt, q, 0));
-                mm1 = fmax(mm1, exchange_peer(*d.px, EX_MINMAX, attempt, q, 1));
-                valid += exchange_peer(*d.px, EX_MINMAX, attempt, q, 3 + q);
+            if (dg.has_px && q != d.rank) {
+                mm0 = fmax(mm0, exchange_peer(dg.px, EX_MINMAX, attempt, q, 0));
+                mm1 = fmax(mm1, exchange_peer(dg.px, EX_MINMAX, attempt, q, 1));
+                valid += exchange_peer(dg.px, EX_MINMAX, attempt, q, 3 + q);
             } else valid += d.minmax_local[3 + q];
         }
         mm2 = valid >= 2.0 ? 2.0 : valid;   // saturate AFTER the sum: two ranks with one valid rollout each are two valid rollouts (mppi.cpp:368-370)
@@ -389,22 +390,23 @@ __device__ __forceinline__ void fma_vec(double *acc, double w, const float4 &v) 
     acc[0] = fma(w, (double)v.x, acc[0]); acc[1] = fma(w, (double)v.y, acc[1]); acc[2] = fma(w, (double)v.z, acc[2]); acc[3] = fma(w, (double)v.w, acc[3]);
 }
 
-// Row groups: when a row has fewer 16-byte vectors than a block has threads (FP32 rows at T = 64: 192), the block's
+// Row groups (G > 1): when a row has fewer 16-byte vectors than a block has threads (FP32 rows at T = 64: 192), the block's
 // threads split into G groups that walk different rows, so every thread has loads in flight (the FP32 kernel ran 192 of
 // 256 threads and reached 2.3 TB/s where the FP64 one reaches 5.7); the groups' sums meet in shared memory in group order.
-template <class R> __global__ void __launch_bounds__(512) k_gradient(const __grid_constant__ DeviceState dg, int groups) {
+// G is a template parameter: G = 1 is the plain kernel, whose row loop the compiler unrolls on its own (128 registers).
+template <class R, int G> __global__ void __launch_bounds__(512) k_gradient(const __grid_constant__ DeviceState dg) {
     const DeviceState d = controller_view(dg, blockIdx.y);
     typedef typename Vec16<R>::type V;
     constexpr int VN = Vec16<R>::n;
-    extern __shared__ __align__(16) double s_group[];   // (groups - 1) x n partial sums
+    extern __shared__ __align__(16) double s_group[];   // (G - 1) x n partial sums
     if (*d.skip) return;
     const int n = d.nu * d.T;
     const int nvec = n / VN;  // host guarantees divisibility
     const V *noise = static_cast<const V *>(d.noise);
-    const int g = groups > 1 ? (int)threadIdx.x / nvec : 0;
-    const int lanes = groups > 1 ? nvec : (int)blockDim.x;          // threads that walk a row together
-    const long long first = (long long)blockIdx.x * groups + g, stride = (long long)gridDim.x * groups;
-    for (int e = groups > 1 ? (int)threadIdx.x - g * nvec : (int)threadIdx.x; e < nvec && g < groups; e += lanes) {
+    const int g = G > 1 ? (int)threadIdx.x / nvec : 0;
+    const int lanes = G > 1 ? nvec : (int)blockDim.x;          // threads that walk a row together
+    const long long first = (long long)blockIdx.x * G + g, stride = (long long)gridDim.x * G;
+    for (int e = G > 1 ? (int)threadIdx.x - g * nvec : (int)threadIdx.x; e < nvec && g < G; e += lanes) {
         double acc[VN];
 #pragma unroll
         for (int i = 0; i < VN; i++) acc[i] = 0.0;
@@ -419,7 +421,7 @@ template <class R> __global__ void __launch_bounds__(512) k_gradient(const __gri
             fma_vec(acc, w0, v0); fma_vec(acc, w1, v1); fma_vec(acc, w2, v2); fma_vec(acc, w3, v3);
         }
         for (; k < d.k_count; k += stride) fma_vec(acc, d.weights[k], __ldg(noise + (size_t)k * nvec + e));
-        if (g == 0) {
+        if (G == 1 || g == 0) {
 #pragma unroll
             for (int i = 0; i < VN; i++) d.grad_partial[(size_t)blockIdx.x * n + e * VN + i] = acc[i];
         } else {
@@ -427,11 +429,11 @@ template <class R> __global__ void __launch_bounds__(512) k_gradient(const __gri
             for (int i = 0; i < VN; i++) s_group[(size_t)(g - 1) * n + e * VN + i] = acc[i];
         }
     }
-    if (groups > 1) {
+    if (G > 1) {
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             double sum = d.grad_partial[(size_t)blockIdx.x * n + i];
-            for (int q = 1; q < groups; q++) sum += s_group[(size_t)(q - 1) * n + i];
+            for (int q = 1; q < G; q++) sum += s_group[(size_t)(q - 1) * n + i];
             d.grad_partial[(size_t)blockIdx.x * n + i] = sum;
         }
     }
@@ -487,7 +489,7 @@ __global__ void __launch_bounds__(1024) k_gradient_reduce(const __grid_constant_
             }
         }
     }
-    if (d.world > 1 && d.px) {
+    if (d.world > 1 && dg.has_px) {
         // the LAST block to get here stores this rank's {sum w, sum w*eps, argmin slots} into the peers' mailboxes:
         // the second exchange of the update rides this kernel's tail (k_finish combines the slots)
         __shared__ int s_last;
@@ -498,7 +500,7 @@ __global__ void __launch_bounds__(1024) k_gradient_reduce(const __grid_constant_
         if (s_last) {
             __threadfence();
             if (threadIdx.x == 0) *d.reduce_done = 0;
-            exchange_push(*d.px, EX_SUMS, d.frame->attempt, d.sums);
+            exchange_push(dg.px, EX_SUMS, d.frame->attempt, d.sums);
         }
     }
 }
@@ -548,23 +550,24 @@ __device__ __forceinline__ bool sg_recurrence_dispatch(int nr, const double *F, 
 
 // element e of the exchanged {sum w, sum w*eps, argmin slots}: combined here in rank order from the peers' slots in the
 // local mailbox (peer-memory exchange; identical bits on every rank), or already all-reduced in place (NCCL, split ABI)
-__device__ __forceinline__ double combined_sum(const DeviceState &d, int e) {
-    if (d.world == 1 || !d.px) return d.sums[e];
+// (px: the exchange description in the kernel's parameter bank; null = no peer exchange)
+__device__ __forceinline__ double combined_sum(const DeviceState &d, const PeerExchange *px, int e) {
+    if (d.world == 1 || !px) return d.sums[e];
     const unsigned long long attempt = d.frame->attempt;
     double acc = 0.0;
-    for (int q = 0; q < d.world; q++) acc += (q == d.rank) ? d.sums[e] : exchange_peer(*d.px, EX_SUMS, attempt, q, e);
+    for (int q = 0; q < d.world; q++) acc += (q == d.rank) ? d.sums[e] : exchange_peer(*px, EX_SUMS, attempt, q, e);
     return acc;
 }
 
-__device__ __forceinline__ void finish_publish_stats(const DeviceState &d, int n) {
+__device__ __forceinline__ void finish_publish_stats(const DeviceState &d, const PeerExchange *px, int n) {
     d.result[n + 0] = d.minmax[0]; d.result[n + 1] = d.minmax[1]; d.result[n + 2] = d.minmax[2];
     long long best = *d.argmin;
     if (d.world > 1) {   // lowest global index among the ranks that hold the global minimum (mppi.cpp:363-366 order)
         best = 0x7fffffffffffffffll;
-        for (int r = 0; r < d.world; r++) { const double v = combined_sum(d, 1 + n + r); if (v > 0.0 && (long long)v - 1 < best) best = (long long)v - 1; }
+        for (int r = 0; r < d.world; r++) { const double v = combined_sum(d, px, 1 + n + r); if (v > 0.0 && (long long)v - 1 < best) best = (long long)v - 1; }
     }
     d.result[n + 3] = __longlong_as_double(best);
-    d.result[n + 4] = combined_sum(d, 0);
+    d.result[n + 4] = combined_sum(d, px, 0);
 }
 
 __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DeviceState dg) {
@@ -578,20 +581,21 @@ __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DeviceSt
     double *sw = tm + d.sg_len;                            // 2w+1 taps
     const int n = d.nu * d.T, ch = blockIdx.x;
     const int skip = *d.skip;
-    if (d.world > 1 && d.px) exchange_wait(*d.px, EX_SUMS, d.frame->attempt);   // the peers' {sum w, sum w*eps, argmin slots} have arrived
+    const PeerExchange *px = (d.world > 1 && dg.has_px) ? &dg.px : nullptr;   // in the parameter bank (see k_weights)
+    const double total = combined_sum(d, px, 0);   // (peer exchange: polls until the peers' {sum w, ...} have arrived)
+    if (px) __syncthreads();                       // ... so that a peer that never arrived is known to every thread below
     // "all nan rollouts" (mppi.cpp:368-370): the reference throws before publishing. A peer that never arrived (exchange
     // time-out) is handled the same way: the engine keeps its last good control sequence, the host reports the error.
-    const bool dead = !(d.minmax[2] >= 2.0) || (d.px && *d.px->error);
+    const bool dead = !(d.minmax[2] >= 2.0) || (px && *px->error_dev);
     if (dead) {   // nothing is published but the statistics
-        if (ch == 0 && threadIdx.x == 0) finish_publish_stats(d, n);
+        if (ch == 0 && threadIdx.x == 0) finish_publish_stats(d, px, n);
         return;
     }
-    const double total = combined_sum(d, 0);
     for (int t = threadIdx.x; t < d.T; t += blockDim.x) {
         const int e = t * d.nu + ch;
         double v = d.U_shift[e];
         if (!skip) {
-            const double g = combined_sum(d, 1 + e) / total;   // weights are normalised by the total (mppi.cpp:403-408)
+            const double g = combined_sum(d, px, 1 + e) / total;   // weights are normalised by the total (mppi.cpp:403-408)
             d.gradient[e] = g;
             v += g * d.gradient_step;
         }
@@ -692,8 +696,8 @@ __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DeviceSt
         const int e = t * d.nu + ch;
         double v = sU[t];
         if (!skip && d.bound) {
-            v = std_min(v, d.cmax[ch]);   // cwiseMin(max).cwiseMax(min), mppi.cpp:443-447; std::min / std::max NaN semantics
-            v = std_max(v, d.cmin[ch]);
+            v = std_min(v, dg.cmax[ch]);   // (dg: dynamic index into the parameter bank, not into a local copy of the state)   // cwiseMin(max).cwiseMax(min), mppi.cpp:443-447; std::min / std::max NaN semantics
+            v = std_max(v, dg.cmin[ch]);
         }
         d.U_shift[e] = v;
         d.U[e] = v;        // publication: m_optimal_control = m_optimal_control_shifted (mppi.cpp:178-182)
@@ -712,7 +716,7 @@ __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DeviceSt
         double2 *dst = reinterpret_cast<double2 *>(d.result);
         for (int i = threadIdx.x; i < n / 2; i += blockDim.x) dst[i] = __ldcg(src + i);
         if ((n & 1) && threadIdx.x == 0) d.result[n - 1] = __ldcg(d.U + n - 1);
-        if (threadIdx.x == 0) { finish_publish_stats(d, n); *d.finish_count = 0; }
+        if (threadIdx.x == 0) { finish_publish_stats(d, px, n); *d.finish_count = 0; }
     }
 }
 
@@ -848,13 +852,13 @@ __global__ void __launch_bounds__(256) k_exchange(const __grid_constant__ Device
         const volatile unsigned long long *flag = reinterpret_cast<const volatile unsigned long long *>(px.mail[px.rank] + flag0) + threadIdx.x;
         const long long t0 = clock64();
         while (*flag != seq) {
-            if (clock64() - t0 > px.timeout_cycles) { *px.error = 1; break; }   // never hang the device on a missing peer
+            if (*px.error_dev || clock64() - t0 > px.timeout_cycles) { *px.error = 1; *px.error_dev = 1; break; }   // never hang the device on a missing peer
             __nanosleep(100);
         }
     }
     if (threadIdx.x == 0) {   // the (co-resident) copy blocks of this launch are done with the payload
         const long long t0 = clock64();
-        while (atomicAdd(px.copies_done, 0) != px.world - 1) { if (clock64() - t0 > px.timeout_cycles) { *px.error = 1; break; } }
+        while (atomicAdd(px.copies_done, 0) != px.world - 1) { if (clock64() - t0 > px.timeout_cycles) { *px.error = 1; *px.error_dev = 1; break; } }
         *px.copies_done = 0;
     }
     __threadfence_system();
@@ -890,9 +894,14 @@ cudaError_t launch_gradient(const DeviceState &d, int precision, cudaStream_t s,
     const int n = d.nu * d.T;
     const int nvec = n / (precision == 0 ? 2 : 4);
     int threads = std::min(512, ((nvec + 127) / 128) * 128), groups = 1;
-    if (nvec <= 256 && d.k_count >= 4096) { groups = std::min(512 / nvec, 4); threads = ((groups * nvec + 31) / 32) * 32; }   // short rows: several rows per block pass
+    if (nvec <= 256 && d.k_count >= 4096) { groups = 512 / nvec >= 4 ? 4 : 2; threads = ((groups * nvec + 31) / 32) * 32; }   // short rows: several rows per block pass
     const size_t smem = groups > 1 ? sizeof(double) * (size_t)(groups - 1) * n : 0;
-    if (precision == 0) k_gradient<double><<<dim3(d.grad_blocks, d.batch), threads, smem, s>>>(d, groups); else k_gradient<float><<<dim3(d.grad_blocks, d.batch), threads, smem, s>>>(d, groups);
+    const dim3 grid(d.grad_blocks, d.batch);
+    if (precision == 0) {
+        if (groups == 1) k_gradient<double, 1><<<grid, threads, smem, s>>>(d); else if (groups == 2) k_gradient<double, 2><<<grid, threads, smem, s>>>(d); else k_gradient<double, 4><<<grid, threads, smem, s>>>(d);
+    } else {
+        if (groups == 1) k_gradient<float, 1><<<grid, threads, smem, s>>>(d); else if (groups == 2) k_gradient<float, 2><<<grid, threads, smem, s>>>(d); else k_gradient<float, 4><<<grid, threads, smem, s>>>(d);
+    }
     k_gradient_reduce<<<dim3((n + 31) / 32, d.batch), 1024, 0, s>>>(d);
     *launches += 2;
     return cudaGetLastError();

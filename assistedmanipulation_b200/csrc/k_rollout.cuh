@@ -47,7 +47,7 @@ __device__ __forceinline__ void rollout_grid_epilogue(const DeviceState &d, cons
             __threadfence();
         }
         __syncthreads();
-        if (d.px) exchange_push(*d.px, EX_MINMAX, frame->attempt, d.minmax_local);
+        if (d.has_px) exchange_push(d.px, EX_MINMAX, frame->attempt, d.minmax_local);
     }
 }
 
@@ -326,7 +326,13 @@ cudaError_t launch_rollout_t(const DeviceState &d, const void *params, bool opti
 #if defined(MPPI_ROLLOUT_F32)
     if constexpr (sizeof(R) == 4 && MPPI_MIXED_STATE >= 2 && !FAITHFUL && (VAR == VAR_TP_FULL || VAR == VAR_AM || VAR == VAR_AM_ENERGY)) {
         static const bool split = !(std::getenv("MPPI_B200_SPLIT") && std::getenv("MPPI_B200_SPLIT")[0] == '0');
-        if (split && !optimal_only) {
+        // two warps per 32 rollouts pay when the doubled grid is still ONE wave (255 registers: four 64-thread blocks per SM);
+        // beyond that — the 32 batched controllers of config 5 — the one-warp kernel's single wave is faster (measured 767 us
+        // against 941)
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        const long long split_blocks = (d.k_count + 31) / 32 * (long long)d.batch;
+        if (split && !optimal_only && split_blocks <= 4ll * sms) {
             const size_t ssmem = sizeof(SplitSlot) * SPLIT_DEPTH + sizeof(double) * ((size_t)d.nu * d.T + (size_t)d.T + 32) + sizeof(float) * 6 * (size_t)d.T;
             auto skern = k_rollout_split<VAR, ParamsT>;
             if (ssmem > 48 * 1024) {

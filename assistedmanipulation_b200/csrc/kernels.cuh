@@ -29,6 +29,21 @@ struct Frame {
     // followed by T x 6 doubles of forecast wrench
 };
 
+// description of the peer-memory exchange of a sharded rollout set (see the comment further down)
+enum ExchangeKind { EX_MINMAX = 0, EX_SUMS = 1, EX_CAND = 2, EX_KINDS = 3 };
+struct PeerExchange {
+    int world, rank;
+    double *mail[MPPI_MAX_WORLD];      // mailbox of every rank as mapped in this process (mail[rank] is local)
+    long long offset[2][EX_KINDS];     // doubles: start of the [world][count] slot array of (parity, kind)
+    long long flags_offset;            // doubles: start of the flags, unsigned long long [2][EX_KINDS][world]
+    long long ll_offset[2][2];         // doubles: start of the flag-in-data slot array of (parity, kind) for EX_MINMAX / EX_SUMS: [world][count][2] 8-byte words
+    int count[EX_KINDS];               // doubles per slot
+    int *error;                        // host-mapped: a peer did not arrive in time
+    int *error_dev;                    // the same flag in device memory (what the kernels test: a host-mapped read is a PCIe round trip)
+    int *copies_done;                  // device: copy blocks of a running k_exchange launch that have read the payload
+    long long timeout_cycles;
+};
+
 // Device-resident state of one engine (pointers only; owned by the engine).
 struct DeviceState {
     // geometry
@@ -63,7 +78,8 @@ struct DeviceState {
     double *minmax_local;  // exchange buffer of a sharded set: {-min, max, 0, valid_0 .. valid_{world-1}} with only this rank's valid slot
                            // filled (<= 2) — combined with MAX elementwise, which gathers the slots; their sum is the valid count
     double *sums;          // exchange buffer {sum w, sum w*eps [nu*T], argmin slot per rank}: this rank's part (p2p) / all-reduced in place (NCCL, split ABI)
-    const struct PeerExchange *px;   // device copy of the peer-memory exchange description, or nullptr
+    int has_px;            // the peer-memory exchange is attached
+    PeerExchange px;       // by value: the kernels read it from their parameter bank, not through a pointer chase
     int *rollout_done;     // blocks of the rollout grid that are done (the last one publishes / pushes the min-max payload)
     int *reduce_done;      // blocks of k_gradient_reduce that are done (the last one pushes the sums payload)
     double *wsum_partial;  // per block of the weights kernel
@@ -123,76 +139,69 @@ __device__ __forceinline__ DeviceState controller_view(const DeviceState &g, int
 #endif
 
 // ---- exchange between the ranks of a sharded rollout set over NVLink peer memory ---------------------------
-// Every rank owns a mailbox (device memory, IPC-mapped into its peers): per update parity and per kind one slot per
-// rank plus one flag per rank. The exchanges ride the kernels that produce and consume their payloads — no launch of
-// their own: the LAST block of the rollout grid to finish stores this rank's {-min, max, valid} into its slot of every
-// peer's mailbox, fences, and raises its flag there with the update's sequence number (exchange_push); every block of
-// k_weights waits for the peers' flags in the local mailbox and combines the slots in rank order (exchange_wait /
-// exchange_peer). Likewise the last block of k_gradient_reduce pushes {sum w, sum w*eps, argmin slots} and the blocks of
-// k_finish combine them — identical bits on every rank. Replaces two NCCL all-reduces (~20 us each at 24 B / 6 KB) and,
-// against round 1, two exchange launches per update (+45 us at 8 GPUs). Only the warm-start candidates (keep_best > 0
-// on a sharded set) still use the stand-alone exchange kernel.
-enum ExchangeKind { EX_MINMAX = 0, EX_SUMS = 1, EX_CAND = 2, EX_KINDS = 3 };
-struct PeerExchange {
-    int world, rank;
-    double *mail[MPPI_MAX_WORLD];      // mailbox of every rank as mapped in this process (mail[rank] is local)
-    long long offset[2][EX_KINDS];     // doubles: start of the [world][count] slot array of (parity, kind)
-    long long flags_offset;            // doubles: start of the flags, unsigned long long [2][EX_KINDS][world]
-    int count[EX_KINDS];               // doubles per slot
-    int *error;                        // host-mapped: a peer did not arrive in time
-    int *copies_done;                  // device: copy blocks of a running k_exchange launch that have read the payload
-    long long timeout_cycles;
-};
-
+// Every rank owns a mailbox (device memory, IPC-mapped into its peers) with, per update parity and per kind, one slot per
+// rank. The two per-update exchanges ride the kernels that produce and consume their payloads — no launch of their own:
+// the LAST block of the rollout grid to finish stores this rank's {-min, max, valid slots} into its slot of every peer's
+// mailbox (exchange_push), and the threads of k_weights poll the elements they need in the local mailbox and combine them in
+// rank order (exchange_peer). Likewise the last block of k_gradient_reduce pushes {sum w, sum w*eps, argmin slots} and the
+// threads of k_finish combine them — identical bits on every rank. Transport: flag-in-data (below). Replaces two NCCL
+// all-reduces (~20 us each at 40 B / 6 KB) and, against round 1, two exchange launches per update. Only the warm-start
+// candidates (keep_best > 0 on a sharded set) still use the stand-alone k_exchange with its payload + fence + flag protocol.
 #if defined(__CUDACC__)
 // sequence number of an exchange: never 0, unique per (update attempt, kind)
 __device__ __forceinline__ unsigned long long exchange_seq(unsigned long long attempt, int kind) { return attempt * 4ull + (unsigned long long)kind + 1ull; }
 
-// ONE WARP (warp 0 of the calling block; the other warps return at once): this rank's payload -> its slot of every peer's
-// mailbox, ONE system-scope fence, then the flags. The payload must be complete and visible to the block (the callers are
-// "last block" epilogues behind a fence + counter + block barrier). A single warp on purpose: a system-scope fence waits
-// for the peer's acknowledgement of everything the SM has in flight, and a thousand threads each issuing one turned a
-// 6 KB push into 10 us (measured at 2 GPUs).
+// ---- flag-in-data transport of the two per-update exchanges (EX_MINMAX, EX_SUMS) -------------------------------------
+// Every double travels as two 8-byte words {32 payload bits | 32-bit sequence number}: an 8-byte store is atomic, so a
+// word that carries this exchange's sequence number carries its payload — no fence, no separate flag, no round trip: the
+// producer's stores go out and the consumers poll the very words they need (the protocol NCCL calls LL). With a payload
+// store + system fence + flag store the push alone waited one NVLink round trip and the flag one more hop (measured at
+// 2 GPUs: ~12 us per exchange on the critical path).
+__device__ __forceinline__ unsigned long long *exchange_ll_slot(const PeerExchange &px, int owner, int kind, unsigned long long attempt, int src_rank, int e) {
+    return reinterpret_cast<unsigned long long *>(px.mail[owner] + px.ll_offset[(int)(attempt & 1ull)][kind]) + ((long long)src_rank * px.count[kind] + e) * 2;
+}
+
+// ONE block (all of its threads may call; at most 256 work): this rank's payload into its slot of every peer's mailbox.
+// The payload must be complete and visible to the block (the callers are "last block" epilogues behind a fence + counter
+// + block barrier).
 __device__ __forceinline__ void exchange_push(const PeerExchange &px, int kind, unsigned long long attempt, const double *payload) {
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
-    const int count = px.count[kind], parity = (int)(attempt & 1ull);
-    const long long slot0 = px.offset[parity][kind] + (long long)px.rank * count;
-    const long long flag0 = px.flags_offset + ((long long)parity * EX_KINDS + kind) * px.world;
-    for (int p = 0; p < px.world; p++) {
-        if (p == px.rank) continue;
-        double *dst = px.mail[p] + slot0;
-        for (int i = lane; i < count; i += 32) dst[i] = __ldcg(payload + i);
-    }
-    __threadfence_system();
-    __syncwarp();
-    if (lane < px.world && lane != px.rank)
-        *(reinterpret_cast<volatile unsigned long long *>(px.mail[lane] + flag0) + px.rank) = exchange_seq(attempt, kind);
-}
-
-// every block that consumes an exchange: wait until every peer's flag in the LOCAL mailbox carries this exchange's
-// sequence number (volatile loads, 2 s timeout -> *px.error instead of a hung device). Only the polling threads fence
-// (acquire); the block barrier hands the ordering on to the others, which read the slots from L2 (__ldcg).
-__device__ __forceinline__ void exchange_wait(const PeerExchange &px, int kind, unsigned long long attempt) {
-    const int parity = (int)(attempt & 1ull);
-    const long long flag0 = px.flags_offset + ((long long)parity * EX_KINDS + kind) * px.world;
-    if (threadIdx.x < px.world && (int)threadIdx.x != px.rank) {
-        const volatile unsigned long long *flag = reinterpret_cast<const volatile unsigned long long *>(px.mail[px.rank] + flag0) + threadIdx.x;
-        const unsigned long long seq = exchange_seq(attempt, kind);
-        const long long t0 = clock64();
-        while (*flag != seq) {
-            if (clock64() - t0 > px.timeout_cycles) { *px.error = 1; break; }   // never hang the device on a missing peer
-            __nanosleep(32);
+    const int count = px.count[kind];
+    const unsigned long long seq = (exchange_seq(attempt, kind) & 0xffffffffull) << 32;
+    const int workers = blockDim.x < 256 ? (int)blockDim.x : 256;
+    if ((int)threadIdx.x >= workers) return;
+    for (int i0 = threadIdx.x; i0 < count; i0 += 4 * workers) {
+        unsigned long long bits[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) bits[j] = (i0 + j * workers < count) ? (unsigned long long)__double_as_longlong(__ldcg(payload + i0 + j * workers)) : 0ull;   // loads first: one round trip
+        for (int p = 0; p < px.world; p++) {
+            if (p == px.rank) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int i = i0 + j * workers;
+                if (i >= count) continue;
+                volatile unsigned long long *dst = exchange_ll_slot(px, p, kind, attempt, px.rank, i);
+                dst[0] = (bits[j] & 0xffffffffull) | seq;
+                dst[1] = (bits[j] >> 32) | seq;
+            }
         }
-        __threadfence_system();
     }
-    __syncthreads();
 }
 
-// element e of rank q's payload as it arrived in the local mailbox (q != rank)
+// element e of rank q's payload (q != rank): poll the two words in the LOCAL mailbox until both carry this exchange's
+// sequence number (2 s timeout -> *px.error instead of a hung device; once a peer is known missing nothing waits again)
 __device__ __forceinline__ double exchange_peer(const PeerExchange &px, int kind, unsigned long long attempt, int q, int e) {
-    return __ldcg(px.mail[px.rank] + px.offset[(int)(attempt & 1ull)][kind] + (long long)q * px.count[kind] + e);
+    const volatile unsigned long long *src = exchange_ll_slot(px, px.rank, kind, attempt, q, e);
+    const unsigned long long seq = exchange_seq(attempt, kind) & 0xffffffffull;
+    const long long t0 = clock64();
+    unsigned long long w0, w1;
+    for (;;) {
+        w0 = src[0]; w1 = src[1];
+        if ((w0 >> 32) == seq && (w1 >> 32) == seq) break;
+        if (*px.error_dev || clock64() - t0 > px.timeout_cycles) { *px.error = 1; *px.error_dev = 1; break; }
+    }
+    return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
 }
+
 #endif
 
 cudaError_t launch_exchange(const DeviceState &d, const PeerExchange &px, int kind, cudaStream_t s);

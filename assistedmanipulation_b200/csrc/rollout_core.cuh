@@ -65,6 +65,19 @@ template <class R> MPPI_HD R left_barrier(const BarrierP<R> &b, R v) {
     return (v <= b.bound) ? outside : inside;
 }
 
+// cost.hpp:105-167 — UpperLogarithmicBarrierFunction / LowerLogarithmicBarrierFunction. Defined by the reference and used
+// by none of its objectives; provided for objectives built on this engine, checked value for value
+// against the reference's own functors (tests/test_device_math_host.py). log10_ : spatial.cuh.
+template <class R> struct LogBarrierP { R bound, scale, offset, maxc; };
+template <class R> MPPI_HD R upper_log_barrier(const LogBarrierP<R> &b, R v) {
+    if (v >= b.bound) return b.maxc;
+    return std_min(b.scale * (-log10_(-v + b.bound) + b.offset), R(0));
+}
+template <class R> MPPI_HD R lower_log_barrier(const LogBarrierP<R> &b, R v) {
+    if (v <= b.bound) return b.maxc;
+    return std_min(b.scale * (-log10_(v - b.bound) + b.offset), R(0));
+}
+
 // FP32 fast mode, barriers on a STATE variable (joint positions, tank energy). The rollout carries those in FP64 (see
 // rollout_franka): which side of the bound the state is on is decided on the FP64 value against the FP64 bound — the
 // reference's 1e10 steps (cost.hpp:59-61,90-92) are then taken by exactly the rollouts that take them in FP64 unless the

@@ -182,6 +182,8 @@ MPPI_HD double acos_(double a) { return acos(a); }
 MPPI_HD float acos_(float a) { return acosf(a); }
 MPPI_HD double exp_(double a) { return exp(a); }
 MPPI_HD float exp_(float a) { return expf(a); }
+MPPI_HD double log10_(double a) { return log10(a); }
+MPPI_HD float log10_(float a) { return log10f(a); }
 MPPI_HD double fabs_(double a) { return fabs(a); }
 MPPI_HD float fabs_(float a) { return fabsf(a); }
 MPPI_HD double fmin_(double a, double b) { return a < b ? a : b; }   // std::min(a,b): b<a ? b : a

@@ -59,7 +59,9 @@ def all_reduce(dist, array, op):
     return t.numpy()
 
 
-# ---- host model of the peer-memory exchange (csrc/k_misc.cu: k_exchange) ---------------------------------------
+# ---- host model of the peer-memory exchange (csrc/kernels.cuh: exchange_push / exchange_peer, k_misc.cu: k_exchange) ----
+# (The two per-update exchanges carry their flag inside every 8-byte word of the payload — one "flag" per element instead
+# of one per slot; the buffer-reuse argument below is the same: a word is overwritten only by the exchange two updates later.)
 # The device protocol, one step at a time, so that its buffer-reuse argument can be checked under ANY interleaving of the
 # ranks (tests/test_sharded_gloo.py): per (parity, kind) every rank's mailbox holds one slot and one flag per rank; a
 # rank stores its payload into its slot of every peer's mailbox and then raises the flag with the sequence number of

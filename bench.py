@@ -232,8 +232,8 @@ def measure(job, wl, steps, warmup, stage_updates=20, complete_updates=0, clocks
             with torch.cuda.stream(engine_stream):
                 job.flush.fill_(step & 0xff)      # evict L2 between timed iterations
             engine_stream.synchronize()           # keep the flush out of the host-clock (e2e) window too
-        if job.world > 1:
-            job.dist.barrier()                    # ranks enter the step together: the in-step exchanges then measure exchange cost, not host skew
+        if job.world > 1 and not job.args.no_step_barrier:
+            job.dist.barrier()                    # ranks enter the step together: the in-step exchanges then measure exchange cost, not accumulated host skew
         t0 = time.perf_counter()
         rc = e.update(x0, 0.05 * step, wrench, seed=1)   # host state in, host control sequence out
         t1 = time.perf_counter()
@@ -466,6 +466,7 @@ def main():
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--forecast", default="table", choices=["table", "kalman"], help="cfg5: host wrench tables, or the device forecast producer fed measured wrenches")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: the library's own kernels over NVLink peer memory, or NCCL all-reduces")
+    ap.add_argument("--no-step-barrier", action="store_true", help="N > 1: no host barrier before every timed update (the ranks are then coupled by the update's own exchanges only)")
     ap.add_argument("--separate-engines", action="store_true", help="cfg5: one engine per controller instead of one batched engine")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

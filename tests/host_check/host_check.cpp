@@ -5,9 +5,7 @@
 #include <cstring>
 #include <vector>
 #include "model_init.h"
-#ifdef HAVE_ROLLOUT_CORE
 #include "rollout_core.cuh"
-#endif
 
 using namespace mppi_b200;
 
@@ -104,6 +102,31 @@ void host_sincos_poly_f32(int n, const float *a, float *s, float *c) {
 // the integer-pipe sign test of the joint-limit term (spatial.cuh)
 void host_is_negative(int n, const double *x, int *out64, int *out32) {
     for (int i = 0; i < n; i++) { out64[i] = is_negative(x[i]) ? 1 : 0; out32[i] = is_negative((float)x[i]) ? 1 : 0; }
+}
+// cost.hpp functors as the kernels evaluate them (rollout_core.cuh): kind 0 quadratic {a,b,c}, 1 left inverse {bound, scale, max},
+// 2 right inverse, 3 upper log {bound, scale, offset, max}, 4 lower log; f32 = in single precision
+void host_cost_functor(int kind, int f32, double a, double b, double c, double d, const double *values, long count, double *out) {
+    for (long i = 0; i < count; i++) {
+        if (f32) {
+            const float v = (float)values[i];
+            switch (kind) {
+                case 0: out[i] = quadratic(QuadP<float>{(float)a, (float)b, (float)c}, v); break;
+                case 1: out[i] = left_barrier(BarrierP<float>{(float)a, (float)b, (float)c}, v); break;
+                case 2: out[i] = right_barrier(BarrierP<float>{(float)a, (float)b, (float)c}, v); break;
+                case 3: out[i] = upper_log_barrier(LogBarrierP<float>{(float)a, (float)b, (float)c, (float)d}, v); break;
+                default: out[i] = lower_log_barrier(LogBarrierP<float>{(float)a, (float)b, (float)c, (float)d}, v); break;
+            }
+        } else {
+            const double v = values[i];
+            switch (kind) {
+                case 0: out[i] = quadratic(QuadP<double>{a, b, c}, v); break;
+                case 1: out[i] = left_barrier(BarrierP<double>{a, b, c}, v); break;
+                case 2: out[i] = right_barrier(BarrierP<double>{a, b, c}, v); break;
+                case 3: out[i] = upper_log_barrier(LogBarrierP<double>{a, b, c, d}, v); break;
+                default: out[i] = lower_log_barrier(LogBarrierP<double>{a, b, c, d}, v); break;
+            }
+        }
+    }
 }
 int host_fast_structure_matches() { std::string w; return fast_structure_matches(&w) ? 1 : 0; }
 int host_topology_matches() { std::string w; return topology_matches(&w) ? 1 : 0; }

@@ -50,5 +50,19 @@ if rank == 0:
         Uo = o.read(abi.READ_OPTIMAL, nu * T)
         assert np.abs(Us[u] - Uo).max() <= 1e-9 * np.abs(Uo).max()
     print("sharded ok", world, "ranks", exchange)
+if exchange == "p2p":
+    # a peer that does not arrive: the update returns an error after the 2 s time-out instead of hanging the device, and
+    # the engine keeps the last good control sequence
+    import time
+    dist.barrier()
+    if rank == 0:
+        t0 = time.perf_counter()
+        rc = e.update(x0, 0.05 * 4, None, seed=5)
+        waited = time.perf_counter() - t0
+        assert rc == abi.ERR_NCCL and "timed out" in e.error(), (rc, e.error())
+        assert 1.0 < waited < 20.0, waited
+        assert np.array_equal(e.read(abi.READ_OPTIMAL, nu * T), Us[-1])
+        print("missing peer ok after %.1f s" % waited)
+    dist.barrier()   # rank 1 kept its mailbox mapped meanwhile
 e.close()
 dist.destroy_process_group()

@@ -226,3 +226,24 @@ def test_optimal_breakdown_matches_oracle(oracle, hc):
     hc.host_rollouts(objective, 0, C.cast(C.byref(params), C.c_void_p), ol.ptr(x0), ol.ptr(U), ol.ptr(wrench), ol.ptr(np.zeros(12 * T)), 1, T, 0.01, 1.0, ol.ptr(out), ol.ptr(got))
     assert np.allclose(got, bd[:7], rtol=1e-9, atol=1e-9)
     assert abs(out[0] - bd[7]) <= 1e-9 * abs(bd[7])
+
+
+@pytest.mark.parametrize("name", ["quadratic", "left_inverse", "left_inverse_zero_scale", "right_inverse", "right_inverse_small_max", "upper_log", "lower_log"])
+def test_kernel_cost_functors_match_the_reference(hc, name):
+    """The cost.hpp functors as the kernels evaluate them (rollout_core.cuh: barriers as selects, the logarithmic barriers
+    of cost.hpp:105-167) against values produced by the REFERENCE's own functors (tests/golden/ref_objective.npz, generated
+    from cost.hpp compiled unmodified): FP64 to the last bits, FP32 to single precision away from the 1e10 steps."""
+    import objective_probe as op
+    golden = np.load(os.path.join(ol.ROOT, "tests", "golden", "ref_objective.npz"))
+    kind, a, b, c, d = op.FUNCTORS[name]
+    v = op.functor_values(kind, a)
+    want = golden["functor/" + name]
+    hc.host_cost_functor.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _dp, C.c_long, _dp]
+    got = np.zeros_like(v)
+    hc.host_cost_functor(kind, 0, a, b, c, d, ol.ptr(v), len(v), ol.ptr(got))
+    assert np.allclose(got, want, rtol=4e-16, atol=0), np.abs(got - want).max()   # selects instead of branches: the same value in every case (a division may differ in the last bit: scale / x as written)
+    got32 = np.zeros_like(v)
+    hc.host_cost_functor(kind, 1, a, b, c, d, ol.ptr(v), len(v), ol.ptr(got32))
+    # single precision: the bound itself is rounded, so values within 1e-6 of it may sit on the other side of the step
+    away = np.abs(v - a) > 1e-5 * max(abs(a), 1.0)
+    assert np.allclose(got32[away], want[away], rtol=2e-5, atol=1e-6 * np.abs(want[away]).max())

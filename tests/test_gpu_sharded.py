@@ -124,6 +124,8 @@ def test_two_gpus_in_library_exchange(exchange):
     worker = os.path.join(ol.ROOT, "tests", "sharded_worker.py")
     env = dict(os.environ, MPPI_B200_TEST_EXCHANGE=exchange)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                          "--master-port", "29611" if exchange == "nccl" else "29612", worker], capture_output=True, text=True, timeout=150, env=env)
+                          "--master-port", "29611" if exchange == "nccl" else "29612", worker], capture_output=True, text=True, timeout=240, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "sharded ok 2 ranks " + exchange in out.stdout
+    if exchange == "p2p":
+        assert "missing peer ok" in out.stdout
