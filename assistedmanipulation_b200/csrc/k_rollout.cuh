@@ -241,6 +241,14 @@ __global__ void __launch_bounds__(64, 1) k_rollout_split(const __grid_constant__
         R taunle[NJ];
 #pragma unroll
         for (int i = 0; i < NJ; i++) taunle[i] = R(0);
+        // PinocchioDynamics::set_state -> calculate(): the kinematics the first stage cost reads, from the initial state (kept
+        // out of the step loop: ~1600 instructions the loop would otherwise jump over every step)
+        {
+            R q0[NJ], qd0[NJ];
+#pragma unroll
+            for (int i = 0; i < NJ; i++) { q0[i] = (R)sx64[i]; qd0[i] = (R)sx64[NJ + i]; }
+            robot_kinematics<R, KF>(M, q0, qd0, K);
+        }
         for (int step = 0; step < T; ++step) {
             const int s = step % SPLIT_DEPTH;
             split_sync(1 + s);                                            // the state warp has filled this slot
@@ -264,7 +272,6 @@ __global__ void __launch_bounds__(64, 1) k_rollout_split(const __grid_constant__
                 energy64 = std_max(0.0, energy64 + p * dt64);
                 energy = (R)energy64;
             }
-            if (step == 0) robot_kinematics<R, KF>(M, q, qd, K);          // PinocchioDynamics::set_state -> calculate()
             const R yaw[2] = {cs[2], sn[2]};
             R cst;
             if constexpr (VAR == VAR_TP_FULL) cst = track_point_cost<R>(P, q, K, yaw, q64);
@@ -277,7 +284,11 @@ __global__ void __launch_bounds__(64, 1) k_rollout_split(const __grid_constant__
             qd[0] = cs[2] * u[0] - sn[2] * u[1];
             qd[1] = sn[2] * u[0] + cs[2] * u[1];
             qd[2] = u[2];
+#if MPPI_ROLLED
+            robot_calculate_rolled<R, POWER, KF>(M, q, qd, nle, K, cs, sn);
+#else
             robot_calculate<R, false, POWER, KF, false, true>(M, q, qd, tau, qdd, nle, K, cs, sn);
+#endif
 #pragma unroll
             for (int i = 0; i < NJ; i++) taunle[i] = tau[i] + nle[i];
         }

@@ -16,6 +16,15 @@
 #ifndef MPPI_MIXED_STATE
 #define MPPI_MIXED_STATE 2
 #endif
+// 1 = the kernels that evaluate kinematics + RNEA every step run those passes, the collision pairs and the joint barriers
+// as loops (robot.cuh robot_calculate_rolled) — a third of the code for kernels bound by instruction fetch. MEASURED AND
+// REJECTED (B200, config 3): rollout stage 988 us unrolled, 2245 us rolled (one warp 2018; loop-body FP64 solver on top
+// 2229): the per-joint results move from registers to thread-local arrays (3.2 KB frames x 224 threads per SM do not
+// fit L1) and each loop iteration is one dependent chain the scheduler cannot interleave with its neighbours. Kept, off,
+// with its host test (identical values), as the record of that measurement.
+#ifndef MPPI_ROLLED
+#define MPPI_ROLLED 0
+#endif
 #ifndef MPPI_MIXED_SOLVER_UNROLL
 #define MPPI_MIXED_SOLVER_UNROLL 7
 #endif
@@ -125,6 +134,20 @@ template <class R> struct AssistedP {
 // and the twenty square roots / reciprocals ran one after the other (~48 cycles each in the static model, a sixth of the
 // assisted-manipulation step); as one block the scheduler overlaps them. Same operations, same order of additions.
 template <class R, bool FLIP> MPPI_HD R self_collision_cost(const BarrierP<R> &lim, const R *radii, int link_mode, const Kinematics<R> &K) {
+#if MPPI_ROLLED
+    // one loop body for the twenty pairs (same operations, same order of additions; see MPPI_ROLLED)
+    R total = R(0);
+#pragma unroll 1
+    for (int i = 0; i < 20; i++) {
+        R dist = R(0);
+        if (link_mode != 0) {
+            const Vec3<R> d = K.link_com[MPPI_PAIR_A(i)] - K.link_com[MPPI_PAIR_B(i)];
+            dist = sqrt_(dot(d, d));
+        }
+        total += left_barrier(lim, FLIP ? radii[i] - dist : dist - radii[i]);
+    }
+    return total;
+#endif
     R distance[20];
     if (link_mode != 0) {
 #pragma unroll
@@ -235,10 +258,18 @@ template <class R> MPPI_HD R assisted_cost(const AssistedP<R> &P, const R *q, co
     if (P.joint_limit) {
         R c = R(0);
         if (sizeof(R) == 4 && q64) {
+#if MPPI_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
             for (int i = 0; i < NJ; i++) c += barrier_signed(P.lower[i], P.lower64[i] - q64[i]) + barrier_signed(P.upper[i], q64[i] - P.upper64[i]);
         } else {
+#if MPPI_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
             for (int i = 0; i < NJ; i++) c += left_barrier(P.lower[i], q[i]) + right_barrier(P.upper[i], q[i]);
         }
         if (bd) bd[0] += (double)c;
@@ -454,7 +485,13 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
             qd[2] = u[2];
             // (carrying the end effector point inside the INERTIA loop was tried: +4 registers, spills, 4 % slower)
             // (LEAN: the end effector point rides the solver's forward loop as a second, independent dependency chain)
-            if constexpr (!LEAN) robot_calculate<R, false, POWER, KF, false, true>(M, q, qd, tau, qdd, nle, K, cs, sn);   // the joint sines / cosines are shared
+            if constexpr (!LEAN) {   // the joint sines / cosines are shared
+#if MPPI_ROLLED
+                robot_calculate_rolled<R, POWER, KF>(M, q, qd, nle, K, cs, sn);
+#else
+                robot_calculate<R, false, POWER, KF, false, true>(M, q, qd, tau, qdd, nle, K, cs, sn);
+#endif
+            }
             if (in.lockstep > 2) lockstep_barrier();
             // the objectives with kinematics (assisted manipulation, full reach-to-pose) always run the unrolled solver: with
             // the placements' structural zeros it executes 940 instructions per step fewer than the loop body (FP32 assisted

@@ -48,7 +48,29 @@ static void calc_plane(const double *q, const double *qd, const double *u, doubl
     ee3[0] = ee.x; ee3[1] = ee.y; ee3[2] = ee.z;
 }
 
+// the ROLLED passes (arm joints as one loop body) must reproduce the unrolled structure-crossing passes
+template <class R>
+static void calc_rolled(const double *q, const double *qd, double *nle, double *kin) {
+    static const RobotModel<R> M = make_robot_model<R>();
+    static const FastModel<R> F = make_fast_model<R>();
+    R q_[12], qd_[12], nle_[12], cs[12], sn[12];
+    for (int i = 0; i < 12; i++) { q_[i] = (R)q[i]; qd_[i] = (R)qd[i]; nle_[i] = 0; cs[i] = 1; sn[i] = 0; }
+    joint_sincos<R>(F, q_, cs, sn);
+    Kinematics<R> K;
+    robot_calculate_rolled<R, true, KIN_MOUNT | KIN_VEL | KIN_MANIP | KIN_LINKS>(M, q_, qd_, nle_, K, cs, sn);
+    for (int i = 0; i < 12; i++) nle[i] = nle_[i];
+    double *k = kin;
+    *k++ = K.ee_pos.x; *k++ = K.ee_pos.y; *k++ = K.ee_pos.z;
+    *k++ = K.mount_pos.x; *k++ = K.mount_pos.y; *k++ = K.mount_pos.z;
+    *k++ = K.ee_lin_vel.x; *k++ = K.ee_lin_vel.y; *k++ = K.ee_lin_vel.z;
+    *k++ = K.manip_det;
+    for (int l = 0; l < 8; l++) { *k++ = K.link_com[l].x; *k++ = K.link_com[l].y; *k++ = K.link_com[l].z; }
+}
+
 extern "C" {
+void host_robot_calculate_rolled(int f32, const double *q, const double *qd, double *nle, double *kin34) {
+    if (f32) calc_rolled<float>(q, qd, nle, kin34); else calc_rolled<double>(q, qd, nle, kin34);
+}
 void host_robot_calculate_plane(int f32, const double *q, const double *qd, const double *u, double *qdd, double *nle, double *kin34, double *ee3) {
     if (f32) calc_plane<float>(q, qd, u, qdd, nle, kin34, ee3); else calc_plane<double>(q, qd, u, qdd, nle, kin34, ee3);
 }

@@ -247,3 +247,23 @@ def test_kernel_cost_functors_match_the_reference(hc, name):
     # single precision: the bound itself is rounded, so values within 1e-6 of it may sit on the other side of the step
     away = np.abs(v - a) > 1e-5 * max(abs(a), 1.0)
     assert np.allclose(got32[away], want[away], rtol=2e-5, atol=1e-6 * np.abs(want[away]).max())
+
+
+@pytest.mark.parametrize("f32", [0, 1])
+def test_rolled_passes_reproduce_the_unrolled_ones(hc, f32):
+    """robot.cuh robot_calculate_rolled (kinematics + RNEA with the seven arm joints as ONE loop body: a third of the code,
+    for the kernels bound by instruction fetch) against the unrolled structure-crossing passes: the loop multiplies through
+    the structural zeros the unrolled build drops, nothing else differs — identical values."""
+    rng = np.random.default_rng(23)
+    hc.host_robot_calculate_rolled.argtypes = [C.c_int, _dp, _dp, _dp, _dp]
+    hc.host_robot_calculate_plane.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+    for _ in range(200):
+        q = abi.huddled_state()[:12] + rng.normal(0, 0.7, 12)
+        qd = rng.normal(0, 1.5, 12)
+        u = rng.normal(0, 3.0, 12)
+        nle_r, kin_r = np.zeros(12), np.zeros(34)
+        qdd, nle_u, kin_u, ee = np.zeros(12), np.zeros(12), np.zeros(34), np.zeros(3)
+        hc.host_robot_calculate_rolled(f32, ol.ptr(q), ol.ptr(qd), ol.ptr(nle_r), ol.ptr(kin_r))
+        hc.host_robot_calculate_plane(f32, ol.ptr(q), ol.ptr(qd), ol.ptr(u), ol.ptr(qdd), ol.ptr(nle_u), ol.ptr(kin_u), ol.ptr(ee))
+        assert np.array_equal(nle_r, nle_u), np.abs(nle_r - nle_u).max()
+        assert np.array_equal(kin_r, kin_u), np.abs(kin_r - kin_u).max()
