@@ -339,14 +339,21 @@ __global__ void __launch_bounds__(256) k_weights(const __grid_constant__ DeviceS
         const unsigned long long attempt = d.frame->attempt;
         // (the exchange description is read from the kernel's parameter bank, `dg`: indexing its arrays through the
         // controller view's copy would park the whole state in local memory; exchange_peer polls until the element is there)
-        mm0 = d.minmax_local[0]; mm1 = d.minmax_local[1];
         double valid = 0.0;
-        for (int q = 0; q < d.world; q++) {
-            if (dg.has_px && q != d.rank) {
-                mm0 = fmax(mm0, exchange_peer(dg.px, EX_MINMAX, attempt, q, 0));
-                mm1 = fmax(mm1, exchange_peer(dg.px, EX_MINMAX, attempt, q, 1));
-                valid += exchange_peer(dg.px, EX_MINMAX, attempt, q, 3 + q);
-            } else valid += d.minmax_local[3 + q];
+        if (dg.has_px) {
+            // one thread per (rank, element) polls its word pair; a thread walking all peers one after the other paid an L2
+            // round trip per peer (measured at 8 ranks: +6 us here, +25 us in k_finish)
+            __shared__ double s_peer[3][MPPI_MAX_WORLD];
+            if (threadIdx.x < 3 * d.world) {
+                const int q = threadIdx.x / 3, e = threadIdx.x - 3 * q;
+                s_peer[e][q] = (q == d.rank) ? d.minmax_local[e] : exchange_peer(dg.px, EX_MINMAX, attempt, q, e);   // element 2 = that rank's own valid count
+            }
+            __syncthreads();
+            mm0 = -CUDART_INF; mm1 = -CUDART_INF;
+            for (int q = 0; q < d.world; q++) { mm0 = fmax(mm0, s_peer[0][q]); mm1 = fmax(mm1, s_peer[1][q]); valid += s_peer[2][q]; }
+        } else {
+            mm0 = d.minmax_local[0]; mm1 = d.minmax_local[1];
+            for (int q = 0; q < d.world; q++) valid += d.minmax_local[3 + q];
         }
         mm2 = valid >= 2.0 ? 2.0 : valid;   // saturate AFTER the sum: two ranks with one valid rollout each are two valid rollouts (mppi.cpp:368-370)
         if (blockIdx.x == 0 && threadIdx.x == 0) { d.minmax[0] = mm0; d.minmax[1] = mm1; d.minmax[2] = mm2; }
@@ -548,29 +555,19 @@ __device__ __forceinline__ bool sg_recurrence_dispatch(int nr, const double *F, 
     }
 }
 
-// element e of the exchanged {sum w, sum w*eps, argmin slots}: combined here in rank order from the peers' slots in the
-// local mailbox (peer-memory exchange; identical bits on every rank), or already all-reduced in place (NCCL, split ABI)
-// (px: the exchange description in the kernel's parameter bank; null = no peer exchange)
-__device__ __forceinline__ double combined_sum(const DeviceState &d, const PeerExchange *px, int e) {
-    if (d.world == 1 || !px) return d.sums[e];
-    const unsigned long long attempt = d.frame->attempt;
-    double acc = 0.0;
-    for (int q = 0; q < d.world; q++) acc += (q == d.rank) ? d.sums[e] : exchange_peer(*px, EX_SUMS, attempt, q, e);
-    return acc;
-}
-
-__device__ __forceinline__ void finish_publish_stats(const DeviceState &d, const PeerExchange *px, int n) {
+// staged: the block's shared-memory copy {sum w (combined), argmin slots} when the peer exchange is attached (k_finish)
+__device__ __forceinline__ void finish_publish_stats(const DeviceState &d, const PeerExchange *px, int n, const double *s_total = nullptr, const double *s_arg = nullptr) {
     d.result[n + 0] = d.minmax[0]; d.result[n + 1] = d.minmax[1]; d.result[n + 2] = d.minmax[2];
     long long best = *d.argmin;
     if (d.world > 1) {   // lowest global index among the ranks that hold the global minimum (mppi.cpp:363-366 order)
         best = 0x7fffffffffffffffll;
-        for (int r = 0; r < d.world; r++) { const double v = combined_sum(d, px, 1 + n + r); if (v > 0.0 && (long long)v - 1 < best) best = (long long)v - 1; }
+        for (int r = 0; r < d.world; r++) { const double v = (px && s_arg) ? s_arg[r] : d.sums[1 + n + r]; if (v > 0.0 && (long long)v - 1 < best) best = (long long)v - 1; }
     }
     d.result[n + 3] = __longlong_as_double(best);
-    d.result[n + 4] = combined_sum(d, px, 0);
+    d.result[n + 4] = (px && s_total) ? *s_total : d.sums[0];
 }
 
-__global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DeviceState dg) {
+__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ DeviceState dg) {
     const DeviceState d = controller_view(dg, blockIdx.y);
     // One BLOCK per control channel (channels are independent, mppi.cpp:424-447): the elementwise work runs over the
     // channel's T entries, the window recurrence on warp 0 with its own scheduler.
@@ -582,20 +579,46 @@ __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DeviceSt
     const int n = d.nu * d.T, ch = blockIdx.x;
     const int skip = *d.skip;
     const PeerExchange *px = (d.world > 1 && dg.has_px) ? &dg.px : nullptr;   // in the parameter bank (see k_weights)
-    const double total = combined_sum(d, px, 0);   // (peer exchange: polls until the peers' {sum w, ...} have arrived)
-    if (px) __syncthreads();                       // ... so that a peer that never arrived is known to every thread below
+    // Peer exchange: the block's threads poll the peers' words of THIS channel's T elements and of {sum w} in parallel — one
+    // (rank, element) per thread and pass — and leave the rank-ordered sums in shared memory.
+    double *s_comb = sw + 2 * d.sg_window + 1 + d.T;   // T + 1 combined values: [0] = sum w, [1 + t] = channel element t
+    double *s_arg = s_comb + d.T + 1;                   // world argmin slots: slot r is filled by rank r alone (the others add 0)
+    if (px) {
+        const unsigned long long attempt = d.frame->attempt;
+        const int per_rank = d.T + 1, items = per_rank * (d.world - 1);
+        double *s_raw = s_arg + d.world;                // (world - 1) x (T + 1) peers' values
+        for (int i = threadIdx.x; i < items + d.world; i += blockDim.x) {
+            if (i >= items) {                           // rank r's own argmin slot (one poll per rank; the publishing thread walking all world x world slots cost 18 us at 8 ranks)
+                const int r = i - items;
+                s_arg[r] = (r == d.rank) ? d.sums[1 + n + r] : exchange_peer(*px, EX_SUMS, attempt, r, 1 + n + r);
+                continue;
+            }
+            const int slot = i / per_rank, j = i - slot * per_rank;
+            const int q = slot < d.rank ? slot : slot + 1;
+            s_raw[i] = exchange_peer(*px, EX_SUMS, attempt, q, j == 0 ? 0 : 1 + (j - 1) * d.nu + ch);
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < per_rank; j += blockDim.x) {
+            const double own = d.sums[j == 0 ? 0 : 1 + (j - 1) * d.nu + ch];
+            double acc = 0.0;
+            for (int q = 0; q < d.world; q++) acc += (q == d.rank) ? own : s_raw[(q < d.rank ? q : q - 1) * per_rank + j];   // rank order: identical bits on every rank
+            s_comb[j] = acc;
+        }
+        __syncthreads();                               // ... and a peer that never arrived is known to every thread below
+    }
+    const double total = px ? s_comb[0] : d.sums[0];
     // "all nan rollouts" (mppi.cpp:368-370): the reference throws before publishing. A peer that never arrived (exchange
     // time-out) is handled the same way: the engine keeps its last good control sequence, the host reports the error.
     const bool dead = !(d.minmax[2] >= 2.0) || (px && *px->error_dev);
     if (dead) {   // nothing is published but the statistics
-        if (ch == 0 && threadIdx.x == 0) finish_publish_stats(d, px, n);
+        if (ch == 0 && threadIdx.x == 0) finish_publish_stats(d, px, n, s_comb, s_arg);
         return;
     }
     for (int t = threadIdx.x; t < d.T; t += blockDim.x) {
         const int e = t * d.nu + ch;
         double v = d.U_shift[e];
         if (!skip) {
-            const double g = combined_sum(d, px, 1 + e) / total;   // weights are normalised by the total (mppi.cpp:403-408)
+            const double g = (px ? s_comb[1 + t] : d.sums[1 + e]) / total;   // weights are normalised by the total (mppi.cpp:403-408)
             d.gradient[e] = g;
             v += g * d.gradient_step;
         }
@@ -716,7 +739,7 @@ __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ DeviceSt
         double2 *dst = reinterpret_cast<double2 *>(d.result);
         for (int i = threadIdx.x; i < n / 2; i += blockDim.x) dst[i] = __ldcg(src + i);
         if ((n & 1) && threadIdx.x == 0) d.result[n - 1] = __ldcg(d.U + n - 1);
-        if (threadIdx.x == 0) { finish_publish_stats(d, px, n); *d.finish_count = 0; }
+        if (threadIdx.x == 0) { finish_publish_stats(d, px, n, s_comb, s_arg); *d.finish_count = 0; }
     }
 }
 
@@ -908,12 +931,13 @@ cudaError_t launch_gradient(const DeviceState &d, int precision, cudaStream_t s,
 }
 
 cudaError_t launch_finish(const DeviceState &d, cudaStream_t s) {
-    const size_t smem = sizeof(double) * (2 * (size_t)d.T + 2 * (size_t)d.sg_len + 2 * (size_t)d.sg_window + 1);
+    size_t smem = sizeof(double) * (2 * (size_t)d.T + 2 * (size_t)d.sg_len + 2 * (size_t)d.sg_window + 1);
+    if (d.world > 1 && d.has_px) smem += sizeof(double) * (((size_t)d.T + 1) * (size_t)d.world + (size_t)d.world);   // combined + argmin slots + the peers' values of one channel
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_finish<<<dim3(d.nu, d.batch), 64, smem, s>>>(d);
+    k_finish<<<dim3(d.nu, d.batch), (d.world > 1 && d.has_px) ? 256 : 64, smem, s>>>(d);
     return cudaGetLastError();
 }
 

@@ -41,7 +41,7 @@ __device__ __forceinline__ void rollout_grid_epilogue(const DeviceState &d, cons
             const int nvalid = atomicAdd(d.valid_count, 0);
             d.minmax_local[0] = nvalid > 0 ? -decode_ordered(atomicMin(&d.minmax_enc[0], ~0ull)) : -CUDART_INF;
             d.minmax_local[1] = nvalid > 0 ? decode_ordered(atomicMax(&d.minmax_enc[1], 0ull)) : -CUDART_INF;
-            d.minmax_local[2] = 0.0;
+            d.minmax_local[2] = nvalid >= 2 ? 2.0 : (double)nvalid;   // this rank's own count again: what the peer-memory exchange gathers (one element per rank)
             for (int r = 0; r < d.world; r++) d.minmax_local[3 + r] = (r == d.rank) ? (nvalid >= 2 ? 2.0 : (double)nvalid) : 0.0;
             *d.rollout_done = 0;
             __threadfence();

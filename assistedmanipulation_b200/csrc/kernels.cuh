@@ -75,7 +75,7 @@ struct DeviceState {
     long long *argmin;     // global index of the best rollout
     int *finish_count;     // channel blocks of k_finish that are done (the last one publishes)
     double *minmax;        // {-min, max, valid(<=2)} of the WHOLE rollout set (written by k_weights; read by k_finish and the host)
-    double *minmax_local;  // exchange buffer of a sharded set: {-min, max, 0, valid_0 .. valid_{world-1}} with only this rank's valid slot
+    double *minmax_local;  // exchange buffer of a sharded set: {-min, max, own valid count, valid_0 .. valid_{world-1}} with only this rank's valid slot
                            // filled (<= 2) — combined with MAX elementwise, which gathers the slots; their sum is the valid count
     double *sums;          // exchange buffer {sum w, sum w*eps [nu*T], argmin slot per rank}: this rank's part (p2p) / all-reduced in place (NCCL, split ABI)
     int has_px;            // the peer-memory exchange is attached

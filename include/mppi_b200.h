@@ -200,7 +200,7 @@ int mppi_b200_update_begin(mppi_b200_engine *engine, const double *state, double
                            const void *noise, int32_t noise_source, uint64_t seed);
 int mppi_b200_update_weights(mppi_b200_engine *engine);
 int mppi_b200_update_finish(mppi_b200_engine *engine);
-/* device addresses of the two exchange buffers (FP64). minmax = {-min, max, 0, and when sharded one slot per rank: that
+/* device addresses of the two exchange buffers (FP64). minmax = {-min, max, this rank's valid count, and when sharded one slot per rank: that
  * rank's count of valid (non-NaN) rollouts, saturated at 2, others 0} — all-reduce all `minmax_count` values with MAX (the
  * slots are disjoint, so MAX gathers them; the engine sums them: two ranks with one valid rollout each are two valid
  * rollouts, mppi.cpp:368-370). sums = {sum w, sum w*eps[nu*T], and when sharded one slot per rank: that rank's best global
