@@ -67,7 +67,7 @@ __device__ __forceinline__ void rollout_grid_epilogue(const DeviceState &d, cons
 #define MPPI_LEAN_MIN_BLOCKS 1
 #endif
 template <class R, int VAR, bool FAITHFUL, class ParamsT, bool BIG = false>
-__global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG) ? MPPI_LEAN_MIN_BLOCKS : 1) k_rollout(const __grid_constant__ DeviceState d, const __grid_constant__ ParamsT P, int optimal_only, int lockstep) {
+__global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG) ? MPPI_LEAN_MIN_BLOCKS : 1) k_rollout(const __grid_constant__ DeviceState d, const __grid_constant__ ParamsT P, int optimal_only) {
     // blockIdx.y = controller of a batched engine. Only the handful of buffers this kernel touches are offset
     // by hand (a full controller_view copy of the state costs ~40 registers here, i.e. a resident warp per SM).
     const size_t c = blockIdx.y;
@@ -93,13 +93,10 @@ __global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG)
     for (int i = threadIdx.x; i < d.T; i += blockDim.x) sDisc[i] = discount_pow(d.discount, i);
     __syncthreads();
 
-    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double cost = 0.0;
     const bool active = optimal_only ? (k == 0) : (k < d.k_count);
-    // lockstep blocks meet at barriers inside the step loop: the threads past the end of the rollout set run the last
-    // rollout once more (and write nothing) instead of leaving
-    if (lockstep && !optimal_only && !active) k = d.k_count - 1;
-    if (active || (lockstep && !optimal_only)) {
+    if (active) {
         // the optimal re-rollout (Trajectory::filter, mppi.cpp:450-479) reads a row of zeros shared by all controllers
         const R *eps = static_cast<const R *>(d.noise) + (optimal_only ? (size_t)0 : (c * (size_t)d.k_count + (size_t)k) * n);
         if constexpr (VAR == VAR_TOY) {
@@ -107,7 +104,6 @@ __global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG)
         } else {
             RolloutInputs<R> in;
             in.x0 = sx; in.x0_64 = sx64; in.U = sU; in.W = has_w ? sW : nullptr; in.T = d.T; in.dt = (R)d.dt; in.dt64 = d.dt; in.discount = d.discount; in.discount_table = sDisc;
-            in.lockstep = optimal_only ? 0 : lockstep;
             if constexpr (STATE_PATH64) in.U64 = sU64;
             double bd[7] = {0, 0, 0, 0, 0, 0, 0};
             cost = rollout_franka<R, VAR, FAITHFUL, ParamsT, BIG>(MPPI_DEVICE_MODEL, MPPI_DEVICE_FAST_MODEL, P, in, eps, optimal_only ? bd : nullptr, MPPI_DEVICE_FAST_MODEL64);
@@ -326,13 +322,11 @@ cudaError_t launch_rollout_t(const DeviceState &d, const void *params, bool opti
     if (optimal_only) block = 32;
     size_t smem = sizeof(R) * ((size_t)d.nu * d.T + 6 * (size_t)d.T + 32) + sizeof(double) * ((size_t)d.T + 32);
     if (sizeof(R) == 4 && MPPI_MIXED_STATE >= 2 && !FAITHFUL && (VAR == VAR_TP_FULL || VAR == VAR_AM || VAR == VAR_AM_ENERGY)) smem += sizeof(double) * (size_t)d.nu * d.T;
-    int lockstep = 0;
     if constexpr (VAR == VAR_AM || VAR == VAR_AM_ENERGY || VAR == VAR_TP_FULL) {
-        // experiment switches (A/B runs): block size and barriers per step of the kernels with the large step body
+        // A/B switch: block size of the one-warp kernels with the large step body. (Barriers inside their step loop were
+        // measured too: the warps of an SM run this straight-line code in lockstep anyway — identical times to 0.1 us.)
         static const int env_block = std::getenv("MPPI_B200_AM_BLOCK") ? std::atoi(std::getenv("MPPI_B200_AM_BLOCK")) : 0;
-        static const int env_lockstep = std::getenv("MPPI_B200_LOCKSTEP") ? std::atoi(std::getenv("MPPI_B200_LOCKSTEP")) : 0;
         if (!optimal_only && env_block > 0) { block = env_block; grid = (d.k_count + block - 1) / block; }
-        lockstep = env_lockstep;
     }
 #if defined(MPPI_ROLLOUT_F32)
     if constexpr (sizeof(R) == 4 && MPPI_MIXED_STATE >= 2 && !FAITHFUL && (VAR == VAR_TP_FULL || VAR == VAR_AM || VAR == VAR_AM_ENERGY)) {
@@ -364,7 +358,7 @@ cudaError_t launch_rollout_t(const DeviceState &d, const void *params, bool opti
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<dim3((unsigned)grid, d.batch), block, smem, s>>>(d, P, optimal_only ? 1 : 0, lockstep);
+    kern<<<dim3((unsigned)grid, d.batch), block, smem, s>>>(d, P, optimal_only ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -357,14 +357,6 @@ MPPI_HD void load_eps(const float *p, float *o) {
 #endif
 }
 
-// Kernels whose step is far larger than the instruction cache (assisted manipulation: 75 KB of straight-line code per
-// step) keep the warps of a block at the same place in that code, so a line fetched for one warp serves them all.
-MPPI_HD void lockstep_barrier() {
-#if defined(__CUDA_ARCH__)
-    __syncthreads();
-#endif
-}
-
 MPPI_HD double discount_pow(double g, int step) { return g == 1.0 ? 1.0 : pow(g, (double)step); }
 
 // Everything one rollout of the Franka+Ridgeback system needs that does not depend on the sample.
@@ -377,7 +369,6 @@ template <class R> struct RolloutInputs {
     int T;
     R dt;
     double dt64 = 0.0;   // the time step unrounded (FP32 fast mode: its FP64 state integrates with this one)
-    int lockstep = 0;    // > 0: the warps of a block meet at a barrier this many times per step (see k_rollout.cuh)
     double discount;
     const double *discount_table = nullptr;   // pow(discount, step) per step, staged by the kernel (keeps pow() out of the step loop)
 };
@@ -438,7 +429,6 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
     R e_next[NJ];
     load_eps(eps, e_next);
     for (int step = 0; step < in.T; ++step) {
-        if (in.lockstep > 0) lockstep_barrier();
         R u[NJ];
         double u64[MIXED_SOLVER ? NJ : 1];
         if constexpr (MIXED_SOLVER) {
@@ -461,7 +451,6 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
         // step, behind which the scheduler cannot move the (independent) dynamics of the same step.
         total += sc;
         if (step + 1 == in.T) break;  // the state after the last step is never costed (mppi.cpp:316-341)
-        if (in.lockstep > 1) lockstep_barrier();
         // PinocchioDynamics::step, pinocchio_dynamics.cpp:226-260
         R tau[NJ], qdd[NJ], nle[NJ];
 #pragma unroll
@@ -492,7 +481,6 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
                 robot_calculate<R, false, POWER, KF, false, true>(M, q, qd, tau, qdd, nle, K, cs, sn);
 #endif
             }
-            if (in.lockstep > 2) lockstep_barrier();
             // the objectives with kinematics (assisted manipulation, full reach-to-pose) always run the unrolled solver: with
             // the placements' structural zeros it executes 940 instructions per step fewer than the loop body (FP32 assisted
             // manipulation 5646 -> 4705, static model 6773 -> 5476 cycles), keeps its per-joint results in registers instead of

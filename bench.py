@@ -296,7 +296,9 @@ def rooflines(wl, m, peaks, counters):
     noise_bytes = m["k_local"] * m["T"] * m["nu"] * esz
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     out = {"roofline": {"kernel": "k_rollout", "bound": "fp64_pipe" if wl["precision"] == abi.FP64 else "fp32_pipe", "achieved": achieved, "peak": m["fma_peak"],
-                        "unit": "TFLOP/s", "frac": achieved / m["fma_peak"], "traffic": cnt.get("rollout_dram_bytes_per_launch"),
+                        "unit": "TFLOP/s", "frac": achieved / m["fma_peak"],
+                        # DRAM bytes of one launch of this size: the captured bytes per rollout-step x this launch's rollout-steps
+                        "traffic": (cnt["rollout_dram_bytes_per_rollout_step"] * m["k_local"] * m["T"]) if "rollout_dram_bytes_per_rollout_step" in cnt else None,
                         "peak_source": "FMA-chain microbenchmark run in this process (mppi_b200_measure_fma_peak); MEASURED_PEAKS.json has no vector FP peak",
                         "algorithmic_flops_per_rollout_step": algorithmic, "executed_flops_per_rollout_step": executed,
                         "executed_frac": (executed * m["k_local"] * m["T"] / rollout_s / 1e12 / m["fma_peak"]) if executed else None,

@@ -60,6 +60,7 @@ def summarise(key, path):
         if "k_rollout" in name and "executed_flops_per_rollout_step" not in out:
             out["executed_flops_per_rollout_step"] = flops / UNITS[key]
             out["rollout_dram_bytes_per_launch"] = rec["dram_bytes"]
+            out["rollout_dram_bytes_per_rollout_step"] = rec["dram_bytes"] / UNITS[key]
             out["rollout_kernel"] = name
             out["rollout_duration_us_under_ncu"] = rec["duration_us"]
     return out

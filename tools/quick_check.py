@@ -1,6 +1,6 @@
 """One short GPU call: smoke() (parity against the oracle) and device timings of the rollout kernels (torch-free).
   python tools/quick_check.py [--no-smoke] [--only cfg2,big,cfg3,cfg2f32,cfg5] [--flips]
-Kernel switches are environment variables read by the library (MPPI_B200_LIB, MPPI_B200_AM_BLOCK, MPPI_B200_LOCKSTEP, ...)."""
+Kernel switches are environment variables read by the library (MPPI_B200_LIB, MPPI_B200_AM_BLOCK, MPPI_B200_SPLIT, ...)."""
 import sys, time, numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 t0 = time.time()
