@@ -11,6 +11,16 @@
 
 namespace mppi_b200 {
 
+int rollout_overlap_level(long long blocks) {
+    static const int sms = [] { int n = 148, dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+    return blocks >= 2ll * sms ? 1 : 2;
+}
+int pdl_level() {
+    static const int level = std::getenv("MPPI_B200_PDL") ? std::atoi(std::getenv("MPPI_B200_PDL")) : 1;
+    return level;
+}
+
+
 cudaError_t upload_robot_model_f64();
 cudaError_t upload_robot_model_f32();
 cudaError_t upload_robot_model() {
@@ -105,6 +115,7 @@ __device__ __forceinline__ void select_smallest(long long count, long long keep,
 // mppi.cpp:222-253 on this rank's rollouts. With one rank the picks ARE the kept set; with several the picks
 // are this rank's candidates, all-gathered and merged by k_merge_kept.
 __global__ void k_select_kept(const __grid_constant__ DeviceState dg) {
+    pdl_wait();
     const DeviceState d = controller_view(dg, blockIdx.y);
     for (long long k = threadIdx.x; k < d.k_count; k += blockDim.x) d.kept[k] = 0;
     __syncthreads();
@@ -126,6 +137,7 @@ __global__ void k_select_kept(const __grid_constant__ DeviceState dg) {
 
 // every rank merges the same world x keep candidate list into the global kept set
 __global__ void k_merge_kept(const __grid_constant__ DeviceState dg) {
+    pdl_wait();
     const DeviceState d = controller_view(dg, blockIdx.y);
     const long long keep = d.keep_best < d.K_total - 2 ? d.keep_best : d.K_total - 2;
     select_smallest(
@@ -176,6 +188,7 @@ template <class R, class RI, int NU> __device__ __forceinline__ void fresh_colum
 }
 
 template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sample(const __grid_constant__ DeviceState dg) {
+    pdl_wait();
     const DeviceState d = controller_view(dg, blockIdx.y);
     // A block produces 256 consecutive columns = one contiguous span of 256*nu values: every thread
     // builds its column in shared memory, then the block streams the span out with 16-byte stores.
@@ -229,6 +242,7 @@ template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sa
 // Box–Muller chain per thread, 32-bit index arithmetic, and kept rollouts are skipped instead of rewritten.
 // Same counters and the same arithmetic as k_sample: the noise is bit-identical.
 template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sample_quads(const __grid_constant__ DeviceState dg) {
+    pdl_wait();
     const DeviceState d = controller_view(dg, blockIdx.y);
     if (blockIdx.x == gridDim.x - 1) { prepare_block(d); return; }
     const long long quads = d.k_count * d.T * (NU / 4);
@@ -254,6 +268,7 @@ template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sa
 // MUFU and FP32 buffers are scaled in FP32. A thread stores its NU values as consecutive 16-byte vectors; a warp covers
 // 32 consecutive columns = one contiguous span. Same counters as every other sampling path: bit-identical noise.
 template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sample_columns(const __grid_constant__ DeviceState dg) {
+    pdl_wait();
     const DeviceState d = controller_view(dg, blockIdx.y);
     if (blockIdx.x == gridDim.x - 1) { prepare_block(d); return; }
     const long long cols = d.k_count * d.T;
@@ -292,6 +307,7 @@ template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sa
 
 // kept rollouts: one block per kept rollout (mppi.cpp:243-252); nothing happens when shift_by <= 0
 template <class R, class RI, int NU> __global__ void k_shift_kept(const __grid_constant__ DeviceState dg) {
+    pdl_wait();
     const DeviceState d = controller_view(dg, blockIdx.y);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *row = reinterpret_cast<R *>(smem_raw);
@@ -322,6 +338,7 @@ template <class R, class RI, int NU> __global__ void k_shift_kept(const __grid_c
 // ---- K3 ---------------------------------------------------------------------------------------------
 // w_k = exp(-cost_scale (c_k - min) / (max - min)), NaN -> 0 (mppi.cpp:381-397); block partial sums
 __global__ void __launch_bounds__(256) k_weights(const __grid_constant__ DeviceState dg) {
+    pdl_wait();
     const DeviceState d = controller_view(dg, blockIdx.y);
     __shared__ double s_part[8];
     double mm0, mm1, mm2;
@@ -402,6 +419,7 @@ __device__ __forceinline__ void fma_vec(double *acc, double w, const float4 &v) 
 // 256 threads and reached 2.3 TB/s where the FP64 one reaches 5.7); the groups' sums meet in shared memory in group order.
 // G is a template parameter: G = 1 is the plain kernel, whose row loop the compiler unrolls on its own (128 registers).
 template <class R, int G> __global__ void __launch_bounds__(512) k_gradient(const __grid_constant__ DeviceState dg) {
+    pdl_wait();
     const DeviceState d = controller_view(dg, blockIdx.y);
     typedef typename Vec16<R>::type V;
     constexpr int VN = Vec16<R>::n;
@@ -418,6 +436,19 @@ template <class R, int G> __global__ void __launch_bounds__(512) k_gradient(cons
 #pragma unroll
         for (int i = 0; i < VN; i++) acc[i] = 0.0;
         long long k = first;
+        // FP32 rows: 8 rows in flight per thread (a 16-byte load carries half as many rows' worth of latency-hiding bytes per
+        // element as in FP64, and the register budget allows it: one 384-thread block per SM either way)
+        if (sizeof(R) == 4) {
+            for (; k + 7 * stride < d.k_count; k += 8 * stride) {
+                V v[8]; double w[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = __ldg(noise + (size_t)(k + j * stride) * nvec + e);
+#pragma unroll
+                for (int j = 0; j < 8; j++) w[j] = d.weights[k + j * stride];
+#pragma unroll
+                for (int j = 0; j < 8; j++) fma_vec(acc, w[j], v[j]);
+            }
+        }
         // 4 rows in flight per thread
         for (; k + 3 * stride < d.k_count; k += 4 * stride) {
             const V v0 = __ldg(noise + (size_t)k * nvec + e);
@@ -450,6 +481,7 @@ template <class R, int G> __global__ void __launch_bounds__(512) k_gradient(cons
 // Block = 32 elements x 32 slices of the partial rows (every thread has at most a few loads, all in
 // flight at once); slice sums are combined in slice order.
 __global__ void __launch_bounds__(1024) k_gradient_reduce(const __grid_constant__ DeviceState dg) {
+    pdl_wait();
     const DeviceState d = controller_view(dg, blockIdx.y);
     __shared__ double part[32][33];
     // A skipped update (max - min < 1e-6 or fewer than two valid rollouts, mppi.cpp:368-375) leaves weights and gradient
@@ -568,6 +600,7 @@ __device__ __forceinline__ void finish_publish_stats(const DeviceState &d, const
 }
 
 __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ DeviceState dg) {
+    pdl_wait();
     const DeviceState d = controller_view(dg, blockIdx.y);
     // One BLOCK per control channel (channels are independent, mppi.cpp:424-447): the elementwise work runs over the
     // channel's T entries, the window recurrence on warp 0 with its own scheduler.
@@ -791,12 +824,10 @@ cudaError_t measure_fma_peak(int precision, double *tflops) {
 
 // ---- launchers -----------------------------------------------------------------------------------------
 cudaError_t launch_select_kept(const DeviceState &d, cudaStream_t s) {
-    k_select_kept<<<dim3(1, d.batch), 1024, 0, s>>>(d);
-    return cudaGetLastError();
+    return launch_chain(k_select_kept, dim3(1, d.batch), dim3(1024), 0, s, d);
 }
 cudaError_t launch_merge_kept(const DeviceState &d, cudaStream_t s) {
-    k_merge_kept<<<1, 256, 0, s>>>(d);
-    return cudaGetLastError();
+    return launch_chain(k_merge_kept, dim3(1), dim3(256), 0, s, d);
 }
 
 template <class R, class RI, int NU> static cudaError_t sample_tt(const DeviceState &d, cudaStream_t s, int *launches) {
@@ -806,7 +837,7 @@ template <class R, class RI, int NU> static cudaError_t sample_tt(const DeviceSt
             cudaError_t e = cudaFuncSetAttribute(k_shift_kept<R, RI, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row);
             if (e != cudaSuccess) return e;
         }
-        k_shift_kept<R, RI, NU><<<dim3((unsigned)d.keep_best, d.batch), 64, row, s>>>(d);
+        { cudaError_t e = launch_chain(k_shift_kept<R, RI, NU>, dim3((unsigned)d.keep_best, d.batch), dim3(64), row, s, d); if (e != cudaSuccess) return e; }
         ++*launches;
     }
     const long long ncols = d.k_count * d.T;
@@ -815,22 +846,19 @@ template <class R, class RI, int NU> static cudaError_t sample_tt(const DeviceSt
         static const int sample_switch = std::getenv("MPPI_B200_SAMPLE_TILE") ? std::atoi(std::getenv("MPPI_B200_SAMPLE_TILE")) : 0;
         const bool tile_only = sample_switch == 1;
         if (d.L_is_diagonal && sample_switch == 0) {
-            k_sample_columns<R, RI, NU><<<dim3((unsigned)((ncols + 255) / 256) + 1, d.batch), 256, 0, s>>>(d);   // + the prepare block
             ++*launches;
-            return cudaGetLastError();
+            return launch_chain(k_sample_columns<R, RI, NU>, dim3((unsigned)((ncols + 255) / 256) + 1, d.batch), dim3(256), 0, s, d);   // + the prepare block
         }
         if (d.L_is_diagonal && !tile_only) {
             const long long quads = ncols * (NU / 4);
-            k_sample_quads<R, RI, NU><<<dim3((unsigned)((quads + 255) / 256) + 1, d.batch), 256, 0, s>>>(d);   // + the prepare block
             ++*launches;
-            return cudaGetLastError();
+            return launch_chain(k_sample_quads<R, RI, NU>, dim3((unsigned)((quads + 255) / 256) + 1, d.batch), dim3(256), 0, s, d);   // + the prepare block
         }
     }
     const unsigned grid = (unsigned)((ncols + 255) / 256);
     const size_t tile = sizeof(R) * 256 * (size_t)NU;
-    k_sample<R, RI, NU><<<dim3(grid + 1, d.batch), 256, tile, s>>>(d);   // + the prepare block
     ++*launches;
-    return cudaGetLastError();
+    return launch_chain(k_sample<R, RI, NU>, dim3(grid + 1, d.batch), dim3(256), tile, s, d);   // + the prepare block
 }
 template <class R> static cudaError_t sample_t(const DeviceState &d, cudaStream_t s, int *launches) {
     if (d.nu == 12) return d.injected_is_double ? sample_tt<R, double, 12>(d, s, launches) : sample_tt<R, R, 12>(d, s, launches);
@@ -850,6 +878,7 @@ cudaError_t launch_rollout(const DeviceState &d, int precision, int variant, boo
 // Block rank: wait for every peer's flag in the local mailbox, combine the slots in rank order into the exchange buffer
 // (MAX for {-min, max, valid}, SUM for {sum w, sum w*eps, argmin slots}; the warm-start candidates are concatenated).
 __global__ void __launch_bounds__(256) k_exchange(const __grid_constant__ DeviceState d, const __grid_constant__ PeerExchange px, int kind) {
+    pdl_wait();
     const int count = px.count[kind];
     const unsigned long long update = d.frame->attempt;
     const int parity = (int)(update & 1ull);
@@ -904,13 +933,11 @@ __global__ void __launch_bounds__(256) k_exchange(const __grid_constant__ Device
 }
 
 cudaError_t launch_exchange(const DeviceState &d, const PeerExchange &px, int kind, cudaStream_t s) {
-    k_exchange<<<px.world, 256, 0, s>>>(d, px, kind);
-    return cudaGetLastError();
+    return launch_chain(k_exchange, dim3(px.world), dim3(256), 0, s, d, px, kind);
 }
 
 cudaError_t launch_weights(const DeviceState &d, cudaStream_t s) {
-    k_weights<<<dim3(d.weight_blocks, d.batch), 256, 0, s>>>(d);
-    return cudaGetLastError();
+    return launch_chain(k_weights, dim3(d.weight_blocks, d.batch), dim3(256), 0, s, d);
 }
 
 cudaError_t launch_gradient(const DeviceState &d, int precision, cudaStream_t s, int *launches) {
@@ -920,14 +947,13 @@ cudaError_t launch_gradient(const DeviceState &d, int precision, cudaStream_t s,
     if (nvec <= 256 && d.k_count >= 4096) { groups = 512 / nvec >= 4 ? 4 : 2; threads = ((groups * nvec + 31) / 32) * 32; }   // short rows: several rows per block pass
     const size_t smem = groups > 1 ? sizeof(double) * (size_t)(groups - 1) * n : 0;
     const dim3 grid(d.grad_blocks, d.batch);
-    if (precision == 0) {
-        if (groups == 1) k_gradient<double, 1><<<grid, threads, smem, s>>>(d); else if (groups == 2) k_gradient<double, 2><<<grid, threads, smem, s>>>(d); else k_gradient<double, 4><<<grid, threads, smem, s>>>(d);
-    } else {
-        if (groups == 1) k_gradient<float, 1><<<grid, threads, smem, s>>>(d); else if (groups == 2) k_gradient<float, 2><<<grid, threads, smem, s>>>(d); else k_gradient<float, 4><<<grid, threads, smem, s>>>(d);
-    }
-    k_gradient_reduce<<<dim3((n + 31) / 32, d.batch), 1024, 0, s>>>(d);
+    void (*kern)(DeviceState) = nullptr;
+    if (precision == 0) kern = groups == 1 ? k_gradient<double, 1> : (groups == 2 ? k_gradient<double, 2> : k_gradient<double, 4>);
+    else kern = groups == 1 ? k_gradient<float, 1> : (groups == 2 ? k_gradient<float, 2> : k_gradient<float, 4>);
+    cudaError_t e = launch_chain(kern, grid, dim3(threads), smem, s, d);
+    if (e != cudaSuccess) return e;
     *launches += 2;
-    return cudaGetLastError();
+    return launch_chain(k_gradient_reduce, dim3((n + 31) / 32, d.batch), dim3(1024), 0, s, d);
 }
 
 cudaError_t launch_finish(const DeviceState &d, cudaStream_t s) {
@@ -937,8 +963,7 @@ cudaError_t launch_finish(const DeviceState &d, cudaStream_t s) {
         cudaError_t e = cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_finish<<<dim3(d.nu, d.batch), (d.world > 1 && d.has_px) ? 256 : 64, smem, s>>>(d);
-    return cudaGetLastError();
+    return launch_chain(k_finish, dim3(d.nu, d.batch), dim3((d.world > 1 && d.has_px) ? 256 : 64), smem, s, d);
 }
 
 }  // namespace mppi_b200

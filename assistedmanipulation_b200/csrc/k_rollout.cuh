@@ -68,6 +68,7 @@ __device__ __forceinline__ void rollout_grid_epilogue(const DeviceState &d, cons
 #endif
 template <class R, int VAR, bool FAITHFUL, class ParamsT, bool BIG = false>
 __global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG) ? MPPI_LEAN_MIN_BLOCKS : 1) k_rollout(const __grid_constant__ DeviceState d, const __grid_constant__ ParamsT P, int optimal_only) {
+    pdl_wait();
     // blockIdx.y = controller of a batched engine. Only the handful of buffers this kernel touches are offset
     // by hand (a full controller_view copy of the state costs ~40 registers here, i.e. a resident warp per SM).
     const size_t c = blockIdx.y;
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__(64, 1) k_rollout_split(const __grid_constant__
     typedef float R;
     constexpr int KF = VariantTraits<VAR>::kin;
     constexpr bool POWER = VariantTraits<VAR>::power;
+    pdl_wait();
     const size_t c = blockIdx.y;
     const size_t n = (size_t)d.nu * d.T;
     const Frame *frame = reinterpret_cast<const Frame *>(reinterpret_cast<const double *>(d.frame) + c * d.frame_doubles);
@@ -344,8 +346,7 @@ cudaError_t launch_rollout_t(const DeviceState &d, const void *params, bool opti
                 cudaError_t e = cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
                 if (e != cudaSuccess) return e;
             }
-            skern<<<dim3((unsigned)((d.k_count + 31) / 32), d.batch), 64, ssmem, s>>>(d, P);
-            return cudaGetLastError();
+            return launch_level(rollout_overlap_level(split_blocks), skern, dim3((unsigned)((d.k_count + 31) / 32), d.batch), dim3(64), ssmem, s, d, P);
         }
     }
 #endif
@@ -358,8 +359,7 @@ cudaError_t launch_rollout_t(const DeviceState &d, const void *params, bool opti
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<dim3((unsigned)grid, d.batch), block, smem, s>>>(d, P, optimal_only ? 1 : 0);
-    return cudaGetLastError();
+    return launch_level(rollout_overlap_level((long long)grid * d.batch), kern, dim3((unsigned)grid, d.batch), dim3(block), smem, s, d, P, optimal_only ? 1 : 0);
 }
 
 template <class R> cudaError_t launch_rollout_r(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s) {

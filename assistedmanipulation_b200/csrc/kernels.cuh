@@ -206,6 +206,44 @@ __device__ __forceinline__ double exchange_peer(const PeerExchange &px, int kind
 
 cudaError_t launch_exchange(const DeviceState &d, const PeerExchange &px, int kind, cudaStream_t s);
 
+// ---- programmatic dependent launch (sm_90+) ------------------------------------------------------------------------
+// The kernels of an update form a chain. Launched with the programmatic-serialisation attribute, a kernel's blocks may be
+// brought onto the SMs while its predecessor is still running; they wait in pdl_wait() — the first statement of every
+// kernel — until the predecessor has COMPLETED and its writes are visible, so nothing about the data flow changes. A
+// kernel launched without the attribute passes pdl_wait() at once.
+// Measured (profiles/r2_pdl_ab.log): between the small kernels the attribute changes nothing inside a CUDA graph (199 us
+// either way at config 2) - all of the gain is the rollout grid moving in under the tail of the sampling kernel
+// (config 3: 1090 -> 1077 us, config 5: 872 -> 852). But blocks placed while the sampling grid still holds part of every
+// SM land two or three to an SM with other SMs left empty, and for a rollout grid smaller than the machine (config 2:
+// 129 blocks on 148 SMs) that costs 57 % of the kernel (291 us per update instead of 199), because its step body streams
+// from L2 through one instruction-fetch path per SM. So the rollout gets the attribute only when its grid is at least
+// two blocks per SM (rollout_overlap_level); MPPI_B200_PDL=2 forces it, =0 turns every attribute off.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__)
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();   // this grid's successor may start moving in
+#endif
+}
+int pdl_level();   // MPPI_B200_PDL: 0 off, 1 (default) as described above, 2 every kernel
+int rollout_overlap_level(long long blocks);   // the level from which a rollout grid of this many blocks gets the attribute
+template <class... KArgs, class... Args>
+inline cudaError_t launch_level(int level, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_level() >= level ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    return launch_level(1, kern, grid, block, smem, s, static_cast<Args &&>(args)...);
+}
+
+#endif
+
 cudaError_t upload_robot_model();  // once per device
 
 cudaError_t launch_select_kept(const DeviceState &d, cudaStream_t s);
