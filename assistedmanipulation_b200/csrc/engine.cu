@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -123,6 +124,7 @@ struct mppi_b200_engine {
     std::string error;
     std::mutex publish_mutex;            // guards h_U + last_rollout_time: mppi_b200_get may run on another thread during an update (mppi.cpp:178-182,492)
     float last_ms = 0.f;
+    bool timing_pending = false;       // last_ms is read from the events on demand (last_device_ms)
     bool profiling = false;
     std::vector<double> weights_total;   // per controller
     std::vector<char> weights_valid;
@@ -448,12 +450,37 @@ int run_optimal(mppi_b200_engine *e) {
     return MPPI_B200_OK;
 }
 
+// The update is over for the caller when k_finish's block of results has landed in host memory: its last word carries the
+// update's number (finish_publish_stats). Polling that word instead of cudaEventSynchronize(ev_end) takes the kernel's
+// retirement, the event's signal and the driver's wake-up out of the caller's latency. The event is still queried now and
+// then: a device fault ends the wait with its error instead of a hang (the kernels' own waits time out after 2 s).
+int wait_published(mppi_b200_engine *e) {
+    const size_t n = (size_t)e->d.nu * e->d.T;
+    const double expect = (double)e->attempts;   // host_prepare stamped the frames with attempts - 1
+    for (unsigned long long spins = 1;; spins++) {
+        bool all = true;
+        for (int c = 0; c < e->batch && all; c++) all = *reinterpret_cast<volatile double *>(e->h_result + (size_t)c * (n + 8) + n + 7) == expect;
+        if (all) break;
+        if ((spins & 255) == 0) {
+            const cudaError_t q = cudaEventQuery(e->ev_end);
+            if (q == cudaSuccess) break;   // everything the stream was given has run
+            if (q != cudaErrorNotReady) return fail(e, MPPI_B200_ERR_CUDA, std::string("update: ") + cudaGetErrorString(q));
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return MPPI_B200_OK;
+}
+
 // wait for the results, then the reference's end-of-update bookkeeping (mppi.cpp:178-186)
 int host_complete(mppi_b200_engine *e) {
     DeviceState &d = e->d;
     const size_t n = (size_t)d.nu * d.T;
-    CUDA_TRY(e, cudaEventSynchronize(e->ev_end));
-    cudaEventElapsedTime(&e->last_ms, e->ev_start, e->ev_end);
+    if (e->profiling) CUDA_TRY(e, cudaEventSynchronize(e->ev_end));
+    else if (int rc = wait_published(e)) return rc;
+    e->timing_pending = true;
     if (e->profiling) {
         for (int i = 0; i < MPPI_B200_STAGES; i++) { float ms = 0.f; cudaEventElapsedTime(&ms, e->ev_stage[i], e->ev_stage[i + 1]); e->stage_s[i] = ms * 1e-3; }
     }
@@ -820,6 +847,10 @@ int mppi_b200_measure_fma_peak(int32_t device, int32_t precision, double *tflops
 
 int mppi_b200_last_update_device_seconds(mppi_b200_engine *e, double *seconds) {
     if (!e || !seconds) return MPPI_B200_ERR_INVALID;
+    if (e->timing_pending) {
+        if (cudaEventSynchronize(e->ev_end) == cudaSuccess) cudaEventElapsedTime(&e->last_ms, e->ev_start, e->ev_end);
+        e->timing_pending = false;
+    }
     *seconds = (double)e->last_ms * 1e-3;
     return MPPI_B200_OK;
 }

@@ -267,7 +267,10 @@ template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sa
 // are shared by the column's three blocks, the Philox products are 32 x 32 -> 64 multiplies, the square root is one
 // MUFU and FP32 buffers are scaled in FP32. A thread stores its NU values as consecutive 16-byte vectors; a warp covers
 // 32 consecutive columns = one contiguous span. Same counters as every other sampling path: bit-identical noise.
-template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sample_columns(const __grid_constant__ DeviceState dg) {
+#ifndef MPPI_SAMPLE_MIN_BLOCKS
+#define MPPI_SAMPLE_MIN_BLOCKS 1
+#endif
+template <class R, class RI, int NU> __global__ void __launch_bounds__(256, MPPI_SAMPLE_MIN_BLOCKS) k_sample_columns(const __grid_constant__ DeviceState dg) {
     pdl_wait();
     const DeviceState d = controller_view(dg, blockIdx.y);
     if (blockIdx.x == gridDim.x - 1) { prepare_block(d); return; }
@@ -597,6 +600,11 @@ __device__ __forceinline__ void finish_publish_stats(const DeviceState &d, const
     }
     d.result[n + 3] = __longlong_as_double(best);
     d.result[n + 4] = (px && s_total) ? *s_total : d.sums[0];
+    // Last word of the host-mapped block: the number of this update. The host polls it instead of waiting for the
+    // stream's end-of-update event (engine.cu: wait_published) — the block is complete when the word arrives (the fence
+    // orders every earlier store of this block's threads, which met at a barrier, ahead of it; PCIe keeps posted writes in order).
+    __threadfence_system();
+    *reinterpret_cast<volatile double *>(d.result + n + 7) = (double)(d.frame->attempt + 1ull);
 }
 
 __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ DeviceState dg) {

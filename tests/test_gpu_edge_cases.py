@@ -172,3 +172,28 @@ def test_get_from_another_thread_during_updates():
     # the reader is held up by the publication copy only, not by an update (the median update here takes ~0.5 ms)
     waits = np.array([s[3] for s in samples])
     assert np.median(waits) < 0.2 * np.median(update_s)
+
+
+def test_host_buffers_refilled_in_place_and_strided_views():
+    """The Python host side keeps the ctypes pointer of a state / wrench array for as long as the caller passes the same
+    object (engine.py: _host_pointer). A buffer refilled in place must be read afresh by every update, and arrays that need
+    a conversion (strided views, Fortran order) are converted on every call."""
+    import engine_lib as el
+    import cases
+    K, T, nu = 256, 16, 12
+    params, W = cases.assisted_params(True, abi.LINKS_BODY_COM), cases.constant_wrench(T)
+    h = abi.make_config(abi.SYSTEM_FRANKA_RIDGEBACK, abi.OBJECTIVE_ASSISTED_MANIPULATION, K, 0.16, dynamics_mode=abi.DYNAMICS_FUSED)
+    a, b = el.Engine(h, params), el.Engine(h, params)
+    state, wrench = abi.huddled_state(10.0), W.copy()                       # reused by `a`
+    columns = np.zeros((state.size, 2))
+    for u in range(4):
+        state[3] = 0.1 * u; wrench[:, 0] = 1.0 + u                           # refilled in place
+        assert a.update(state, 0.05 * u, wrench, seed=9) == 0, a.error()
+        if u % 2:                                                            # the same values through arrays that need a copy
+            columns[:, 0] = state
+            assert b.update(columns[:, 0], 0.05 * u, np.asfortranarray(wrench), seed=9) == 0, b.error()
+        else:
+            assert b.update(state.copy(), 0.05 * u, wrench.copy(), seed=9) == 0, b.error()
+        assert np.array_equal(a.read(abi.READ_OPTIMAL, nu * T), b.read(abi.READ_OPTIMAL, nu * T)), u
+        assert np.array_equal(a.read(abi.READ_COSTS, K + 2), b.read(abi.READ_COSTS, K + 2)), u
+    a.close(); b.close()
