@@ -308,7 +308,14 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     // few rollouts: fewer partial rows for the second stage; many: two blocks per SM
     d.grad_blocks = (int)std::min<long long>(std::max<long long>(d.k_count / 32, 1), 2LL * sms);
-    A(d.wsum_partial, (size_t)d.weight_blocks); A(d.grad_partial, (size_t)d.grad_blocks * n);
+    d.wsum_stride = std::max(d.weight_blocks, d.grad_blocks);
+    // One rank and a small rollout set (at most ~5000 rollouts: no more partial rows than k_finish's twelve blocks combine in
+    // a microsecond): weights inside the weighted-sum kernel, its partial rows combined by k_finish. Measured, graph replay:
+    // config 2 200.6 -> 198.5 us, config 5 877 -> 865 us; with 296 partial rows (K = 16 384) k_finish lost what the two
+    // kernels had cost (+12 us), hence the bound. MPPI_B200_FUSED_TAIL=0 / =2: never / whenever the weights fit shared memory.
+    static const int fuse_tail = std::getenv("MPPI_B200_FUSED_TAIL") ? std::atoi(std::getenv("MPPI_B200_FUSED_TAIL")) : 1;
+    d.fused_tail = (fuse_tail > 0 && c->world_size == 1 && (fuse_tail > 1 || d.grad_blocks <= 160) && (d.k_count + d.grad_blocks - 1) / d.grad_blocks + 4 <= MPPI_FUSED_ROWS) ? 1 : 0;
+    A(d.wsum_partial, (size_t)d.wsum_stride); A(d.grad_partial, (size_t)d.grad_blocks * n);
     A(d.gradient, n); A(d.skip, 1); A1(d.L, (size_t)nu * nu); A(d.optimal_cost, 1); A(d.breakdown, 8);
     d.noise = dev_alloc<unsigned char>(e, e->noise_elems * esz); ok = ok && d.noise;
     d.injected = nullptr; d.injected_is_double = 0;
@@ -408,8 +415,8 @@ int enqueue_begin(mppi_b200_engine *e, const void *noise, int32_t noise_source) 
 }
 
 int enqueue_weights(mppi_b200_engine *e) {
-    int launches = 1;
-    CUDA_TRY(e, launch_weights(e->d, e->stream));
+    int launches = e->d.fused_tail ? 0 : 1;
+    if (!e->d.fused_tail) CUDA_TRY(e, launch_weights(e->d, e->stream));   // (fused tail: inside the weighted-sum kernel)
     STAGE(e, 5);
     CUDA_TRY(e, launch_gradient(e->d, e->cfg.precision, e->stream, &launches));
     e->launches += launches;

@@ -421,50 +421,96 @@ __device__ __forceinline__ void fma_vec(double *acc, double w, const float4 &v) 
 // threads split into G groups that walk different rows, so every thread has loads in flight (the FP32 kernel ran 192 of
 // 256 threads and reached 2.3 TB/s where the FP64 one reaches 5.7); the groups' sums meet in shared memory in group order.
 // G is a template parameter: G = 1 is the plain kernel, whose row loop the compiler unrolls on its own (128 registers).
-template <class R, int G> __global__ void __launch_bounds__(512) k_gradient(const __grid_constant__ DeviceState dg) {
+// FUSED (one rank, at most MPPI_FUSED_ROWS rollouts per block): the block first computes the weights of ITS rollouts — what
+// k_weights does for all of them (mppi.cpp:381-397), including the decode of the running min / max, the skip decision and
+// the argmin — keeps them in shared memory, and leaves its partial sum of the weights in wsum_partial[block]; its row of
+// partial sums is written channel-major ([nu][T]) for k_finish, which combines the rows itself. Two kernels (k_weights,
+// k_gradient_reduce) and their launch gaps less per update: ~6 us of a 200 us update at K = 4096.
+template <class R, int G, bool FUSED> __global__ void __launch_bounds__(512) k_gradient(const __grid_constant__ DeviceState dg) {
     pdl_wait();
     const DeviceState d = controller_view(dg, blockIdx.y);
     typedef typename Vec16<R>::type V;
     constexpr int VN = Vec16<R>::n;
     extern __shared__ __align__(16) double s_group[];   // (G - 1) x n partial sums
-    if (*d.skip) return;
+    __shared__ double s_w[FUSED ? MPPI_FUSED_ROWS : 1];
+    const long long stride = (long long)gridDim.x * G;
+    if constexpr (FUSED) {
+        __shared__ double s_part[16];
+        const int nvalid = *d.valid_count;
+        const double mm0 = nvalid > 0 ? -decode_ordered(d.minmax_enc[0]) : -CUDART_INF;
+        const double mm1 = nvalid > 0 ? decode_ordered(d.minmax_enc[1]) : -CUDART_INF;
+        const double mm2 = nvalid >= 2 ? 2.0 : (double)nvalid;
+        const double minimum = -mm0, difference = mm1 - minimum;
+        const bool bad = !(mm2 >= 2.0) || !(difference >= 1e-6);  // all-NaN / early return (mppi.cpp:368-375)
+        if (blockIdx.x == 0 && threadIdx.x == 0) { d.minmax[0] = mm0; d.minmax[1] = mm1; d.minmax[2] = mm2; if (bad) *d.skip = 1; }
+        // local row li = j * G + g  <->  rollout (blockIdx.x * G + g) + j * stride  (group g walks j = 0, 1, ...)
+        double w_sum = 0.0;
+        for (int li = threadIdx.x; li < MPPI_FUSED_ROWS; li += blockDim.x) {
+            const long long k = (long long)blockIdx.x * G + (li % G) + (long long)(li / G) * stride;
+            double w = 0.0;
+            if (k < d.k_count) {
+                const double c = d.costs[k];
+                if (c == minimum) atomicMin(d.argmin, k + d.k_begin);
+                if (!bad) { w = (c != c) ? 0.0 : exp(-d.cost_scale * (c - minimum) / difference); d.weights[k] = w; }
+            }
+            s_w[li] = w;
+            w_sum += w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w_sum += __shfl_xor_sync(0xffffffffu, w_sum, o);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = w_sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int i = 0; i < (int)((blockDim.x + 31) >> 5); i++) t += s_part[i];   // fixed order
+            d.wsum_partial[blockIdx.x] = t;
+        }
+        if (bad) return;
+    } else {
+        if (*d.skip) return;
+    }
     const int n = d.nu * d.T;
     const int nvec = n / VN;  // host guarantees divisibility
     const V *noise = static_cast<const V *>(d.noise);
     const int g = G > 1 ? (int)threadIdx.x / nvec : 0;
     const int lanes = G > 1 ? nvec : (int)blockDim.x;          // threads that walk a row together
-    const long long first = (long long)blockIdx.x * G + g, stride = (long long)gridDim.x * G;
+    const long long first = (long long)blockIdx.x * G + g;
+    // weight of this thread's j-th row (rollout first + j * stride)
+    auto weight_of = [&](long long k, int j) -> double { if constexpr (FUSED) return s_w[j * G + g]; else return d.weights[k]; };
+    // where element i of the row goes in the block's row of partial sums
+    auto slot_of = [&](int i) -> size_t { if constexpr (FUSED) { const int t = i / d.nu; return (size_t)(i - t * d.nu) * d.T + t; } else return (size_t)i; };
     for (int e = G > 1 ? (int)threadIdx.x - g * nvec : (int)threadIdx.x; e < nvec && g < G; e += lanes) {
         double acc[VN];
 #pragma unroll
         for (int i = 0; i < VN; i++) acc[i] = 0.0;
         long long k = first;
+        int j = 0;
         // FP32 rows: 8 rows in flight per thread (a 16-byte load carries half as many rows' worth of latency-hiding bytes per
         // element as in FP64, and the register budget allows it: one 384-thread block per SM either way)
         if (sizeof(R) == 4) {
-            for (; k + 7 * stride < d.k_count; k += 8 * stride) {
+            for (; k + 7 * stride < d.k_count; k += 8 * stride, j += 8) {
                 V v[8]; double w[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) v[j] = __ldg(noise + (size_t)(k + j * stride) * nvec + e);
+                for (int q = 0; q < 8; q++) v[q] = __ldg(noise + (size_t)(k + q * stride) * nvec + e);
 #pragma unroll
-                for (int j = 0; j < 8; j++) w[j] = d.weights[k + j * stride];
+                for (int q = 0; q < 8; q++) w[q] = weight_of(k + q * stride, j + q);
 #pragma unroll
-                for (int j = 0; j < 8; j++) fma_vec(acc, w[j], v[j]);
+                for (int q = 0; q < 8; q++) fma_vec(acc, w[q], v[q]);
             }
         }
         // 4 rows in flight per thread
-        for (; k + 3 * stride < d.k_count; k += 4 * stride) {
+        for (; k + 3 * stride < d.k_count; k += 4 * stride, j += 4) {
             const V v0 = __ldg(noise + (size_t)k * nvec + e);
             const V v1 = __ldg(noise + (size_t)(k + stride) * nvec + e);
             const V v2 = __ldg(noise + (size_t)(k + 2 * stride) * nvec + e);
             const V v3 = __ldg(noise + (size_t)(k + 3 * stride) * nvec + e);
-            const double w0 = d.weights[k], w1 = d.weights[k + stride], w2 = d.weights[k + 2 * stride], w3 = d.weights[k + 3 * stride];
+            const double w0 = weight_of(k, j), w1 = weight_of(k + stride, j + 1), w2 = weight_of(k + 2 * stride, j + 2), w3 = weight_of(k + 3 * stride, j + 3);
             fma_vec(acc, w0, v0); fma_vec(acc, w1, v1); fma_vec(acc, w2, v2); fma_vec(acc, w3, v3);
         }
-        for (; k < d.k_count; k += stride) fma_vec(acc, d.weights[k], __ldg(noise + (size_t)k * nvec + e));
+        for (; k < d.k_count; k += stride, j++) fma_vec(acc, weight_of(k, j), __ldg(noise + (size_t)k * nvec + e));
         if (G == 1 || g == 0) {
 #pragma unroll
-            for (int i = 0; i < VN; i++) d.grad_partial[(size_t)blockIdx.x * n + e * VN + i] = acc[i];
+            for (int i = 0; i < VN; i++) d.grad_partial[(size_t)blockIdx.x * n + (G == 1 ? slot_of(e * VN + i) : (size_t)(e * VN + i))] = acc[i];
         } else {
 #pragma unroll
             for (int i = 0; i < VN; i++) s_group[(size_t)(g - 1) * n + e * VN + i] = acc[i];
@@ -475,7 +521,12 @@ template <class R, int G> __global__ void __launch_bounds__(512) k_gradient(cons
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             double sum = d.grad_partial[(size_t)blockIdx.x * n + i];
             for (int q = 1; q < G; q++) sum += s_group[(size_t)(q - 1) * n + i];
-            d.grad_partial[(size_t)blockIdx.x * n + i] = sum;
+            if constexpr (!FUSED) d.grad_partial[(size_t)blockIdx.x * n + i] = sum;
+            else s_group[(size_t)(G - 1) * n + i] = sum;   // (fused: the row is rewritten channel-major below, through a staging row)
+        }
+        if constexpr (FUSED) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += blockDim.x) d.grad_partial[(size_t)blockIdx.x * n + slot_of(i)] = s_group[(size_t)(G - 1) * n + i];
         }
     }
 }
@@ -596,10 +647,10 @@ __device__ __forceinline__ void finish_publish_stats(const DeviceState &d, const
     long long best = *d.argmin;
     if (d.world > 1) {   // lowest global index among the ranks that hold the global minimum (mppi.cpp:363-366 order)
         best = 0x7fffffffffffffffll;
-        for (int r = 0; r < d.world; r++) { const double v = (px && s_arg) ? s_arg[r] : d.sums[1 + n + r]; if (v > 0.0 && (long long)v - 1 < best) best = (long long)v - 1; }
+        for (int r = 0; r < d.world; r++) { const double v = px ? s_arg[r] : d.sums[1 + n + r]; if (v > 0.0 && (long long)v - 1 < best) best = (long long)v - 1; }
     }
     d.result[n + 3] = __longlong_as_double(best);
-    d.result[n + 4] = (px && s_total) ? *s_total : d.sums[0];
+    d.result[n + 4] = s_total ? *s_total : d.sums[0];
     // Last word of the host-mapped block: the number of this update. The host polls it instead of waiting for the
     // stream's end-of-update event (engine.cu: wait_published) — the block is complete when the word arrives (the fence
     // orders every earlier store of this block's threads, which met at a barrier, ahead of it; PCIe keeps posted writes in order).
@@ -647,19 +698,57 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ DeviceSt
         }
         __syncthreads();                               // ... and a peer that never arrived is known to every thread below
     }
-    const double total = px ? s_comb[0] : d.sums[0];
+    // Fused tail (one rank): this block combines its channel's T elements over the rows of partial sums the weighted-sum
+    // kernel left channel-major — coalesced 8 T-byte reads, `slices` rows in flight per element, fixed order — and the blocks'
+    // partial sums of the weights; k_gradient_reduce is not launched.
+    const bool fused = d.fused_tail != 0;
+    if (fused) {
+        double *s_red = s_comb + d.T + 1;
+        const int slices = min(8, max(1, (int)blockDim.x / d.T)), rows = d.grad_blocks;
+        for (int i = threadIdx.x; i < slices * d.T; i += blockDim.x) {
+            const int sl = i / d.T, t = i - sl * d.T;
+            const double *src = d.grad_partial + (size_t)ch * d.T + t;
+            double a[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) a[q] = 0.0;
+            int b = sl;
+            for (; b + 7 * slices < rows; b += 8 * slices) {   // eight rows in flight per thread
+#pragma unroll
+                for (int q = 0; q < 8; q++) a[q] += src[(size_t)(b + q * slices) * n];
+            }
+            for (; b < rows; b += slices) a[0] += src[(size_t)b * n];
+            s_red[i] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+        }
+        if (threadIdx.x >= blockDim.x - 32) {   // the last warp: sum of the weights, warp-strided partial sums and a fixed-order shuffle tree
+            const int lane = threadIdx.x & 31;
+            double w = 0.0;
+            for (int b = lane; b < rows; b += 32) w += d.wsum_partial[b];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+            if (lane == 0) s_comb[0] = w;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < d.T; t += blockDim.x) {
+            double a = s_red[t];
+            for (int sl = 1; sl < slices; sl++) a += s_red[sl * d.T + t];
+            s_comb[1 + t] = a;
+        }
+        __syncthreads();
+    }
+    const bool staged = px || fused;
+    const double total = staged ? s_comb[0] : d.sums[0];
     // "all nan rollouts" (mppi.cpp:368-370): the reference throws before publishing. A peer that never arrived (exchange
     // time-out) is handled the same way: the engine keeps its last good control sequence, the host reports the error.
     const bool dead = !(d.minmax[2] >= 2.0) || (px && *px->error_dev);
     if (dead) {   // nothing is published but the statistics
-        if (ch == 0 && threadIdx.x == 0) finish_publish_stats(d, px, n, s_comb, s_arg);
+        if (ch == 0 && threadIdx.x == 0) finish_publish_stats(d, px, n, staged ? s_comb : nullptr, s_arg);
         return;
     }
     for (int t = threadIdx.x; t < d.T; t += blockDim.x) {
         const int e = t * d.nu + ch;
         double v = d.U_shift[e];
         if (!skip) {
-            const double g = (px ? s_comb[1 + t] : d.sums[1 + e]) / total;   // weights are normalised by the total (mppi.cpp:403-408)
+            const double g = (staged ? s_comb[1 + t] : d.sums[1 + e]) / total;   // weights are normalised by the total (mppi.cpp:403-408)
             d.gradient[e] = g;
             v += g * d.gradient_step;
         }
@@ -780,7 +869,7 @@ __global__ void __launch_bounds__(256) k_finish(const __grid_constant__ DeviceSt
         double2 *dst = reinterpret_cast<double2 *>(d.result);
         for (int i = threadIdx.x; i < n / 2; i += blockDim.x) dst[i] = __ldcg(src + i);
         if ((n & 1) && threadIdx.x == 0) d.result[n - 1] = __ldcg(d.U + n - 1);
-        if (threadIdx.x == 0) { finish_publish_stats(d, px, n, s_comb, s_arg); *d.finish_count = 0; }
+        if (threadIdx.x == 0) { finish_publish_stats(d, px, n, staged ? s_comb : nullptr, s_arg); *d.finish_count = 0; }
     }
 }
 
@@ -948,18 +1037,23 @@ cudaError_t launch_weights(const DeviceState &d, cudaStream_t s) {
     return launch_chain(k_weights, dim3(d.weight_blocks, d.batch), dim3(256), 0, s, d);
 }
 
+template <class R, bool FUSED> static void (*gradient_kernel(int groups))(DeviceState) {
+    return groups == 1 ? k_gradient<R, 1, FUSED> : (groups == 2 ? k_gradient<R, 2, FUSED> : k_gradient<R, 4, FUSED>);
+}
+
 cudaError_t launch_gradient(const DeviceState &d, int precision, cudaStream_t s, int *launches) {
     const int n = d.nu * d.T;
     const int nvec = n / (precision == 0 ? 2 : 4);
     int threads = std::min(512, ((nvec + 127) / 128) * 128), groups = 1;
     if (nvec <= 256 && d.k_count >= 4096) { groups = 512 / nvec >= 4 ? 4 : 2; threads = ((groups * nvec + 31) / 32) * 32; }   // short rows: several rows per block pass
-    const size_t smem = groups > 1 ? sizeof(double) * (size_t)(groups - 1) * n : 0;
+    const bool fused = d.fused_tail != 0;
+    const size_t smem = groups > 1 ? sizeof(double) * (size_t)(groups - (fused ? 0 : 1)) * n : 0;   // (fused: + the staging row of the channel-major rewrite)
     const dim3 grid(d.grad_blocks, d.batch);
     void (*kern)(DeviceState) = nullptr;
-    if (precision == 0) kern = groups == 1 ? k_gradient<double, 1> : (groups == 2 ? k_gradient<double, 2> : k_gradient<double, 4>);
-    else kern = groups == 1 ? k_gradient<float, 1> : (groups == 2 ? k_gradient<float, 2> : k_gradient<float, 4>);
+    if (precision == 0) kern = fused ? gradient_kernel<double, true>(groups) : gradient_kernel<double, false>(groups);
+    else kern = fused ? gradient_kernel<float, true>(groups) : gradient_kernel<float, false>(groups);
     cudaError_t e = launch_chain(kern, grid, dim3(threads), smem, s, d);
-    if (e != cudaSuccess) return e;
+    if (e != cudaSuccess || fused) { *launches += 1; return e; }
     *launches += 2;
     return launch_chain(k_gradient_reduce, dim3((n + 31) / 32, d.batch), dim3(1024), 0, s, d);
 }
@@ -967,11 +1061,12 @@ cudaError_t launch_gradient(const DeviceState &d, int precision, cudaStream_t s,
 cudaError_t launch_finish(const DeviceState &d, cudaStream_t s) {
     size_t smem = sizeof(double) * (2 * (size_t)d.T + 2 * (size_t)d.sg_len + 2 * (size_t)d.sg_window + 1);
     if (d.world > 1 && d.has_px) smem += sizeof(double) * (((size_t)d.T + 1) * (size_t)d.world + (size_t)d.world);   // combined + argmin slots + the peers' values of one channel
+    if (d.fused_tail) smem += sizeof(double) * (9 * (size_t)d.T + 1);   // combined + up to eight slices of the channel's partial sums
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    return launch_chain(k_finish, dim3(d.nu, d.batch), dim3((d.world > 1 && d.has_px) ? 256 : 64), smem, s, d);
+    return launch_chain(k_finish, dim3(d.nu, d.batch), dim3(((d.world > 1 && d.has_px) || d.fused_tail) ? 256 : 64), smem, s, d);
 }
 
 }  // namespace mppi_b200

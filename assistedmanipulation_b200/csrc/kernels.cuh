@@ -13,6 +13,7 @@ namespace mppi_b200 {
 constexpr int MAX_NU = 12;
 constexpr int MAX_WINDOW = 64;  // Savitzky–Golay half window supported by the finish kernel
 constexpr int MPPI_MAX_WORLD = 16;
+constexpr int MPPI_FUSED_ROWS = 512;   // rollouts per block of the weighted-sum kernel up to which it computes their weights itself (shared memory)
 
 // Per-update inputs, written by the host into pinned memory and copied to the device in ONE
 // transfer; kernels read it from global memory so a captured CUDA graph stays valid.
@@ -82,10 +83,13 @@ struct DeviceState {
     PeerExchange px;       // by value: the kernels read it from their parameter bank, not through a pointer chase
     int *rollout_done;     // blocks of the rollout grid that are done (the last one publishes / pushes the min-max payload)
     int *reduce_done;      // blocks of k_gradient_reduce that are done (the last one pushes the sums payload)
-    double *wsum_partial;  // per block of the weights kernel
-    double *grad_partial;  // [grad_blocks][nu*T]
+    double *wsum_partial;  // per block of the weights kernel (fused tail: per block of the weighted-sum kernel), wsum_stride per controller
+    double *grad_partial;  // [grad_blocks][nu*T]; fused tail: every row channel-major, [nu][T]
     int grad_blocks;
     int weight_blocks;
+    int wsum_stride;       // max(weight_blocks, grad_blocks)
+    int fused_tail;        // one rank, <= MPPI_FUSED_ROWS rollouts per weighted-sum block: the weights are computed by the weighted-sum kernel's
+                           // blocks (each for its own rollouts) and the partial sums are combined by k_finish - two kernels less per update
     double *gradient;      // normalised gradient (get_gradient())
     int *skip;             // 1 when max-min < 1e-6 (mppi.cpp:373-375): weights/gradient/U left untouched
     double *L;             // nu x nu column-major noise transform V*sqrt(Lambda) (gaussian.hpp:48-55)
@@ -128,7 +132,7 @@ __device__ __forceinline__ DeviceState controller_view(const DeviceState &g, int
     d.minmax_enc = g.minmax_enc + 2 * c; d.valid_count = g.valid_count + c; d.argmin = g.argmin + c; d.finish_count = g.finish_count + c;
     d.minmax = g.minmax + 4 * c; d.minmax_local = g.minmax_local + (size_t)c * (3 + MPPI_MAX_WORLD); d.sums = g.sums + c * (1 + n);
     d.rollout_done = g.rollout_done + c; d.reduce_done = g.reduce_done + c;
-    d.wsum_partial = g.wsum_partial + (size_t)c * g.weight_blocks; d.grad_partial = g.grad_partial + (size_t)c * g.grad_blocks * n;
+    d.wsum_partial = g.wsum_partial + (size_t)c * g.wsum_stride; d.grad_partial = g.grad_partial + (size_t)c * g.grad_blocks * n;
     d.skip = g.skip + c;
     d.sg_uu = g.sg_uu + (size_t)c * g.nu * g.sg_len; d.sg_tt = g.sg_tt + (size_t)c * g.nu * g.sg_len; d.sg_started = g.sg_started + c * g.nu;
     d.frame_snap = g.frame_snap + (size_t)c * g.frame_doubles;

@@ -28,5 +28,9 @@ for u in range(3):
     res["noise%d" % u] = e.read(abi.READ_NOISE, (K + 2) * T * 12)
     res["costs%d" % u] = e.read(abi.READ_COSTS, K + 2)
     res["U%d" % u] = e.read(abi.READ_OPTIMAL, 12 * T)
+    res["weights%d" % u] = e.read(abi.READ_WEIGHTS, K + 2)
+    res["gradient%d" % u] = e.read(abi.READ_GRADIENT, 12 * T)
+    res["minmax%d" % u] = e.read(abi.READ_MINMAX, 2)
+    res["argmin%d" % u] = np.array([e.query(abi.QUERY_ARGMIN)], dtype=np.float64)
 e.close()
 np.savez(out, **res)

@@ -64,6 +64,24 @@ def test_two_warp_rollout_kernel_is_bit_identical_with_the_one_warp_path(tmp_pat
         assert np.array_equal(split[k], one[k], equal_nan=True), k
 
 
+@pytest.mark.parametrize("precision", [abi.FP64, abi.FP32])
+@pytest.mark.parametrize("objective", ["trackpoint", "assisted"])
+def test_fused_tail_of_the_update_matches_the_separate_kernels(tmp_path, precision, objective):
+    """One rank with a small rollout set: the weighted-sum kernel computes the weights of its own rollouts and k_finish
+    combines the partial sums (k_misc.cu, FUSED). MPPI_B200_FUSED_TAIL=0 runs k_weights / k_gradient / k_gradient_reduce /
+    k_finish as separate kernels — what a sharded or a large rollout set always runs. Same costs, minimum and best rollout
+    bit for bit; the sums are taken in another (fixed) order, so the normalised weights, the gradient and the controls agree
+    to rounding — over updates with a kept set and a shift."""
+    fused = _alt_run(tmp_path, "fused", precision, {}, objective)
+    apart = _alt_run(tmp_path, "apart", precision, {"MPPI_B200_FUSED_TAIL": "0"}, objective)
+    for k in ("noise", "costs", "minmax", "argmin"):
+        assert np.array_equal(fused[k + "0"], apart[k + "0"], equal_nan=True), k
+    for u in range(3):   # (the rollouts of update u > 0 start from controls that differ in the last bits)
+        for k in ("weights", "gradient", "U"):
+            a, b = fused[k + str(u)], apart[k + str(u)]
+            assert np.abs(a - b).max() <= (1e-12 if u == 0 else 1e-8) * np.abs(b).max(), (k, u)
+
+
 @pytest.mark.parametrize("precision,c_tol,u_tol", [(abi.FP64, 1e-9, 1e-9), (abi.FP32, 1e-3, 2e-4)])
 def test_alternative_builds(tmp_path, precision, c_tol, u_tol):
     """The builds kept for A/B runs against the defaults (unrolled rollout kernel, k_sample_quads), each in its own
