@@ -317,6 +317,8 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     d.fused_tail = (fuse_tail > 0 && c->world_size == 1 && (fuse_tail > 1 || d.grad_blocks <= 160) && (d.k_count + d.grad_blocks - 1) / d.grad_blocks + 4 <= MPPI_FUSED_ROWS) ? 1 : 0;
     A(d.wsum_partial, (size_t)d.wsum_stride); A(d.grad_partial, (size_t)d.grad_blocks * n);
     A(d.gradient, n); A(d.skip, 1); A1(d.L, (size_t)nu * nu); A(d.optimal_cost, 1); A(d.breakdown, 8);
+    d.chase = 0;
+    A1(d.chase_prepared, 1);
     d.noise = dev_alloc<unsigned char>(e, e->noise_elems * esz); ok = ok && d.noise;
     d.injected = nullptr; d.injected_is_double = 0;
     d.sg_enabled = c->smoothing ? 1 : 0;
@@ -329,6 +331,18 @@ int mppi_b200_create(const mppi_b200_config *c, const void *objective_params, si
     // diagonal covariance: eps_i = sqrt(Sigma_ii) z_i (host_math.h); otherwise the kernels multiply by L
     d.L_is_diagonal = host_math::diagonal_noise_transform(nu, c->covariance, d.Ldiag) ? 1 : 0;
     CREATE_TRY(cudaMemcpy(d.L, L.data(), L.size() * sizeof(double), cudaMemcpyHostToDevice));
+    {   // Noise chase (rollout_core.cuh): the blocks of a rollout grid no larger than the machine draw their own noise on
+        // seven more warps each, and the rollouts start on the first steps' noise while the rest is being drawn. One
+        // controller, the column sampling path (diagonal covariance, 12 channels), the lean reach-to-pose kernel;
+        // MPPI_B200_CHASE=0 keeps the sampling kernel.
+        static const bool chase = !(std::getenv("MPPI_B200_CHASE") && std::getenv("MPPI_B200_CHASE")[0] == '0');
+        static const bool column_path = !(std::getenv("MPPI_B200_SAMPLE_TILE") && std::atoi(std::getenv("MPPI_B200_SAMPLE_TILE")) != 0);
+        if (chase && column_path && B == 1 && nu == 12 && d.L_is_diagonal) {
+            int eligible = 0;
+            CREATE_TRY(launch_rollout(d, c->precision, e->variant, e->faithful, e->params.data(), false, nullptr, &eligible));
+            d.chase = eligible;
+        }
+    }
     if (c->smoothing) {
         const std::vector<double> w = sg_weights(d.sg_window, (int)c->smoothing_order);
         CREATE_TRY(cudaMemcpy(d.sg_weights, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));

@@ -37,33 +37,8 @@ __device__ __forceinline__ double decode_ordered(unsigned long long e) {
     unsigned long long b = (e & 0x8000000000000000ull) ? (e & 0x7fffffffffffffffull) : ~e;
     return __longlong_as_double((long long)b);
 }
-cudaError_t launch_rollout_f64(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s);
-cudaError_t launch_rollout_f32(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s);
-
-// ---- prepare: time shift of the optimal control, rollout 1 = -U_prev, reset of the reductions -------
-// mppi.cpp:194-206 (shift), :269 (rollout[1].noise = -m_optimal_control, the UNSHIFTED optimum).
-// Runs as the extra last block of k_sample: nothing here is read by the sampling blocks (the two static rollouts
-// are produced by the sampling blocks themselves), so one launch and one dependency level less per update.
-__device__ __forceinline__ void prepare_block(const DeviceState &d) {
-    const int n = d.nu * d.T;
-    const long long shift = d.frame->shift_by;
-    for (int i = threadIdx.x; i < d.frame_doubles; i += blockDim.x) d.frame_snap[i] = reinterpret_cast<const double *>(d.frame)[i];
-    if (shift > 0) {
-        for (int e = threadIdx.x; e < n; e += blockDim.x) {
-            const int t = e / d.nu, dd = e - t * d.nu;
-            const long long shifted = d.T - shift;  // columns that survive
-            const int src_t = (t < shifted) ? (int)(t + shift) : d.T - 1;
-            d.U_shift[e] = d.U[src_t * d.nu + dd];
-        }
-    }
-    if (threadIdx.x == 0) {
-        d.minmax_enc[0] = 0xffffffffffffffffull;
-        d.minmax_enc[1] = 0ull;
-        *d.valid_count = 0;
-        *d.argmin = 0x7fffffffffffffffll;
-        *d.skip = 0;
-    }
-}
+cudaError_t launch_rollout_f64(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s, int *chase_query = nullptr);
+cudaError_t launch_rollout_f32(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s, int *chase_query = nullptr);
 
 // ---- warm start: the keep_best lowest-cost rollouts of the PREVIOUS update (stable order) -----------
 // mppi.cpp:222-253. One block; each round finds the smallest (cost, index) pair that is strictly
@@ -195,7 +170,7 @@ template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R *tile = reinterpret_cast<R *>(smem_raw);
     __shared__ double sL[MAX_NU * MAX_NU];
-    if (blockIdx.x == gridDim.x - 1) { prepare_block(d); return; }
+    if (blockIdx.x == gridDim.x - 1) { prepare_block(d, (int)threadIdx.x, (int)blockDim.x); return; }
     if (!d.L_is_diagonal) { for (int i = threadIdx.x; i < d.nu * d.nu; i += blockDim.x) sL[i] = d.L[i]; __syncthreads(); }
     const long long col0 = (long long)blockIdx.x * blockDim.x;
     const long long col = col0 + threadIdx.x;   // local column index
@@ -244,7 +219,7 @@ template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sa
 template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sample_quads(const __grid_constant__ DeviceState dg) {
     pdl_wait();
     const DeviceState d = controller_view(dg, blockIdx.y);
-    if (blockIdx.x == gridDim.x - 1) { prepare_block(d); return; }
+    if (blockIdx.x == gridDim.x - 1) { prepare_block(d, (int)threadIdx.x, (int)blockDim.x); return; }
     const long long quads = d.k_count * d.T * (NU / 4);
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= quads) return;
@@ -273,7 +248,7 @@ template <class R, class RI, int NU> __global__ void __launch_bounds__(256) k_sa
 template <class R, class RI, int NU> __global__ void __launch_bounds__(256, MPPI_SAMPLE_MIN_BLOCKS) k_sample_columns(const __grid_constant__ DeviceState dg) {
     pdl_wait();
     const DeviceState d = controller_view(dg, blockIdx.y);
-    if (blockIdx.x == gridDim.x - 1) { prepare_block(d); return; }
+    if (blockIdx.x == gridDim.x - 1) { prepare_block(d, (int)threadIdx.x, (int)blockDim.x); return; }
     const long long cols = d.k_count * d.T;
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= cols) return;
@@ -281,31 +256,7 @@ template <class R, class RI, int NU> __global__ void __launch_bounds__(256, MPPI
     column_coordinates(g, cols, d.T, &kl, &t);
     R v[NU];
     if (!sample_column<R, RI, NU>(d, dg.Ldiag, kl, t, v)) return;
-    R *dst = static_cast<R *>(d.noise) + (size_t)g * NU;   // 16-byte aligned: the buffer is, and NU % 4 == 0
-    // 32-byte stores (sm_100: STG.256) wherever the address allows: every store then fills whole 32-byte sectors. With
-    // 16-byte stores the column's sectors arrived in halves from different instructions and the write stream stalled
-    // at 3.5 TB/s whatever the instruction count.
-    if constexpr (sizeof(R) == 8 && NU % 4 == 0) {
-#pragma unroll
-        for (int i = 0; i < NU / 4; i++)   // NU * 8 bytes per column: a multiple of 32, so every column starts on a sector
-            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i), "d"((double)v[4 * i]), "d"((double)v[4 * i + 1]), "d"((double)v[4 * i + 2]), "d"((double)v[4 * i + 3]) : "memory");
-    } else if constexpr (sizeof(R) == 4 && NU == 12) {
-        // 48 bytes per column: even columns start on a sector (32 + 16), odd ones 16 bytes into one (16 + 32)
-        const float *f = reinterpret_cast<const float *>(v);
-        if ((g & 1) == 0) {
-            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]) : "memory");
-            *reinterpret_cast<float4 *>(dst + 8) = make_float4(f[8], f[9], f[10], f[11]);
-        } else {
-            *reinterpret_cast<float4 *>(dst) = make_float4(f[0], f[1], f[2], f[3]);
-            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 4), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]), "f"(f[8]), "f"(f[9]), "f"(f[10]), "f"(f[11]) : "memory");
-        }
-    } else if constexpr (sizeof(R) == 8) {
-#pragma unroll
-        for (int i = 0; i < NU / 2; i++) reinterpret_cast<double2 *>(dst)[i] = make_double2((double)v[2 * i], (double)v[2 * i + 1]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < NU / 4; i++) reinterpret_cast<float4 *>(dst)[i] = make_float4((float)v[4 * i], (float)v[4 * i + 1], (float)v[4 * i + 2], (float)v[4 * i + 3]);
-    }
+    store_column<R, NU>(static_cast<R *>(d.noise) + (size_t)g * NU, v, (g & 1) != 0);
 }
 
 // kept rollouts: one block per kept rollout (mppi.cpp:243-252); nothing happens when shift_by <= 0
@@ -937,6 +888,7 @@ template <class R, class RI, int NU> static cudaError_t sample_tt(const DeviceSt
         { cudaError_t e = launch_chain(k_shift_kept<R, RI, NU>, dim3((unsigned)d.keep_best, d.batch), dim3(64), row, s, d); if (e != cudaSuccess) return e; }
         ++*launches;
     }
+    if (d.chase) return cudaSuccess;   // the columns come from the sampling warps of the rollout blocks (sample_core.cuh: chase_sampler)
     const long long ncols = d.k_count * d.T;
     if constexpr (NU % 4 == 0) {
         // MPPI_B200_SAMPLE_TILE=1 keeps the general kernel, =2 the one-thread-per-Philox-block kernel (A/B measurements)
@@ -966,8 +918,8 @@ cudaError_t launch_sample(const DeviceState &d, int precision, cudaStream_t s, i
     return precision == 0 ? sample_t<double>(d, s, launches) : sample_t<float>(d, s, launches);
 }
 
-cudaError_t launch_rollout(const DeviceState &d, int precision, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s) {
-    return precision == 0 ? launch_rollout_f64(d, variant, faithful, params, optimal_only, s) : launch_rollout_f32(d, variant, faithful, params, optimal_only, s);
+cudaError_t launch_rollout(const DeviceState &d, int precision, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s, int *chase_query) {
+    return precision == 0 ? launch_rollout_f64(d, variant, faithful, params, optimal_only, s, chase_query) : launch_rollout_f32(d, variant, faithful, params, optimal_only, s, chase_query);
 }
 
 // ---- peer-memory exchange (kernels.cuh: PeerExchange) ---------------------------------------------------------

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <math_constants.h>
 #include "kernels.cuh"
+#include "sample_core.cuh"
 
 namespace mppi_b200 {
 
@@ -29,11 +30,11 @@ __device__ __forceinline__ double decode_ordered(unsigned long long e) {
 // Sharded rollout set (never batched): the LAST block of the rollout grid to get here publishes this rank's
 // {-min, max, 0, valid slots} exchange payload and, with the peer-memory exchange attached, stores it into the peers'
 // mailboxes — the first exchange of the update rides the rollout grid's tail instead of two launches of its own.
-__device__ __forceinline__ void rollout_grid_epilogue(const DeviceState &d, const Frame *frame) {
+__device__ __forceinline__ void rollout_grid_epilogue(const DeviceState &d, const Frame *frame, int rollout_blocks) {
     __shared__ int s_last;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(d.rollout_done, 1) == (int)gridDim.x - 1;
+    if (threadIdx.x == 0) s_last = atomicAdd(d.rollout_done, 1) == rollout_blocks - 1;
     __syncthreads();
     if (s_last) {
         __threadfence();
@@ -66,9 +67,12 @@ __device__ __forceinline__ void rollout_grid_epilogue(const DeviceState &d, cons
 #ifndef MPPI_LEAN_MIN_BLOCKS
 #define MPPI_LEAN_MIN_BLOCKS 1
 #endif
-template <class R, int VAR, bool FAITHFUL, class ParamsT, bool BIG = false>
-__global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG) ? MPPI_LEAN_MIN_BLOCKS : 1) k_rollout(const __grid_constant__ DeviceState d, const __grid_constant__ ParamsT P, int optimal_only) {
+template <class R, int VAR, bool FAITHFUL, class ParamsT, bool BIG = false, bool CHASE = false>
+__global__ void __launch_bounds__(CHASE ? 256 : 128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG) ? MPPI_LEAN_MIN_BLOCKS : 1) k_rollout(const __grid_constant__ DeviceState d, const __grid_constant__ ParamsT P, int optimal_only) {
     pdl_wait();
+    // CHASE = noise chase (rollout_core.cuh), its own instantiation of the kernel: warp 0 of the block integrates 32 rollouts,
+    // the block's other seven warps draw their noise
+    constexpr bool chase = CHASE;
     // blockIdx.y = controller of a batched engine. Only the handful of buffers this kernel touches are offset
     // by hand (a full controller_view copy of the state costs ~40 registers here, i.e. a resident warp per SM).
     const size_t c = blockIdx.y;
@@ -81,7 +85,17 @@ __global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG)
     R *sx = sW + 6 * d.T;                            // 32
     double *sDisc = reinterpret_cast<double *>(sx + 32);   // T discount factors std::pow(gamma, step) (mppi.cpp:326)
     const double *Usrc = d.U_shift + c * n;
-    for (int i = threadIdx.x; i < d.nu * d.T; i += blockDim.x) sU[i] = (R)Usrc[i];
+    if (chase && frame->shift_by > 0) {
+        // the prepare block (on the sampling warps of this grid's first block) is shifting the control sequence meanwhile: the same
+        // shift of the published sequence, read directly (mppi.cpp:194-206)
+        const long long shift = frame->shift_by, kept_steps = d.T - shift;
+        for (int i = threadIdx.x; i < d.nu * d.T; i += blockDim.x) {
+            const int t = i / d.nu, dd = i - t * d.nu;
+            sU[i] = (R)d.U[(size_t)((t < kept_steps) ? (int)(t + shift) : d.T - 1) * d.nu + dd];
+        }
+    } else {
+        for (int i = threadIdx.x; i < d.nu * d.T; i += blockDim.x) sU[i] = (R)Usrc[i];
+    }
     const int has_w = frame->has_wrench;
     for (int i = threadIdx.x; i < 6 * d.T; i += blockDim.x) sW[i] = has_w ? (R)wrench[i] : R(0);
     for (int i = threadIdx.x; i < 32; i += blockDim.x) sx[i] = (R)frame->x0[i];
@@ -92,11 +106,26 @@ __global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG)
     double *sU64 = sx64 + 32;
     if constexpr (STATE_PATH64) for (int i = threadIdx.x; i < d.nu * d.T; i += blockDim.x) sU64[i] = Usrc[i];
     for (int i = threadIdx.x; i < d.T; i += blockDim.x) sDisc[i] = discount_pow(d.discount, i);
+    if constexpr (CHASE) for (int i = threadIdx.x; i < (d.T + CHASE_STEPS - 1) / CHASE_STEPS; i += blockDim.x) s_chase_columns[i] = 0u;
     __syncthreads();
 
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // (noise chase: 32 rollouts per block whatever its size — the threads past warp 0 are the sampling threads)
+    const long long k = chase ? (long long)blockIdx.x * 32 + threadIdx.x : (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double cost = 0.0;
-    const bool active = optimal_only ? (k == 0) : (k < d.k_count);
+    const bool active = optimal_only ? (k == 0) : (k < d.k_count && !(chase && threadIdx.x >= 32));
+    if constexpr (CHASE) {
+        if (chase && threadIdx.x >= 32) {
+            const int j = (int)threadIdx.x - 32, ns = (int)blockDim.x - 32;
+            if (blockIdx.x == 0) {
+                // the update's prepare block first (it is short), flagged for the min / max atomics at the end of every block
+                // (on the last sampling warp alone, so that this block's first chunk is not held up, it measured 1.6 us SLOWER)
+                prepare_block(d, j, ns);
+                asm volatile("bar.sync 1, %0;" ::"r"(ns) : "memory");
+                if (j == 0) { __threadfence(); asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(d.chase_prepared), "r"((unsigned)(frame->attempt + 1ull)) : "memory"); }
+            }
+            chase_sampler<R, NJ>(d, d.Ldiag, (long long)blockIdx.x * 32, j, ns);
+        }
+    }
     if (active) {
         // the optimal re-rollout (Trajectory::filter, mppi.cpp:450-479) reads a row of zeros shared by all controllers
         const R *eps = static_cast<const R *>(d.noise) + (optimal_only ? (size_t)0 : (c * (size_t)d.k_count + (size_t)k) * n);
@@ -107,7 +136,7 @@ __global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG)
             in.x0 = sx; in.x0_64 = sx64; in.U = sU; in.W = has_w ? sW : nullptr; in.T = d.T; in.dt = (R)d.dt; in.dt64 = d.dt; in.discount = d.discount; in.discount_table = sDisc;
             if constexpr (STATE_PATH64) in.U64 = sU64;
             double bd[7] = {0, 0, 0, 0, 0, 0, 0};
-            cost = rollout_franka<R, VAR, FAITHFUL, ParamsT, BIG>(MPPI_DEVICE_MODEL, MPPI_DEVICE_FAST_MODEL, P, in, eps, optimal_only ? bd : nullptr, MPPI_DEVICE_FAST_MODEL64);
+            cost = rollout_franka<R, VAR, FAITHFUL, ParamsT, BIG, CHASE>(MPPI_DEVICE_MODEL, MPPI_DEVICE_FAST_MODEL, P, in, eps, optimal_only ? bd : nullptr, MPPI_DEVICE_FAST_MODEL64);
             if (optimal_only && active) {
                 for (int i = 0; i < 7; i++) d.breakdown[8 * c + i] = bd[i];
                 d.breakdown[8 * c + 7] = cost;
@@ -116,6 +145,17 @@ __global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG)
         if (active) { if (optimal_only) d.optimal_cost[c] = cost; else d.costs[c * (size_t)d.k_count + k] = cost; }
     }
     if (optimal_only) return;
+    if constexpr (CHASE) {
+        if (chase) {   // the prepare block has reset the running min / max (long ago)
+            const unsigned target = (unsigned)(frame->attempt + 1ull);
+            unsigned seen;
+            for (unsigned spins = 0;; spins++) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(d.chase_prepared) : "memory");
+                if (seen == target) break;
+                if (spins > (1u << 22)) __trap();
+            }
+        }
+    }
 
     // block min / max over the non-NaN costs
     const bool valid = active && !(cost != cost);
@@ -133,7 +173,7 @@ __global__ void __launch_bounds__(128, (VAR == VAR_TP_LEAN && !FAITHFUL && !BIG)
         atomicMax(&d.minmax_enc[2 * c + 1], encode_ordered(mx));
         atomicAdd(d.valid_count + c, cnt);
     }
-    if (d.world > 1) rollout_grid_epilogue(d, frame);
+    if (d.world > 1) rollout_grid_epilogue(d, frame, (int)gridDim.x);
 }
 
 // ---- K2 for the FP32 fast mode of the objectives with kinematics (assisted manipulation, full reach-to-pose) ----------
@@ -308,13 +348,16 @@ __global__ void __launch_bounds__(64, 1) k_rollout_split(const __grid_constant__
             atomicAdd(d.valid_count + c, cnt);
         }
     }
-    if (d.world > 1) rollout_grid_epilogue(d, frame);
+    if (d.world > 1) rollout_grid_epilogue(d, frame, (int)gridDim.x);
 }
 #endif
 
 template <class R, int VAR, bool FAITHFUL, class ParamsT>
-cudaError_t launch_rollout_t(const DeviceState &d, const void *params, bool optimal_only, cudaStream_t s) {
+cudaError_t launch_rollout_t(const DeviceState &d, const void *params, bool optimal_only, cudaStream_t s, int *chase_query) {
     const ParamsT &P = *static_cast<const ParamsT *>(params);
+    // chase_query: no launch — whether the rollout blocks of a launch for this state would draw their own noise (engine creation)
+    constexpr bool CAN_CHASE = VAR == VAR_TP_LEAN && !FAITHFUL;
+    if (chase_query) { *chase_query = 0; if (!CAN_CHASE) return cudaSuccess; }
     // few rollouts: one warp per block spreads them over the SMs; many: 128-thread blocks
     int block = d.k_count <= 148 * 64 ? 32 : (d.k_count <= 148 * 256 ? 64 : 128);
     // the kernels with the 75 KB step body are bound by instruction fetch, which the warps of an SM share: 128-thread
@@ -359,25 +402,45 @@ cudaError_t launch_rollout_t(const DeviceState &d, const void *params, bool opti
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
+    if constexpr (CAN_CHASE) {
+        // Noise chase: a grid of one-warp blocks no larger than the machine — its blocks land one to an SM, which is otherwise
+        // empty — gets seven sampling warps per block (256 threads x 255 registers: the SM's whole register file)
+        if (chase_query) {
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const bool unrolled = kern == k_rollout<R, VAR, FAITHFUL, ParamsT, true>;   // (not the loop-body build of MPPI_B200_BIG_FROM)
+            *chase_query = (unrolled && d.batch == 1 && block == 32 && grid <= sms && d.T <= CHASE_STEPS * CHASE_MAX_CHUNKS) ? 1 : 0;
+            return cudaSuccess;
+        }
+        if (!optimal_only && d.chase) {
+            auto ckern = k_rollout<R, VAR, FAITHFUL, ParamsT, true, true>;   // (the unrolled build)
+            if (smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(ckern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+            }
+            return launch_level(2, ckern, dim3((unsigned)grid, 1), dim3(256), smem, s, d, P, 0);
+        }
+    }
     return launch_level(rollout_overlap_level((long long)grid * d.batch), kern, dim3((unsigned)grid, d.batch), dim3(block), smem, s, d, P, optimal_only ? 1 : 0);
 }
 
-template <class R> cudaError_t launch_rollout_r(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s) {
+template <class R> cudaError_t launch_rollout_r(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s, int *chase_query) {
     switch (variant) {
-        case VAR_TOY: return launch_rollout_t<R, VAR_TOY, false, ToyP<R>>(d, params, optimal_only, s);
-        case VAR_TP_LEAN: return faithful ? launch_rollout_t<R, VAR_TP_LEAN, true, TrackPointP<R>>(d, params, optimal_only, s)
-                                          : launch_rollout_t<R, VAR_TP_LEAN, false, TrackPointP<R>>(d, params, optimal_only, s);
-        case VAR_TP_FULL: return faithful ? launch_rollout_t<R, VAR_TP_FULL, true, TrackPointP<R>>(d, params, optimal_only, s)
-                                          : launch_rollout_t<R, VAR_TP_FULL, false, TrackPointP<R>>(d, params, optimal_only, s);
-        case VAR_AM: return faithful ? launch_rollout_t<R, VAR_AM, true, AssistedP<R>>(d, params, optimal_only, s)
-                                     : launch_rollout_t<R, VAR_AM, false, AssistedP<R>>(d, params, optimal_only, s);
-        case VAR_AM_ENERGY: return faithful ? launch_rollout_t<R, VAR_AM_ENERGY, true, AssistedP<R>>(d, params, optimal_only, s)
-                                            : launch_rollout_t<R, VAR_AM_ENERGY, false, AssistedP<R>>(d, params, optimal_only, s);
+        case VAR_TOY: return launch_rollout_t<R, VAR_TOY, false, ToyP<R>>(d, params, optimal_only, s, chase_query);
+        case VAR_TP_LEAN: return faithful ? launch_rollout_t<R, VAR_TP_LEAN, true, TrackPointP<R>>(d, params, optimal_only, s, chase_query)
+                                          : launch_rollout_t<R, VAR_TP_LEAN, false, TrackPointP<R>>(d, params, optimal_only, s, chase_query);
+        case VAR_TP_FULL: return faithful ? launch_rollout_t<R, VAR_TP_FULL, true, TrackPointP<R>>(d, params, optimal_only, s, chase_query)
+                                          : launch_rollout_t<R, VAR_TP_FULL, false, TrackPointP<R>>(d, params, optimal_only, s, chase_query);
+        case VAR_AM: return faithful ? launch_rollout_t<R, VAR_AM, true, AssistedP<R>>(d, params, optimal_only, s, chase_query)
+                                     : launch_rollout_t<R, VAR_AM, false, AssistedP<R>>(d, params, optimal_only, s, chase_query);
+        case VAR_AM_ENERGY: return faithful ? launch_rollout_t<R, VAR_AM_ENERGY, true, AssistedP<R>>(d, params, optimal_only, s, chase_query)
+                                            : launch_rollout_t<R, VAR_AM_ENERGY, false, AssistedP<R>>(d, params, optimal_only, s, chase_query);
     }
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_rollout_f64(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s);
-cudaError_t launch_rollout_f32(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s);
+cudaError_t launch_rollout_f64(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s, int *chase_query = nullptr);
+cudaError_t launch_rollout_f32(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s, int *chase_query = nullptr);
 
 }  // namespace mppi_b200

@@ -22,7 +22,7 @@ cudaError_t upload_robot_model_f32() {
     const FastModel<double> fd = make_fast_model<double>();
     return cudaMemcpyToSymbol(c_fast_f32_state, &fd, sizeof fd);
 }
-cudaError_t launch_rollout_f32(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s) {
-    return launch_rollout_r<float>(d, variant, faithful, params, optimal_only, s);
+cudaError_t launch_rollout_f32(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s, int *chase_query) {
+    return launch_rollout_r<float>(d, variant, faithful, params, optimal_only, s, chase_query);
 }
 }  // namespace mppi_b200

@@ -17,7 +17,7 @@ cudaError_t upload_robot_model_f64() {
     const FastModel<double> f = make_fast_model<double>();
     return cudaMemcpyToSymbol(c_fast_f64, &f, sizeof f);
 }
-cudaError_t launch_rollout_f64(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s) {
-    return launch_rollout_r<double>(d, variant, faithful, params, optimal_only, s);
+cudaError_t launch_rollout_f64(const DeviceState &d, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s, int *chase_query) {
+    return launch_rollout_r<double>(d, variant, faithful, params, optimal_only, s, chase_query);
 }
 }  // namespace mppi_b200

@@ -90,6 +90,9 @@ struct DeviceState {
     int wsum_stride;       // max(weight_blocks, grad_blocks)
     int fused_tail;        // one rank, <= MPPI_FUSED_ROWS rollouts per weighted-sum block: the weights are computed by the weighted-sum kernel's
                            // blocks (each for its own rollouts) and the partial sums are combined by k_finish - two kernels less per update
+    // noise chase (rollout_core.cuh / sample_core.cuh): the blocks of a small rollout grid draw their own noise
+    int chase;             // 0 = the sampling kernel runs on its own
+    unsigned *chase_prepared;   // the update number (low word) of the last prepare block run by the rollout grid's first block
     double *gradient;      // normalised gradient (get_gradient())
     int *skip;             // 1 when max-min < 1e-6 (mppi.cpp:373-375): weights/gradient/U left untouched
     double *L;             // nu x nu column-major noise transform V*sqrt(Lambda) (gaussian.hpp:48-55)
@@ -252,9 +255,9 @@ cudaError_t upload_robot_model();  // once per device
 
 cudaError_t launch_select_kept(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_merge_kept(const DeviceState &d, cudaStream_t s);
-cudaError_t launch_sample(const DeviceState &d, int precision, cudaStream_t s, int *launches);
+cudaError_t launch_sample(const DeviceState &d, int precision, cudaStream_t s, int *launches);   // (d.chase: the warm-start shift only)
 // objective params: pointer to the host-side block in kernel arithmetic (ToyP/TrackPointP/AssistedP<R>)
-cudaError_t launch_rollout(const DeviceState &d, int precision, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s);
+cudaError_t launch_rollout(const DeviceState &d, int precision, int variant, bool faithful, const void *params, bool optimal_only, cudaStream_t s, int *chase_query = nullptr);
 cudaError_t launch_weights(const DeviceState &d, cudaStream_t s);
 cudaError_t launch_gradient(const DeviceState &d, int precision, cudaStream_t s, int *launches);
 cudaError_t launch_finish(const DeviceState &d, cudaStream_t s);

@@ -337,21 +337,52 @@ template <class R> MPPI_HD R assisted_cost(const AssistedP<R> &P, const R *q, co
     return cost;
 }
 
-// one step of a rollout's noise row: 12 values, 16-byte aligned (rows are multiples of 16 bytes)
-MPPI_HD void load_eps(const double *p, double *o) {
+// ---- noise chase (small rollout sets; k_rollout.cuh) ---------------------------------------------------------------------
+// When the rollout grid leaves most of every SM empty (K = 4096: one warp per SM), the sampling kernel's work moves INTO the
+// rollout blocks: seven more warps per block draw the noise of the block's own 32 rollouts, chunk by chunk of CHASE_STEPS
+// steps, while warp 0 integrates — the rollout starts ~1 us after the launch instead of behind a 10 us sampling kernel, and
+// nothing crosses a block. A chunk is complete when the block's shared-memory counter of its columns reaches
+// CHASE_COLUMNS; the rollout warp looks at the counter in front of its first load of the chunk. In a launch without
+// sampling warps the counters are preset, so the wait needs no test of its own.
+constexpr int CHASE_STEPS = 4;
+constexpr int CHASE_COLUMNS = 32 * CHASE_STEPS;   // columns of one chunk: 32 rollouts x CHASE_STEPS steps
+constexpr int CHASE_MAX_CHUNKS = 256;             // horizons up to 1024 steps
+#if defined(__CUDACC__)
+__shared__ unsigned s_chase_columns[CHASE_MAX_CHUNKS];   // written by the kernel before its first barrier
+// GUARD: give up (trap) after ~1 s — for the wait in front of the step loop. The waits inside the loop are as few
+// instructions as possible (the unrolled FP64 step body is 31.1 KB of a 32 KB instruction cache level: 50 more instructions
+// in it cost 8 % of the kernel); once chunk 0 has arrived the sampling warps are running, and they wait for nothing.
+template <bool GUARD> __device__ __forceinline__ void noise_chase_wait(int chunk) {
+    const unsigned address = (unsigned)__cvta_generic_to_shared(s_chase_columns + chunk);
+    unsigned seen;
+    for (unsigned spins = 0;; spins++) {
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(address) : "memory");
+        if (seen == (unsigned)CHASE_COLUMNS) break;
+        if (GUARD && spins > (1u << 24)) __trap();
+    }
+}
+// the values must be in registers here (keeps the compiler from sinking their computation below the loads that follow,
+// which would cost a copy of the previous noise column per step)
+__device__ __forceinline__ void pin_values(double *v) { asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]), "+d"(v[5]), "+d"(v[6]), "+d"(v[7]), "+d"(v[8]), "+d"(v[9]), "+d"(v[10]), "+d"(v[11])); }
+__device__ __forceinline__ void pin_values(float *v) { asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11])); }
+#endif
+
+// one step of a rollout's noise row: 12 values, 16-byte aligned (rows are multiples of 16 bytes). COHERENT: ordinary loads —
+// the kernels whose blocks may draw the noise themselves (above) read rows written by another warp during the launch.
+template <bool COHERENT = false> MPPI_HD void load_eps(const double *p, double *o) {
 #if defined(__CUDA_ARCH__)
     const double2 *v = reinterpret_cast<const double2 *>(p);
 #pragma unroll
-    for (int i = 0; i < 6; i++) { const double2 t = __ldg(v + i); o[2 * i] = t.x; o[2 * i + 1] = t.y; }
+    for (int i = 0; i < 6; i++) { const double2 t = COHERENT ? v[i] : __ldg(v + i); o[2 * i] = t.x; o[2 * i + 1] = t.y; }
 #else
     for (int i = 0; i < 12; i++) o[i] = p[i];
 #endif
 }
-MPPI_HD void load_eps(const float *p, float *o) {
+template <bool COHERENT = false> MPPI_HD void load_eps(const float *p, float *o) {
 #if defined(__CUDA_ARCH__)
     const float4 *v = reinterpret_cast<const float4 *>(p);
 #pragma unroll
-    for (int i = 0; i < 3; i++) { const float4 t = __ldg(v + i); o[4 * i] = t.x; o[4 * i + 1] = t.y; o[4 * i + 2] = t.z; o[4 * i + 3] = t.w; }
+    for (int i = 0; i < 3; i++) { const float4 t = COHERENT ? v[i] : __ldg(v + i); o[4 * i] = t.x; o[4 * i + 1] = t.y; o[4 * i + 2] = t.z; o[4 * i + 3] = t.w; }
 #else
     for (int i = 0; i < 12; i++) o[i] = p[i];
 #endif
@@ -377,7 +408,7 @@ template <class R> struct RolloutInputs {
 // eps: this rollout's noise, [t][d]. Returns the rollout cost (NaN = failed rollout, mppi.cpp:331-334).
 // BIG: the build for rollout sets that fill the machine (see k_rollout.cuh)
 // F64: the solver's model in FP64 (FP32 fast mode of the objectives with barrier steps: see MIXED_SOLVER below); null otherwise
-template <class R, int VAR, bool FAITHFUL, class ParamsT, bool BIG = false>
+template <class R, int VAR, bool FAITHFUL, class ParamsT, bool BIG = false, bool CHASE = false>   // CHASE: see "noise chase" above
 MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, const ParamsT &P, const RolloutInputs<R> &in, const R *eps, double *bd, const FastModel<double> *F64 = nullptr) {
     constexpr int KF = VariantTraits<VAR>::kin;
     constexpr bool POWER = VariantTraits<VAR>::power;
@@ -427,7 +458,10 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
     }
     double total = 0.0;
     R e_next[NJ];
-    load_eps(eps, e_next);
+#if defined(__CUDA_ARCH__)
+    if constexpr (CHASE) noise_chase_wait<true>(0);
+#endif
+    load_eps<CHASE>(eps, e_next);
     for (int step = 0; step < in.T; ++step) {
         R u[NJ];
         double u64[MIXED_SOLVER ? NJ : 1];
@@ -438,7 +472,10 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
 #pragma unroll
             for (int d = 0; d < NJ; d++) u[d] = in.U[step * NJ + d] + e_next[d];
         }
-        if (step + 1 < in.T) load_eps(eps + (step + 1) * NJ, e_next);  // next step's noise is in flight during this step
+#if defined(__CUDA_ARCH__)
+        if constexpr (CHASE) pin_values(u);
+#endif
+        if (step + 1 < in.T) load_eps<CHASE>(eps + (step + 1) * NJ, e_next);  // next step's noise is in flight during this step
         R c;
         R yaw[2] = {cs[2], sn[2]};
         const R *yawp = FAITHFUL ? nullptr : yaw;
@@ -545,6 +582,11 @@ MPPI_HD double rollout_franka(const RobotModel<R> &M, const FastModel<R> &F, con
 #pragma unroll
             for (int i = 2; i < 10; i++) { cs[i] = (R)cs64[i]; sn[i] = (R)sn64[i]; }
         } else if constexpr (!FAITHFUL && (!LEAN || BIG)) joint_sincos<R>(F, q, cs, sn);
+#if defined(__CUDA_ARCH__)
+        // the next iteration loads the noise of step + 2: its chunk is awaited HERE, at the loop's latch, where the step's
+        // straight-line code ends anyway (a wait in front of the load split the step's basic block: +4 % kernel time)
+        if constexpr (CHASE) { if ((step + 2) % CHASE_STEPS == 0 && step + 2 < in.T) noise_chase_wait<false>((step + 2) / CHASE_STEPS); }
+#endif
     }
     return total;
 }

@@ -161,4 +161,87 @@ template <int NU> MPPI_HD void quad_coordinates(long long g, long long quads, in
     }
 }
 
+
+#if defined(__CUDACC__)
+// One column's NU values to the noise buffer. 32-byte stores (sm_100: STG.256) wherever the address allows: every store
+// then fills whole 32-byte sectors. With 16-byte stores the column's sectors arrived in halves from different
+// instructions and the write stream stalled at 3.5 TB/s whatever the instruction count. `odd`: parity of the column's
+// index in the buffer (FP32 columns are 48 bytes: even ones start on a sector, odd ones 16 bytes into one).
+template <class R, int NU> __device__ __forceinline__ void store_column(R *dst, const R *v, bool odd) {
+    if constexpr (sizeof(R) == 8 && NU % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < NU / 4; i++)   // NU * 8 bytes per column: a multiple of 32, so every column starts on a sector
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i), "d"((double)v[4 * i]), "d"((double)v[4 * i + 1]), "d"((double)v[4 * i + 2]), "d"((double)v[4 * i + 3]) : "memory");
+    } else if constexpr (sizeof(R) == 4 && NU == 12) {
+        const float *f = reinterpret_cast<const float *>(v);
+        if (!odd) {
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]) : "memory");
+            *reinterpret_cast<float4 *>(dst + 8) = make_float4(f[8], f[9], f[10], f[11]);
+        } else {
+            *reinterpret_cast<float4 *>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 4), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]), "f"(f[8]), "f"(f[9]), "f"(f[10]), "f"(f[11]) : "memory");
+        }
+    } else if constexpr (sizeof(R) == 8) {
+#pragma unroll
+        for (int i = 0; i < NU / 2; i++) reinterpret_cast<double2 *>(dst)[i] = make_double2((double)v[2 * i], (double)v[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NU / 4; i++) reinterpret_cast<float4 *>(dst)[i] = make_float4((float)v[4 * i], (float)v[4 * i + 1], (float)v[4 * i + 2], (float)v[4 * i + 3]);
+    }
+}
+
+// ---- prepare: time shift of the optimal control, rollout 1 = -U_prev, reset of the reductions -------
+// mppi.cpp:194-206 (shift), :269 (rollout[1].noise = -m_optimal_control, the UNSHIFTED optimum).
+// Runs as the extra last block of k_sample: nothing here is read by the sampling blocks (the two static rollouts
+// are produced by the sampling blocks themselves), so one launch and one dependency level less per update — or, with the
+// noise chase, on the sampling warps of the rollout grid's first block (threads tid of nthreads).
+__device__ __forceinline__ void prepare_block(const DeviceState &d, int tid, int nthreads) {
+    const int n = d.nu * d.T;
+    const long long shift = d.frame->shift_by;
+    for (int i = tid; i < d.frame_doubles; i += nthreads) d.frame_snap[i] = reinterpret_cast<const double *>(d.frame)[i];
+    if (shift > 0) {
+        for (int e = tid; e < n; e += nthreads) {
+            const int t = e / d.nu, dd = e - t * d.nu;
+            const long long shifted = d.T - shift;  // columns that survive
+            const int src_t = (t < shifted) ? (int)(t + shift) : d.T - 1;
+            d.U_shift[e] = d.U[src_t * d.nu + dd];
+        }
+    }
+    if (tid == 0) {
+        d.minmax_enc[0] = 0xffffffffffffffffull;
+        d.minmax_enc[1] = 0ull;
+        *d.valid_count = 0;
+        *d.argmin = 0x7fffffffffffffffll;
+        *d.skip = 0;
+    }
+}
+
+
+// ---- sampling warps of a rollout block (noise chase, rollout_core.cuh) ------------------------------------------------
+// Thread j of the `ns` sampling threads of the block that integrates rollouts [first, first + 32). The block's columns are
+// enumerated chunk-major — chunk c = steps [c CHASE_STEPS, (c+1) CHASE_STEPS) of the 32 rollouts, CHASE_COLUMNS columns — and
+// thread j takes columns j, j + ns, ...: the first chunks are complete after one column time. Every column, drawn or not
+// (kept rollout, past the end of the set or of the horizon), is counted in its chunk's shared-memory counter after a
+// block-scope fence; the rollout warp waits for CHASE_COLUMNS (noise_chase_wait). Same counters, same arithmetic as
+// k_sample_columns: identical noise.
+template <class R, int NU> __device__ __forceinline__ void chase_sampler(const DeviceState &d, const double *ldiag, long long first, int j, int ns) {
+    const int chunks = (d.T + CHASE_STEPS - 1) / CHASE_STEPS;
+    for (int i = j; i < chunks * CHASE_COLUMNS; i += ns) {
+        const int c = i / CHASE_COLUMNS, within = i - c * CHASE_COLUMNS;
+        const long long kl = first + within / CHASE_STEPS;
+        const int t = c * CHASE_STEPS + within % CHASE_STEPS;
+        if (kl < d.k_count && t < d.T) {
+            R v[NU];
+            const bool fresh = d.injected_is_double ? sample_column<R, double, NU>(d, ldiag, kl, t, v) : sample_column<R, R, NU>(d, ldiag, kl, t, v);
+            if (fresh) {
+                const long long col = kl * d.T + t;
+                store_column<R, NU>(static_cast<R *>(d.noise) + (size_t)col * NU, v, (col & 1) != 0);
+            }
+        }
+        __threadfence_block();
+        atomicAdd(s_chase_columns + c, 1u);
+    }
+}
+#endif
+
 }  // namespace mppi_b200

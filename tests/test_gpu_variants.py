@@ -82,6 +82,18 @@ def test_fused_tail_of_the_update_matches_the_separate_kernels(tmp_path, precisi
             assert np.abs(a - b).max() <= (1e-12 if u == 0 else 1e-8) * np.abs(b).max(), (k, u)
 
 
+@pytest.mark.parametrize("precision", [abi.FP64, abi.FP32])
+def test_rollout_blocks_that_draw_their_own_noise_are_bit_identical_with_the_sampling_kernel(tmp_path, precision):
+    """Small rollout sets of the reach-to-pose controller (a grid of one-warp blocks no larger than the machine): seven more
+    warps per rollout block draw the block's noise chunk by chunk while warp 0 integrates (rollout_core.cuh "noise chase");
+    MPPI_B200_CHASE=0 runs k_sample_columns ahead of the rollout kernel as for every other configuration. Same counters,
+    same arithmetic, same order of every sum: all buffers are bit-identical over updates with a kept set and a time shift."""
+    chase = _alt_run(tmp_path, "chase", precision, {})
+    apart = _alt_run(tmp_path, "sampling_kernel", precision, {"MPPI_B200_CHASE": "0"})
+    for k in chase.files:
+        assert np.array_equal(chase[k], apart[k], equal_nan=True), k
+
+
 @pytest.mark.parametrize("precision,c_tol,u_tol", [(abi.FP64, 1e-9, 1e-9), (abi.FP32, 1e-3, 2e-4)])
 def test_alternative_builds(tmp_path, precision, c_tol, u_tol):
     """The builds kept for A/B runs against the defaults (unrolled rollout kernel, k_sample_quads), each in its own

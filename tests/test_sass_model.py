@@ -24,7 +24,7 @@ def _model(obj, pattern, *extra):
 
 
 def test_config2_kernel_stays_near_its_fp64_issue_floor():
-    (instr, fp64, cycles, floor), out = _model("k_rollout_f64.o", "Li1ELb0ENS_11TrackPointPIdEELb0EEE")
+    (instr, fp64, cycles, floor), out = _model("k_rollout_f64.o", "Li1ELb0ENS_11TrackPointPIdEELb0ELb0EEE")
     assert floor == 2 * fp64
     assert 2000 <= fp64 <= 2200, out          # 2585 before the round's second half, 2173 before the joint offsets' structural zeros
     assert instr <= 3100 and cycles <= 5800, out   # 3668 instructions / 7597 cycles before; 5250 with the guarded slow path counted; this loop-body build only runs behind MPPI_B200_BIG_FROM (A/B), its schedule moves by ~100 cycles with unrelated edits
@@ -33,8 +33,8 @@ def test_config2_kernel_stays_near_its_fp64_issue_floor():
 
 
 def test_unrolled_and_assisted_kernels_keep_their_instruction_counts():
-    (instr, fp64, _, _), out = _model("k_rollout_f64.o", "Li1ELb0ENS_11TrackPointPIdEELb1EEE")
+    (instr, fp64, _, _), out = _model("k_rollout_f64.o", "Li1ELb0ENS_11TrackPointPIdEELb1ELb0EEE")
     assert instr <= 2100 and fp64 <= 1650, out     # 3120 / 2515 at first, 2445 / 1956 before the joint offsets' structural zeros
     # config 3 / 5 kernel: FP32 kinematics / RNEA / objective around the FP64 state path (solver, sines, integration) since round 2
-    (instr, fp64, cycles, _), out = _model("k_rollout_f32.o", "IfLi4ELb0ENS_9AssistedPIfEELb0EEE")
+    (instr, fp64, cycles, _), out = _model("k_rollout_f32.o", "IfLi4ELb0ENS_9AssistedPIfEELb0ELb0EEE")
     assert instr <= 5400 and 1300 <= fp64 <= 1600 and cycles <= 9200, out   # all FP32: 8832 instructions at first, 4705 at the end of round 1; 5238 (1456 FP64) with the FP64 state path

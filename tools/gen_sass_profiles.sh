@@ -13,19 +13,19 @@ echo "# Calibration on B200: cfg2 kernel of r1_cfg2_final.ncu-rep models 7597 cy
 echo "# FP64 kernels: the range-reduction slow path of the shared sines / cosines (robot_fast.cuh:$FOLD, behind a forward branch taken only for |angle| >= 2^31) is left out (--skip)."
 echo
 echo "## lean reach-to-pose kernel, FP64, unrolled build — configs 2 and 4 (default for every rollout count)   [start: 3120 instructions, 2515 FP64; 2445 / 1956 / 5083 cycles before the joint placements' structural zeros]"
-python $T $O/k_rollout_f64.o 'Li1ELb0ENS_11TrackPointPIdEELb1EEE' --lines 12 $SK
+python $T $O/k_rollout_f64.o 'Li1ELb0ENS_11TrackPointPIdEELb1ELb0EEE' --lines 12 $SK
 echo
 echo "## same, loop-body build (MPPI_B200_BIG_FROM; config 2 ran it when the round's GPU numbers were taken)   [start: 3668 instructions, 2585 FP64, 7597 cycles; 2918 / 2173 / 5140 before the structural zeros]"
-python $T $O/k_rollout_f64.o 'Li1ELb0ENS_11TrackPointPIdEELb0EEE' --lines 12 $SK
+python $T $O/k_rollout_f64.o 'Li1ELb0ENS_11TrackPointPIdEELb0ELb0EEE' --lines 12 $SK
 echo
 echo "## config 3 / 5 kernel (FP32 assisted manipulation + energy tank)   [start: 8832 instructions, 18154 cycles; 5895 / 7629 before the self-collision pairs became one basic block; 5646 / 6773 with the solver's arm joints as a loop]"
-python $T $O/k_rollout_f32.o 'IfLi4ELb0ENS_9AssistedPIfEELb0EEE' --lines 12
+python $T $O/k_rollout_f32.o 'IfLi4ELb0ENS_9AssistedPIfEELb0ELb0EEE' --lines 12
 echo
 echo "## lean reach-to-pose kernel in FP32, unrolled build (default)"
-python $T $O/k_rollout_f32.o 'IfLi1ELb0ENS_11TrackPointPIfEELb1EEE' --fp64-issue 1
+python $T $O/k_rollout_f32.o 'IfLi1ELb0ENS_11TrackPointPIfEELb1ELb0EEE' --fp64-issue 1
 echo
 echo "## same, loop-body build"
-python $T $O/k_rollout_f32.o 'IfLi1ELb0ENS_11TrackPointPIfEELb0EEE' --fp64-issue 1
+python $T $O/k_rollout_f32.o 'IfLi1ELb0ENS_11TrackPointPIfEELb0ELb0EEE' --fp64-issue 1
 } > profiles/${R}_sass_model.txt
 {
 echo "# Call-site attribution of one rollout step (tools/sass_cycles.py --phases rollout_core.cuh): instructions and stall cycles per call made by"
