@@ -196,7 +196,17 @@ struct SplitSlot {          // one step's state of 32 rollouts, lane fastest: ev
     float cs[8][32], sn[8][32];   // joints 2..9
     float u[10][32];              // the control applied at this step (channels 10, 11 — the gripper — are ignored by the dynamics)
 };
-__device__ __forceinline__ void split_arrive(int id) { __threadfence_block(); asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+// (no fence in front of bar.arrive: the barrier orders the thread's earlier shared-memory accesses for its participants — PTX's
+// own producer / consumer pattern — while a block-scope fence also waits for the state warp's noise loads in flight)
+#ifndef MPPI_SPLIT_FENCE
+#define MPPI_SPLIT_FENCE 0
+#endif
+__device__ __forceinline__ void split_arrive(int id) {
+#if MPPI_SPLIT_FENCE
+    __threadfence_block();
+#endif
+    asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
+}
 __device__ __forceinline__ void split_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 #if defined(MPPI_ROLLOUT_F32)
