@@ -162,6 +162,13 @@ template <int NU> MPPI_HD void quad_coordinates(long long g, long long quads, in
 }
 
 
+// Column i of a rollout block's chunk-major enumeration (noise chase, rollout_core.cuh): chunk c = steps [c CHASE_STEPS,
+// (c + 1) CHASE_STEPS) of the block's 32 rollouts; within a chunk consecutive columns are consecutive steps of one rollout.
+MPPI_HD void chase_column_coordinates(int i, int *chunk, int *rollout, int *t) {
+    const int c = i / CHASE_COLUMNS, within = i - c * CHASE_COLUMNS;
+    *chunk = c; *rollout = within / CHASE_STEPS; *t = c * CHASE_STEPS + within % CHASE_STEPS;
+}
+
 #if defined(__CUDACC__)
 // One column's NU values to the noise buffer. 32-byte stores (sm_100: STG.256) wherever the address allows: every store
 // then fills whole 32-byte sectors. With 16-byte stores the column's sectors arrived in halves from different
@@ -227,9 +234,9 @@ __device__ __forceinline__ void prepare_block(const DeviceState &d, int tid, int
 template <class R, int NU> __device__ __forceinline__ void chase_sampler(const DeviceState &d, const double *ldiag, long long first, int j, int ns) {
     const int chunks = (d.T + CHASE_STEPS - 1) / CHASE_STEPS;
     for (int i = j; i < chunks * CHASE_COLUMNS; i += ns) {
-        const int c = i / CHASE_COLUMNS, within = i - c * CHASE_COLUMNS;
-        const long long kl = first + within / CHASE_STEPS;
-        const int t = c * CHASE_STEPS + within % CHASE_STEPS;
+        int c, r, t;
+        chase_column_coordinates(i, &c, &r, &t);
+        const long long kl = first + r;
         if (kl < d.k_count && t < d.T) {
             R v[NU];
             const bool fresh = d.injected_is_double ? sample_column<R, double, NU>(d, ldiag, kl, t, v) : sample_column<R, R, NU>(d, ldiag, kl, t, v);

@@ -89,6 +89,10 @@ void host_quad_coordinates(long long g, long long quads, int T, long long *kl, i
 void host_sg_weights(int m, int n, double *out) { const auto w = host_math::sg_weights(m, n); for (size_t i = 0; i < w.size(); i++) out[i] = w[i]; }
 void host_noise_transform(int n, const double *cov, double *L) { const auto l = host_math::noise_transform(n, cov); for (size_t i = 0; i < l.size(); i++) L[i] = l[i]; }
 int host_diagonal_noise_transform(int n, const double *cov, double *ldiag) { return host_math::diagonal_noise_transform(n, cov, ldiag) ? 1 : 0; }
+// the chunk-major column enumeration of a rollout block that draws its own noise, and its constants
+void host_chase_coordinates(int i, int *chunk, int *rollout, int *t) { chase_column_coordinates(i, chunk, rollout, t); }
+int host_chase_steps() { return CHASE_STEPS; }
+int host_chase_columns() { return CHASE_COLUMNS; }
 void host_philox(const unsigned *ctr4, const unsigned *key2, unsigned *out4) {
     const uint4 r = philox4x32_10(make_uint4(ctr4[0], ctr4[1], ctr4[2], ctr4[3]), make_uint2(key2[0], key2[1]));
     out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;

@@ -85,3 +85,29 @@ def test_cpp_facade_compiles_and_refuses_without_gpu(tmp_path):
         pytest.skip("a CUDA device is present")
     r = subprocess.run([exe, "toy", "16", "0.2", "1", "-", str(tmp_path / "o.bin")], capture_output=True, text=True)
     assert r.returncode == 3 and "no CPU fallback" in r.stderr  # Trajectory::create returned nullptr with a reason
+
+
+def test_python_host_side_keeps_pointers_of_reused_buffers_only():
+    """engine.py _host_pointer: the ctypes pointer of a state / wrench array is built once per array OBJECT (the caller
+    refills it in place); arrays that need a conversion are converted — and their copy kept alive — on every call; a
+    new object in the same argument slot replaces the cached one. No device needed: the method touches no library."""
+    import numpy as np
+    from assistedmanipulation_b200 import engine
+    e = engine.Engine.__new__(engine.Engine)
+    e._pointers, e._converted = {}, {}
+    a = np.arange(4.0)
+    p = e._host_pointer("state", a)
+    assert C.addressof(p.contents) == a.ctypes.data and e._host_pointer("state", a) is p      # cached by identity
+    a[1] = 7.0
+    assert e._host_pointer("state", a)[1] == 7.0                                               # the same memory, refilled in place
+    b = np.arange(4.0) + 10
+    q = e._host_pointer("state", b)
+    assert C.addressof(q.contents) == b.ctypes.data and e._pointers["state"][0] is b          # a new object replaces the entry
+    strided = np.arange(8.0)[::2]
+    r = e._host_pointer("state", strided)
+    assert [r[i] for i in range(4)] == [0.0, 2.0, 4.0, 6.0] and "state" not in e._pointers     # converted, not cached ...
+    strided[1] = -1.0
+    assert e._host_pointer("state", strided)[1] == -1.0                                        # ... so a change is seen by the next call
+    assert e._host_pointer("wrench", None) is None
+    w32 = np.ones((3, 6), dtype=np.float32)
+    assert e._host_pointer("wrench", w32)[17] == 1.0 and "wrench" not in e._pointers and e._converted["wrench"].dtype == np.float64

@@ -33,6 +33,7 @@ def sc():
     lib.host_sample_columns.argtypes = lib.host_sample_quads.argtypes
     lib.host_quad_coordinates.argtypes = [C.c_longlong, C.c_longlong, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.host_philox.argtypes = [C.c_void_p] * 3
+    lib.host_chase_coordinates.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     return lib
 
 
@@ -180,3 +181,32 @@ def test_noise_transform_is_the_reference_factor(sc):
     assert sc.host_diagonal_noise_transform(12, S.ctypes.data, ld.ctypes.data) == 1
     assert np.array_equal(ld, np.sqrt(d))                          # ... the engine samples with the plain one
     assert np.array_equal(np.sort(np.linalg.norm(L, axis=0)), np.sort(ld))
+
+
+@pytest.mark.parametrize("T", [1, 3, 4, 64, 130])
+def test_chunk_major_enumeration_of_a_block_that_draws_its_own_noise(sc, T):
+    """sample_core.cuh chase_sampler: sampling thread j of ns takes columns j, j + ns, ... of the block's chunk-major
+    enumeration and adds one to the chunk's counter per column; the rollout warp starts a chunk when its counter reaches
+    CHASE_COLUMNS. Every (rollout of the block, step) must be produced exactly once, every chunk must collect exactly
+    CHASE_COLUMNS contributions (columns past the horizon count without being drawn), the chunks must complete in order of
+    time, and the first chunk must be among the first columns handed out (one column time after the launch)."""
+    steps, columns = sc.host_chase_steps(), sc.host_chase_columns()
+    assert columns == 32 * steps
+    chunks, ns = (T + steps - 1) // steps, 6 * 32
+    seen, per_chunk, last_chunk = set(), [0] * chunks, -1
+    c, r, t = C.c_int(), C.c_int(), C.c_int()
+    for j in range(ns):
+        for i in range(j, chunks * columns, ns):
+            sc.host_chase_coordinates(i, C.byref(c), C.byref(r), C.byref(t))
+            assert 0 <= r.value < 32 and c.value == t.value // steps == i // columns
+            per_chunk[c.value] += 1
+            if t.value < T:
+                assert (r.value, t.value) not in seen
+                seen.add((r.value, t.value))
+    assert seen == {(r, t) for r in range(32) for t in range(T)}
+    assert per_chunk == [columns] * chunks
+    for i in range(chunks * columns):   # chunk-major: a chunk's columns are contiguous, so the first pass of the threads completes chunk 0
+        sc.host_chase_coordinates(i, C.byref(c), C.byref(r), C.byref(t))
+        assert c.value >= last_chunk
+        last_chunk = c.value
+    assert columns <= ns   # chunk 0 = the first `columns` indices, one per sampling thread
