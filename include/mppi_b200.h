@@ -258,7 +258,9 @@ int mppi_b200_read(mppi_b200_engine *engine, int32_t what, void *dst, size_t byt
 #define MPPI_B200_QUERY_BATCH 10
 int mppi_b200_query(mppi_b200_engine *engine, int32_t what, int64_t *value);
 
-/* time of the kernels of the last update on the device, seconds (CUDA events on the engine stream) */
+/* time of the kernels of the last update on the device, seconds (CUDA events on the engine stream). mppi_b200_update returns
+ * when the update's results have landed in host memory, which is a few microseconds before the stream's end-of-update event:
+ * this call waits for that event first. */
 int mppi_b200_last_update_device_seconds(mppi_b200_engine *engine, double *seconds);
 
 /* Per-stage device time of the last update (CUDA events between the stages; off by default because
