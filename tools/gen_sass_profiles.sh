@@ -15,6 +15,9 @@ echo
 echo "## lean reach-to-pose kernel, FP64, unrolled build — configs 2 and 4 (default for every rollout count)   [start: 3120 instructions, 2515 FP64; 2445 / 1956 / 5083 cycles before the joint placements' structural zeros]"
 python $T $O/k_rollout_f64.o 'Li1ELb0ENS_11TrackPointPIdEELb1ELb0EEE' --lines 12 $SK
 echo
+echo "## the same kernel with the sampling warps of the noise chase (config 2 and every other small reach-to-pose rollout set; the 5-instruction inner loop is the chunk wait at the latch, modelled with 7 trips where it normally takes one)"
+python $T $O/k_rollout_f64.o 'Li1ELb0ENS_11TrackPointPIdEELb1ELb1EEE' --lines 6 $SK
+echo
 echo "## same, loop-body build (MPPI_B200_BIG_FROM; config 2 ran it when the round's GPU numbers were taken)   [start: 3668 instructions, 2585 FP64, 7597 cycles; 2918 / 2173 / 5140 before the structural zeros]"
 python $T $O/k_rollout_f64.o 'Li1ELb0ENS_11TrackPointPIdEELb0ELb0EEE' --lines 12 $SK
 echo
@@ -32,12 +35,12 @@ echo "# Call-site attribution of one rollout step (tools/sass_cycles.py --phases
 echo "# rollout_franka, through the inline chains of the SASS line table (nvdisasm -gi). Static, no GPU; kernels as committed."
 echo
 echo "## lean reach-to-pose kernel, FP64, unrolled build (configs 2 and 4)"
-python $T $O/k_rollout_f64.o 'k_rolloutIdLi1ELb0ENS_11TrackPointPIdEELb1' --phases rollout_core.cuh --phase-depth 1 $SK
+python $T $O/k_rollout_f64.o 'k_rolloutIdLi1ELb0ENS_11TrackPointPIdEELb1ELb0' --phases rollout_core.cuh --phase-depth 1 $SK
 echo
 echo "## same, loop-body build"
-python $T $O/k_rollout_f64.o 'k_rolloutIdLi1ELb0ENS_11TrackPointPIdEELb0' --phases rollout_core.cuh --phase-depth 1 $SK
+python $T $O/k_rollout_f64.o 'k_rolloutIdLi1ELb0ENS_11TrackPointPIdEELb0ELb0' --phases rollout_core.cuh --phase-depth 1 $SK
 echo
 echo "## config 3 / 5 kernel (FP32 assisted manipulation + energy tank)"
-python $T $O/k_rollout_f32.o 'k_rolloutIfLi4ELb0ENS_9AssistedPIfEELb0' --phases rollout_core.cuh --phase-depth 2 --fp64-issue 1 | grep -v "robot_fast.cuh"
+python $T $O/k_rollout_f32.o 'k_rolloutIfLi4ELb0ENS_9AssistedPIfEELb0ELb0' --phases rollout_core.cuh --phase-depth 2 --fp64-issue 1 | grep -v "robot_fast.cuh"
 } > profiles/${R}_sass_phases.txt
 grep -H "per step" profiles/${R}_sass_model.txt
